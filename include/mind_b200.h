@@ -1,0 +1,128 @@
+/*
+ * mind_b200.h -- C ABI of libmind_b200.so, the B200-native (sm_100a) implementation of
+ * MIND's scenario-prediction hot path.
+ *
+ * The reference (HKUST-Aerial-Robotics/MIND) is pure Python and has no FFI of its own; the
+ * boundary it does have is the string-imported network class
+ *     net_cfg["network"] = "module:Class"      planners/mind/configs/networks/net_cfg.py:10
+ * resolved in MINDPlanner.init_network           planners/mind/planner.py:42-49
+ * and the two calls the tree generator makes on it
+ *     network.pre_process(data); network(data_in)  planners/mind/scenario_tree.py:69-71
+ * The Python class mind_b200.predictor:ScenePredNetB200 mirrors that surface and calls the
+ * entry points below through ctypes (binding shown in INTEGRATION.md).  Every entry point
+ * cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Device pointers are owned by
+ * the caller; the library owns its packed weights and small descriptor tables.  All work is
+ * enqueued asynchronously on the caller's stream; no hidden synchronisation in mind_forward /
+ * mind_tree_* .  Every function returns 0 on success, non-zero on error with a message
+ * available from mind_last_error().  There is no CPU fallback: without a CUDA device
+ * mind_create fails.
+ */
+#ifndef MIND_B200_H
+#define MIND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct MindCtx MindCtx;
+
+/* Network hyper-parameters are those of planners/mind/configs/networks/net_cfg.py:4-25
+ * (fixed: 14 actor channels x 48 steps, 10 nodes x 16 lane channels, d=128, 6 fusion layers,
+ * 8 heads, 6 modes, 60 predicted steps, Bezier order 7). */
+#define MIND_D 128
+#define MIND_ACTOR_C 14
+#define MIND_ACTOR_T 48
+#define MIND_LANE_NODES 10
+#define MIND_LANE_C 16
+#define MIND_MODES 6
+#define MIND_PRED 60
+#define MIND_RPE_C 5
+
+/* precision modes of the N^2 contractions in the rela-fusion layers */
+#define MIND_PREC_FP32 0 /* exact fp32 SIMT path: validation comparator, bit-stable ordering */
+#define MIND_PREC_F16TC 1 /* tcgen05 kind::f16 operands, fp32 accumulate, fp16 edge stream */
+
+/* ---- life cycle:  ScenePredNet(cfg, device)            planners/mind/planner.py:45 ---- */
+int mind_create(MindCtx** out, int device);
+void mind_destroy(MindCtx* ctx);
+const char* mind_last_error(void);
+/* library / build info string (arch, git-free) */
+const char* mind_build_info(void);
+
+/* ---- weights:  net.load_state_dict(ckpt["state_dict"])  planners/mind/planner.py:46-47 ----
+ * Called once per state_dict entry with the reference's own key (328 keys) and a HOST fp32
+ * pointer; mind_finalize_weights uploads and repacks (split of proj_memory 384 -> 3x128,
+ * fused q/S/T projection, fp16 copies for the tensor-core path, transposed conv filters).
+ * Two extra keys carry the Bezier bases the reference builds in __init__
+ * (planners/mind/networks/network.py:449-464): "__bezier_T" [60*8], "__bezier_Tp" [60*7]. */
+int mind_set_weight(MindCtx* ctx, const char* key, const float* host, int64_t numel);
+int mind_finalize_weights(MindCtx* ctx);
+
+/* options: "precision" (MIND_PREC_*), "chunk_scenes" (exact path workspace bound) */
+int mind_set_option(MindCtx* ctx, const char* name, int64_t value);
+
+/* ---- one batched forward:  network(data_in)   planners/mind/networks/network.py:582-595 ----
+ * Ragged batch of n_scenes scenes.  actor_off / lane_off are HOST prefix arrays [n_scenes+1].
+ * Either rpe (HOST array of n_scenes DEVICE pointers, each [5, M_b, M_b] fp32, the 'scene'
+ * entry of data['RPE'], planners/mind/utils.py:193-212) or ctrs+vecs (device [sum M_b, 2]
+ * anchors; the library then evaluates get_rpe itself) must be given; M_b = Na_b + Nl_b.  */
+typedef struct {
+    int32_t n_scenes;
+    const int32_t* actor_off; /* host [n_scenes+1] */
+    const int32_t* lane_off;  /* host [n_scenes+1] */
+    const float* actors;      /* dev [sumNa, 14, 48]   ACTORS    */
+    const float* lanes;       /* dev [sumNl, 10, 16]   LANES     */
+    const float* const* rpe;  /* host [n_scenes] of dev ptrs, or NULL */
+    const float* ctrs;        /* dev [sumM, 2] or NULL (actors of scene b first, then lanes) */
+    const float* vecs;        /* dev [sumM, 2] or NULL */
+    const float* tgt_nodes;   /* dev [n_scenes, 10, 16] TGT_NODES */
+    const float* tgt_rpe;     /* dev [n_scenes, 20]     TGT_RPE   */
+} MindBatch;
+
+/* Output layouts are the reference's (network.py:545-554), scenes concatenated along actors:
+ *   cls [n_scenes, 6]            softmax mode probabilities (res_cls[b] = cls[b:b+1])
+ *   reg [sumNa, 6, 60, 5]        x, y (actor-local), exp(cov) x3   (res_reg[b] = rows of b)
+ *   vel [sumNa, 6, 60, 2]        res_aux[b][0]
+ *   cov_vel [sumNa, 6, 60, 3]    res_aux[b][1]   (may be NULL)
+ *   param [sumNa, 6, 8, 5]       res_aux[b][2] permuted to actor-major (may be NULL)      */
+typedef struct {
+    float* cls;
+    float* reg;
+    float* vel;
+    float* cov_vel;
+    float* param;
+} MindOutputs;
+
+/* bytes of caller-provided device workspace mind_forward needs for this batch shape */
+int64_t mind_workspace_bytes(MindCtx* ctx, int32_t n_scenes, int32_t sum_actors, int32_t sum_lanes,
+                             int32_t max_tokens /* max_b (Na_b+Nl_b+1) */);
+
+int mind_forward(MindCtx* ctx, const MindBatch* batch, const MindOutputs* out, void* workspace,
+                 int64_t workspace_bytes, void* cuda_stream);
+
+/* debug taps used by the stage-level parity tests: copy an internal stage buffer of the LAST
+ * forward (still in the workspace) to a device buffer.  names: "actor_feat" [sumNa,128],
+ * "lane_feat" [sumNl+B,128] (tgt polylines last), "actors_fused" [sumNa,128],
+ * "cls_tok" [B,128].  Returns the number of floats written or <0. */
+int64_t mind_debug_tap(MindCtx* ctx, const char* name, float* dst, int64_t capacity, void* cuda_stream);
+
+/* bring-up self test of the TMA + tcgen05 + TMEM plumbing: D[0:128*128] = A . W^T (fp16 operands,
+ * fp32 accumulate) and D[128*128: 2*128*128] = the A tile read back through the software
+ * swizzle.  All three are HOST buffers (A, W: 128*128 floats; D: 2*128*128 floats). */
+int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host);
+
+/* cudaDeviceSynchronize + kernel-side protocol error flag (0 = clean) */
+int mind_sync_check(MindCtx* ctx);
+
+/* number of kernels the library launched since creation (bench.py's gpu_launches) */
+int64_t mind_launch_count(MindCtx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIND_B200_H */

@@ -1,0 +1,783 @@
+// Fused rela-fusion layer for sm_100a: TMA-staged edge tiles, tcgen05.mma (kind::f16, fp32
+// accumulators in TMEM) for the four N^2 contractions, warp-level LayerNorm / online softmax
+// epilogues straight out of TMEM.  Reference semantics: RelaFusionLayer._build_memory and
+// _mha_block, planners/mind/networks/network.py:182-226.
+//
+// Work decomposition: one work item = (scene b, 16 queries j0..j0+15); the CTA walks the keys in
+// chunks of 8, so a tile is 8 keys x 16 queries = 128 pair rows = the 128 TMEM lanes.
+//   G1:  D1[128x128]  = edge_tile(fp16) . W_e^T                      (+S[j]+T[i], LN, ReLU -> memory)
+//   G2:  Dpe|Dk|Dv    = memory(fp16)   . [W_pe ; W_k ; W_v]^T
+//   edge' = LN(edge + ReLU(LN(Dpe + b)))  written back in place (fp16) by TMA
+//   per-thread online softmax over the keys a thread sees, merged across the 8 key slots at the
+//   end of the work item.  `memory`, K and V never touch HBM.
+#include "fusion_tc.h"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace mind {
+
+namespace tc {
+
+constexpr int kThreads = 256;
+constexpr float kEps = 1e-5f;
+
+// ---- shared memory map (bytes, relative to a 1024-aligned base) ----
+constexpr uint32_t SM_W = 0;                          // [2 kblock][512 rows][128 B]  = 131072
+constexpr uint32_t SM_TILE0 = 131072;                 // [2 kblock][128 rows][128 B]  = 32768
+constexpr uint32_t SM_TILE1 = SM_TILE0 + 32768;
+constexpr uint32_t SM_S = SM_TILE1 + 32768;           // float [16][132]
+constexpr uint32_t SM_Q = SM_S + 16 * 132 * 4;        // float [16][132]
+constexpr uint32_t SM_T = SM_Q + 16 * 132 * 4;        // float [8][132]
+constexpr uint32_t SM_P = SM_T + 8 * 132 * 4;         // float [8][128] layer params
+constexpr uint32_t SM_STAT = SM_P + 8 * 128 * 4;      // float2 [2 buf][2 half][128]
+constexpr uint32_t SM_BAR = SM_STAT + 2 * 2 * 128 * 8;
+constexpr uint32_t SM_TMEM = SM_BAR + 64;
+constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
+constexpr uint32_t SMEM_BYTES = SM_TOTAL + 1024;      // slack for manual 1024 B alignment
+static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+// param rows
+enum { P_MEM_G = 0, P_MEM_B, P_BPE, P_PE_G, P_PE_B, P_NE_G, P_NE_B, P_BV };
+
+// error codes written to *err before trapping
+enum { E_LOAD_W = 1, E_LOAD_EDGE = 2, E_MMA1 = 3, E_MMA2 = 4 };
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// bounded wait: a protocol bug becomes a trapped launch (error code in *err), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// tcgen05 shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B,
+// 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD_X32(taddr, r)                                                                                      \
+    asm volatile(                                                                                                  \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                  \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"  \
+        "%28,%29,%30,%31}, [%32];"                                                                                 \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),         \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),   \
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])  \
+        : "r"(taddr)                                                                                               \
+        : "memory")
+#define TMEM_LD_X16(taddr, r)                                                                                    \
+    asm volatile(                                                                                                \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
+        : "r"(taddr)                                                                                             \
+        : "memory")
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows x 128 B] block that
+// uses the 128-byte swizzle (chunk index XOR row%8), block base 1024-aligned
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused layer kernel
+// ---------------------------------------------------------------------------------------------
+struct LayerArgs {
+    const TcWork* work;
+    int n_work;
+    const float* stq;     // [B*Nmax, 384]
+    const float* params;  // [8][128]
+    float* attn;          // [B*Nmax, 128]
+    int Nmax;
+    int has_edge;
+    int* err;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));   // generic pointer to the aligned base
+    float* sS = reinterpret_cast<float*>(sgen + SM_S);
+    float* sQ = reinterpret_cast<float*>(sgen + SM_Q);
+    float* sT = reinterpret_cast<float*>(sgen + SM_T);
+    float* sP = reinterpret_cast<float*>(sgen + SM_P);
+    float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);
+    volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
+    const uint32_t bar_w = sbase + SM_BAR, bar_load = bar_w + 8, bar_m1 = bar_w + 16, bar_m2 = bar_w + 24;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = warp >> 2;                  // column half: channels [64*half, 64*half+64)
+    const int row = (warp & 3) * 32 + lane;      // TMEM lane = pair row inside the tile
+    const int i_l = row >> 4, j_l = row & 15;
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1); mbar_init(bar_load, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_TMEM), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 8 * 128; i += kThreads) sP[i] = a.params[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sTmem;
+
+    // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, 131072u);
+        for (int kb = 0; kb < 2; ++kb)
+            for (int m = 0; m < 4; ++m) tma_load_2d(sbase + SM_W + kb * 65536 + m * 16384, &wmap, bar_w, kb * 64, m * 128);
+    }
+    mbar_wait(bar_w, 0, a.err, E_LOAD_W);
+
+    uint32_t par = 0;       // phase parity of bar_load / bar_m1 / bar_m2 (each completes once per tile)
+    int cur = 0;            // tile buffer holding the current edge tile; the other one receives `memory`
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t col0 = (uint32_t)half * 64;
+    const float* Pm = sP;
+
+    for (int wi = blockIdx.x; wi < a.n_work; wi += gridDim.x) {
+        const TcWork wk = a.work[wi];
+        const int N = wk.n, j0 = wk.j0, b = wk.b;
+        const int n_chunks = (N + 7) >> 3;
+        const int64_t tok0 = (int64_t)b * a.Nmax;
+        if (tid == 0) {   // first edge tile of the work item
+            mbar_expect_tx(bar_load, 32768u);
+            tma_load_4d(sbase + SM_TILE0 + cur * 32768, &emap, bar_load, 0, j0, 0, b);
+            tma_load_4d(sbase + SM_TILE0 + cur * 32768 + 16384, &emap, bar_load, 64, j0, 0, b);
+        }
+        // S (src term, per query j) and q tiles
+        for (int idx = tid; idx < 16 * 32; idx += kThreads) {
+            const int jj = idx >> 5, c4 = idx & 31;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+            if (j0 + jj < N) {
+                const float* p = a.stq + (tok0 + j0 + jj) * 384;
+                s = reinterpret_cast<const float4*>(p)[c4];
+                q = reinterpret_cast<const float4*>(p + 256)[c4];
+            }
+            *reinterpret_cast<float4*>(sS + jj * 132 + c4 * 4) = s;
+            *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = q;
+        }
+        float acc[64], mrun[4], lrun[4];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { mrun[h] = -INFINITY; lrun[h] = 0.f; }
+
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int i0 = ch * 8;
+            const uint32_t tX = sbase + SM_TILE0 + cur * 32768;          // edge tile (in place -> edge')
+            const uint32_t tY = sbase + SM_TILE0 + (cur ^ 1) * 32768;    // memory tile, then prefetch target
+            {   // T (target term, per key i) tile
+                const int ii = tid >> 5, c4 = tid & 31;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i0 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + ii) * 384 + 128)[c4];
+                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = t;
+            }
+            mbar_wait(bar_load, par, a.err, E_LOAD_EDGE);      // every thread observes the TMA completion
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id128 = umma_idesc_f16(128);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
+                    const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+                    umma_f16(tmem + 0, umma_desc_sw128(tX + ko), umma_desc_sw128(sbase + SM_W + kw), id128, kk > 0);
+                }
+                umma_commit(bar_m1);
+            }
+            __syncthreads();                                   // B0: sT / sS / sQ visible
+            mbar_wait(bar_m1, par, a.err, E_MMA1);
+            tc_fence_after();
+
+            // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 A operand of G2 ----
+            float v[64];
+            {
+                uint32_t r[32];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    TMEM_LD_X32(tmem + lane_base + col0 + p * 32, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const int c = (int)col0 + p * 32 + k4 * 4;
+                        const float4 s = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
+                        const float4 t = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
+                        const float x0 = __uint_as_float(r[k4 * 4 + 0]) + s.x + t.x;
+                        const float x1 = __uint_as_float(r[k4 * 4 + 1]) + s.y + t.y;
+                        const float x2 = __uint_as_float(r[k4 * 4 + 2]) + s.z + t.z;
+                        const float x3 = __uint_as_float(r[k4 * 4 + 3]) + s.w + t.w;
+                        v[p * 32 + k4 * 4 + 0] = x0; v[p * 32 + k4 * 4 + 1] = x1;
+                        v[p * 32 + k4 * 4 + 2] = x2; v[p * 32 + k4 * 4 + 3] = x3;
+                        s1 += (x0 + x1) + (x2 + x3);
+                        s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                    }
+                }
+                sStat[(0 * 2 + half) * 128 + row] = make_float2(s1, s2);
+            }
+            if (tid == 0) tma_wait_read0();                    // previous edge' store has left tY
+            tc_fence_before();
+            __syncthreads();                                   // B1
+            {
+                const float2 o = sStat[(0 * 2 + (half ^ 1)) * 128 + row];
+                const float2 m = sStat[(0 * 2 + half) * 128 + row];
+                const float mean = (o.x + m.x) * (1.f / 128.f);
+                const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + kEps);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float y[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = (int)col0 + c8 * 8 + e;
+                        y[e] = fmaxf((v[c8 * 8 + e] - mean) * rstd * Pm[P_MEM_G * 128 + c] + Pm[P_MEM_B * 128 + c], 0.f);
+                    }
+                    uint4 u;
+                    u.x = pack_h2(y[0], y[1]); u.y = pack_h2(y[2], y[3]); u.z = pack_h2(y[4], y[5]); u.w = pack_h2(y[6], y[7]);
+                    st_shared_v4(tY + half * 16384 + sw128(row, c8), u);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();                                   // B2: memory tile complete
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id128 = umma_idesc_f16(128), id256 = umma_idesc_f16(256);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
+                    const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+                    const uint64_t ad = umma_desc_sw128(tY + ko);
+                    if (a.has_edge) umma_f16(tmem + 128, ad, umma_desc_sw128(sbase + SM_W + kw + 128 * 128), id128, kk > 0);
+                    umma_f16(tmem + 256, ad, umma_desc_sw128(sbase + SM_W + kw + 256 * 128), id256, kk > 0);
+                }
+                umma_commit(bar_m2);
+            }
+            mbar_wait(bar_m2, par, a.err, E_MMA2);
+            tc_fence_after();
+            if (tid == 0 && ch + 1 < n_chunks) {               // prefetch next edge tile into tY (free now)
+                mbar_expect_tx(bar_load, 32768u);
+                tma_load_4d(tY, &emap, bar_load, 0, j0, i0 + 8, b);
+                tma_load_4d(tY + 16384, &emap, bar_load, 64, j0, i0 + 8, b);
+            }
+
+            // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
+            if (a.has_edge) {
+                uint32_t r[32];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    TMEM_LD_X32(tmem + lane_base + 128 + col0 + p * 32, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float x = __uint_as_float(r[k]) + Pm[P_BPE * 128 + (int)col0 + p * 32 + k];
+                        v[p * 32 + k] = x;
+                        s1 += x;
+                        s2 += x * x;
+                    }
+                }
+                sStat[(1 * 2 + half) * 128 + row] = make_float2(s1, s2);
+                __syncthreads();                               // B3
+                {
+                    const float2 o = sStat[(1 * 2 + (half ^ 1)) * 128 + row];
+                    const float2 m = sStat[(1 * 2 + half) * 128 + row];
+                    const float mean = (o.x + m.x) * (1.f / 128.f);
+                    const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
+                    const float rstd = rsqrtf(var + kEps);
+                    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        const uint4 eu = ld_shared_v4(tX + half * 16384 + sw128(row, c8));
+                        const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
+                        const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = (int)col0 + c8 * 8 + e;
+                            const float u = fmaxf((v[c8 * 8 + e] - mean) * rstd * Pm[P_PE_G * 128 + c] + Pm[P_PE_B * 128 + c], 0.f);
+                            const float x = ev[e] + u;
+                            v[c8 * 8 + e] = x;
+                            s1 += x;
+                            s2 += x * x;
+                        }
+                    }
+                }
+                sStat[(0 * 2 + half) * 128 + row] = make_float2(s1, s2);
+                __syncthreads();                               // B4
+                {
+                    const float2 o = sStat[(0 * 2 + (half ^ 1)) * 128 + row];
+                    const float2 m = sStat[(0 * 2 + half) * 128 + row];
+                    const float mean = (o.x + m.x) * (1.f / 128.f);
+                    const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
+                    const float rstd = rsqrtf(var + kEps);
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float y[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = (int)col0 + c8 * 8 + e;
+                            y[e] = (v[c8 * 8 + e] - mean) * rstd * Pm[P_NE_G * 128 + c] + Pm[P_NE_B * 128 + c];
+                        }
+                        uint4 u;
+                        u.x = pack_h2(y[0], y[1]); u.y = pack_h2(y[2], y[3]); u.z = pack_h2(y[4], y[5]); u.w = pack_h2(y[6], y[7]);
+                        st_shared_v4(tX + half * 16384 + sw128(row, c8), u);
+                    }
+                }
+            }
+
+            // ---- epilogue 2b: per-thread online softmax over this thread's key (i0 + i_l) ----
+            {
+                const bool key_ok = (i0 + i_l < N);            // padded keys never enter the softmax
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    uint32_t rk[16], rv[16];
+                    TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
+                    TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
+                    tmem_wait_ld();
+                    if (!key_ok) continue;
+                    float s = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 q = *reinterpret_cast<const float4*>(sQ + j_l * 132 + (int)col0 + h * 16 + k4 * 4);
+                        s = fmaf(q.x, __uint_as_float(rk[k4 * 4 + 0]), s);
+                        s = fmaf(q.y, __uint_as_float(rk[k4 * 4 + 1]), s);
+                        s = fmaf(q.z, __uint_as_float(rk[k4 * 4 + 2]), s);
+                        s = fmaf(q.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                    }
+                    const float mnew = fmaxf(mrun[h], s);
+                    const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
+                    const float p = __expf(s - mnew);
+                    lrun[h] = lrun[h] * corr + p;
+                    mrun[h] = mnew;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[h * 16 + k] = fmaf(p, __uint_as_float(rv[k]), acc[h * 16 + k] * corr);
+                }
+            }
+
+            if (a.has_edge) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();                               // B5: edge' tile complete
+                if (tid == 0) {
+                    tma_store_4d(&emap, tX, 0, j0, i0, b);
+                    tma_store_4d(&emap, tX + 16384, 64, j0, i0, b);
+                    tma_commit();
+                }
+            } else {
+                tc_fence_before();
+                __syncthreads();
+            }
+            cur ^= 1;
+            par ^= 1;
+        }
+
+        // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
+        // lanes l and l^16 hold key slots 2w and 2w+1 of the same query
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float mo = __shfl_xor_sync(0xffffffffu, mrun[h], 16);
+            const float lo = __shfl_xor_sync(0xffffffffu, lrun[h], 16);
+            const float mn = fmaxf(mrun[h], mo);
+            const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
+            const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+            lrun[h] = lrun[h] * ca + lo * cb;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float ao = __shfl_xor_sync(0xffffffffu, acc[h * 16 + k], 16);
+                acc[h * 16 + k] = acc[h * 16 + k] * ca + ao * cb;
+            }
+            mrun[h] = mn;
+        }
+        // scratch in tile buffer `cur` (free: no prefetch was issued for it): [3 src][2 half][16 j][76]
+        float* scr = reinterpret_cast<float*>(sgen + SM_TILE0 + cur * 32768);
+        const int wq = warp & 3;
+        if (wq != 0 && lane < 16) {
+            float* d = scr + (((wq - 1) * 2 + half) * 16 + lane) * 76;
+#pragma unroll
+            for (int k = 0; k < 64; ++k) d[k] = acc[k];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { d[64 + h] = mrun[h]; d[68 + h] = lrun[h]; }
+        }
+        __syncthreads();
+        if (wq == 0 && lane < 16 && j0 + lane < N) {
+#pragma unroll
+            for (int src = 0; src < 3; ++src) {
+                const float* d = scr + ((src * 2 + half) * 16 + lane) * 76;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float mo = d[64 + h], lo = d[68 + h];
+                    const float mn = fmaxf(mrun[h], mo);
+                    const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
+                    const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+                    lrun[h] = lrun[h] * ca + lo * cb;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[h * 16 + k] = acc[h * 16 + k] * ca + d[h * 16 + k] * cb;
+                    mrun[h] = mn;
+                }
+            }
+            float* o = a.attn + (tok0 + j0 + lane) * 128 + col0;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float inv = 1.f / lrun[h];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int c = h * 16 + k4 * 4;
+                    float4 r;
+                    r.x = acc[c + 0] * inv + Pm[P_BV * 128 + (int)col0 + c + 0];
+                    r.y = acc[c + 1] * inv + Pm[P_BV * 128 + (int)col0 + c + 1];
+                    r.z = acc[c + 2] * inv + Pm[P_BV * 128 + (int)col0 + c + 2];
+                    r.w = acc[c + 3] * inv + Pm[P_BV * 128 + (int)col0 + c + 3];
+                    *reinterpret_cast<float4*>(o + c) = r;
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();   // scratch consumed before the next work item's first tile lands in it
+    }
+
+    if (tid == 0) tma_wait_all0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// self test kernel: one 128x128x128 product through the same TMA / descriptor / TMEM helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+k_tc_selftest(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap, float* out, int* err) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + 65536 + 64);
+    const uint32_t bar_l = sbase + 65536, bar_m = bar_l + 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(bar_l, 1); mbar_init(bar_m, 1); fence_barrier_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + 65536 + 64), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sTmem;
+    if (tid == 0) {
+        mbar_expect_tx(bar_l, 65536u);
+        for (int kb = 0; kb < 2; ++kb) {
+            tma_load_2d(sbase + kb * 16384, &amap, bar_l, kb * 64, 0);
+            tma_load_2d(sbase + 32768 + kb * 16384, &wmap, bar_l, kb * 64, 0);
+        }
+        mbar_wait(bar_l, 0, err, E_LOAD_EDGE);
+        tc_fence_after();
+        for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
+            umma_f16(tmem, umma_desc_sw128(sbase + ko), umma_desc_sw128(sbase + 32768 + ko), umma_idesc_f16(128), kk > 0);
+        }
+        umma_commit(bar_m);
+    }
+    mbar_wait(bar_m, 0, err, E_MMA1);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    // also read back the A tile through the software swizzle to validate sw128()
+    for (int p = 0; p < 4; ++p) {
+        uint32_t r[32];
+        TMEM_LD_X32(tmem + ((uint32_t)(warp * 32) << 16) + p * 32, r);
+        tmem_wait_ld();
+        for (int k = 0; k < 32; ++k) out[row * 128 + p * 32 + k] = __uint_as_float(r[k]);
+    }
+    for (int c8 = 0; c8 < 16; ++c8) {
+        const uint4 u = ld_shared_v4(sbase + (c8 >> 3) * 16384 + sw128(row, c8 & 7));
+        const float2 e0 = unpack_h2(u.x), e1 = unpack_h2(u.y), e2 = unpack_h2(u.z), e3 = unpack_h2(u.w);
+        float* o = out + 128 * 128 + row * 128 + c8 * 8;
+        o[0] = e0.x; o[1] = e0.y; o[2] = e1.x; o[3] = e1.y; o[4] = e2.x; o[5] = e2.y; o[6] = e3.x; o[7] = e3.y;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+char g_tc_err[256];
+const char* tcfail(const char* what, int code) {
+    snprintf(g_tc_err, sizeof g_tc_err, "%s (code %d)", what, code);
+    return g_tc_err;
+}
+
+// 2-D fp16 [rows][128] K-major operand map, box [64 k][128 rows], 128 B swizzle
+const char* make_map_2d(void* out, const void* base, int rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+    cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : tcfail("cuTensorMapEncodeTiled(2d)", (int)r);
+}
+// 4-D fp16 edge stream [B][N(i)][N(j)][128], box [64 c][16 j][8 i][1]
+const char* make_map_edge(void* out, const void* base, int B, int N) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+    cuuint64_t dims[4] = {128, (cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[3] = {256, (cuuint64_t)N * 256, (cuuint64_t)N * N * 256};
+    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : tcfail("cuTensorMapEncodeTiled(4d)", (int)r);
+}
+}  // namespace
+
+void tc_free(TcWeights& w) {
+    for (auto& l : w.layer) {
+        if (l.Wcat) cudaFree(l.Wcat);
+        if (l.params) cudaFree(l.params);
+        l.Wcat = nullptr; l.params = nullptr;
+    }
+    if (w.d_work) cudaFree(w.d_work);
+    if (w.d_err) cudaFree(w.d_err);
+    w.d_work = nullptr; w.d_err = nullptr; w.work_cap = 0; w.packed = false;
+}
+
+const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]) {
+    for (int l = 0; l < 6; ++l) {
+        TcLayerDev& d = w.layer[l];
+        std::vector<__half> W((size_t)512 * 128, __float2half(0.f));
+        std::vector<float> P((size_t)8 * 128, 0.f);
+        const TcHostLayer& h = hl[l];
+        for (int o = 0; o < 128; ++o)
+            for (int k = 0; k < 128; ++k) {
+                W[(size_t)o * 128 + k] = __float2half_rn(h.Wmem[(size_t)o * 384 + k]);
+                if (h.Wpe) W[(size_t)(128 + o) * 128 + k] = __float2half_rn(h.Wpe[(size_t)o * 128 + k]);
+                W[(size_t)(256 + o) * 128 + k] = __float2half_rn(h.Win[(size_t)(128 + o) * 128 + k]);
+                W[(size_t)(384 + o) * 128 + k] = __float2half_rn(h.Win[(size_t)(256 + o) * 128 + k]);
+            }
+        for (int c = 0; c < 128; ++c) {
+            P[tc::P_MEM_G * 128 + c] = h.mem_g[c];
+            P[tc::P_MEM_B * 128 + c] = h.mem_b[c];
+            if (h.Wpe) {
+                P[tc::P_BPE * 128 + c] = h.bpe[c];
+                P[tc::P_PE_G * 128 + c] = h.pe_g[c];
+                P[tc::P_PE_B * 128 + c] = h.pe_b[c];
+                P[tc::P_NE_G * 128 + c] = h.ne_g[c];
+                P[tc::P_NE_B * 128 + c] = h.ne_b[c];
+            }
+            P[tc::P_BV * 128 + c] = h.bin[256 + c];
+        }
+        d.has_edge = h.Wpe ? 1 : 0;
+        if (!d.Wcat && cudaMalloc(&d.Wcat, W.size() * sizeof(__half)) != cudaSuccess) return "cudaMalloc(Wcat) failed";
+        if (!d.params && cudaMalloc(&d.params, P.size() * sizeof(float)) != cudaSuccess) return "cudaMalloc(params) failed";
+        if (cudaMemcpy(d.Wcat, W.data(), W.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return "copy Wcat failed";
+        if (cudaMemcpy(d.params, P.data(), P.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return "copy params failed";
+        if (const char* e = make_map_2d(d.wmap, d.Wcat, 512)) return e;
+    }
+    if (!w.d_err) {
+        if (cudaMalloc(&w.d_err, sizeof(int)) != cudaSuccess) return "cudaMalloc(err) failed";
+        cudaMemset(w.d_err, 0, sizeof(int));
+    }
+    w.packed = true;
+    return nullptr;
+}
+
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, cudaStream_t st) {
+    if (!w.packed) return "weights not packed";
+    std::vector<TcWork> work;
+    for (int b = 0; b < B; ++b) {
+        const int n = sd[b].n_actor + sd[b].n_lane + 1;
+        for (int j0 = 0; j0 < n; j0 += 16) work.push_back(TcWork{b, j0, n, 0});
+    }
+    // longest work items first (static round-robin over persistent CTAs)
+    std::stable_sort(work.begin(), work.end(), [](const TcWork& x, const TcWork& y) { return x.n > y.n; });
+    if ((int)work.size() > w.work_cap) {
+        if (w.d_work) cudaFree(w.d_work);
+        if (cudaMalloc(&w.d_work, work.size() * sizeof(TcWork)) != cudaSuccess) return "cudaMalloc(work) failed";
+        w.work_cap = (int)work.size();
+    }
+    if (cudaMemcpyAsync(w.d_work, work.data(), work.size() * sizeof(TcWork), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return "copy work list failed";
+    w.n_work = (int)work.size();
+    if (w.emap_ptr != edge16 || w.emap_B != B || w.emap_N != Nmax) {
+        if (const char* e = make_map_edge(w.emap, edge16, B, Nmax)) return e;
+        w.emap_ptr = edge16; w.emap_B = B; w.emap_N = Nmax;
+    }
+    w.B = B; w.Nmax = Nmax;
+    return nullptr;
+}
+
+const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, float* attn, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(tc::k_rela_fusion_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
+            return "cudaFuncSetAttribute(smem) failed";
+        attr = true;
+    }
+    tc::LayerArgs a;
+    a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn = attn;
+    a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err;
+    const int grid = std::max(1, std::min(w.n_work, sm_count));
+    CUtensorMap em, wm;
+    memcpy(&em, w.emap, sizeof em);
+    memcpy(&wm, w.layer[layer].wmap, sizeof wm);
+    tc::k_rela_fusion_tc<<<grid, tc::kThreads, tc::SMEM_BYTES, st>>>(em, wm, a);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    return nullptr;
+}
+
+const char* tc_selftest(const float* A_host, const float* W_host, float* D_host) {
+    __half *dA = nullptr, *dW = nullptr;
+    float* dO = nullptr;
+    int* dErr = nullptr;
+    std::vector<__half> hA(128 * 128), hW(128 * 128);
+    for (int i = 0; i < 128 * 128; ++i) { hA[i] = __float2half_rn(A_host[i]); hW[i] = __float2half_rn(W_host[i]); }
+    if (cudaMalloc(&dA, 32768) != cudaSuccess || cudaMalloc(&dW, 32768) != cudaSuccess ||
+        cudaMalloc(&dO, 2 * 65536) != cudaSuccess || cudaMalloc(&dErr, 4) != cudaSuccess)
+        return "selftest cudaMalloc failed";
+    cudaMemcpy(dA, hA.data(), 32768, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, hW.data(), 32768, cudaMemcpyHostToDevice);
+    cudaMemset(dErr, 0, 4);
+    cudaMemset(dO, 0, 2 * 65536);
+    alignas(64) CUtensorMap am, wm;
+    if (const char* e = make_map_2d(&am, dA, 128)) return e;
+    if (const char* e = make_map_2d(&wm, dW, 128)) return e;
+    const int smem = 65536 + 128 + 1024;
+    if (cudaFuncSetAttribute(tc::k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return "selftest attribute failed";
+    tc::k_tc_selftest<<<1, 128, smem>>>(am, wm, dO, dErr);
+    ++g_launches;
+    cudaError_t e = cudaDeviceSynchronize();
+    const char* ret = nullptr;
+    if (e != cudaSuccess) {
+        int code = 0;
+        cudaMemcpy(&code, dErr, 4, cudaMemcpyDeviceToHost);
+        ret = tcfail(cudaGetErrorString(e), code);
+    } else {
+        cudaMemcpy(D_host, dO, 2 * 65536, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dErr);
+    return ret;
+}
+
+}  // namespace mind

@@ -1,0 +1,47 @@
+// Tensor-core (tcgen05 / TMEM / TMA) rela-fusion layer: interface used by mind_api.cu.
+#pragma once
+#include "kernels.h"
+#include <vector>
+
+namespace mind {
+
+// host pointers to the fp32 parameters of one RelaFusionLayer (reference network.py:124-232)
+struct TcHostLayer {
+    const float *Wmem, *mem_g, *mem_b;          // proj_memory: [128,384], LN
+    const float *Wpe, *bpe, *pe_g, *pe_b;       // proj_edge (null on the last layer)
+    const float *ne_g, *ne_b;                   // norm_edge
+    const float *Win, *bin;                     // MHA in_proj [384,128], [384]
+};
+
+struct TcWork { int32_t b, j0, n, pad; };      // one work item: scene b, queries j0..j0+15, n tokens
+
+struct TcLayerDev {
+    __half* Wcat = nullptr;     // [512][128] fp16 rows: W_e | W_pe | W_k | W_v   (K-major B operands)
+    float* params = nullptr;    // [8][128] fp32: mem_g, mem_b, bpe, pe_g, pe_b, ne_g, ne_b, bv
+    int has_edge = 0;
+    alignas(64) unsigned char wmap[128];   // CUtensorMap over Wcat
+};
+
+struct TcWeights {
+    TcLayerDev layer[6];
+    bool packed = false;
+    // per-forward state
+    TcWork* d_work = nullptr; int work_cap = 0; int n_work = 0;
+    int* d_err = nullptr;
+    alignas(64) unsigned char emap[128];   // CUtensorMap over the edge stream
+    const void* emap_ptr = nullptr; int emap_B = 0, emap_N = 0;
+    int B = 0, Nmax = 0;
+};
+
+// all return nullptr on success, else an error string
+const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]);
+void tc_free(TcWeights& w);
+// per forward: work list + tensor map over edge16 [B,Nmax,Nmax,128] fp16
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, cudaStream_t st);
+// One fused layer over the whole batch: updates edge16 in place (layers 0-4), reads STQ
+// [B*Nmax,384] (S | T | q/4), writes attn [B*Nmax,128] (attention output before out-proj).
+const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, float* attn, int sm_count, cudaStream_t st);
+// bring-up self test: D[128,128] = A[128,128] . W[128,128]^T through TMA + tcgen05 + TMEM
+const char* tc_selftest(const float* A_host, const float* W_host, float* D_host);
+
+}  // namespace mind

@@ -1,0 +1,87 @@
+// Internal launch interface between mind_api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace mind {
+
+// running launch counter (bench.py gpu_launches)
+extern int64_t g_launches;
+
+struct GemmArgs {
+    const float* A = nullptr; int lda = 0;      // [M,K]
+    const float* W = nullptr; int ldw = 0;      // [N,K] (torch Linear layout), row stride ldw
+    const float* bias = nullptr;                // [N] or null
+    const float* gbias = nullptr; int gsize = 1; int ldg = 0;   // per row-group bias [(m/gsize), N]
+    float* C = nullptr; int ldc = 0;            // [M,N]
+    int M = 0, N = 0, K = 0;
+    int relu = 0;
+};
+void launch_gemm(const GemmArgs& g, cudaStream_t st);
+
+// out[r,:] = act(LN(x[r,:] (+ res[r,:]))) ; D <= 1536, D % 4 == 0
+void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta,
+                      float* out, int64_t rows, int D, int relu, cudaStream_t st);
+
+// max over groups of `g` consecutive rows: in [G*g, D] -> out [G, D]
+void launch_group_max(const float* in, float* out, int64_t G, int g, int D, cudaStream_t st);
+
+// ---- ActorNet (reference network.py:12-61) : one CTA per actor, all layers in shared memory
+struct ActorNetWeights {
+    // conv filters pre-transposed to [ci][k][co]; 1x1 shortcut filters to [ci][co]
+    const float* g_conv1[4][2]; const float* g_conv2[4][2];
+    const float* g_bn1w[4][2]; const float* g_bn1b[4][2];
+    const float* g_bn2w[4][2]; const float* g_bn2b[4][2];
+    const float* g_ds[4]; const float* g_dsw[4]; const float* g_dsb[4];   // block 0 of each group
+    const float* lat_conv[4]; const float* lat_w[4]; const float* lat_b[4];
+    const float* out_conv1; const float* out_conv2;
+    const float* out_bn1w; const float* out_bn1b; const float* out_bn2w; const float* out_bn2b;
+};
+void launch_actor_net(const float* actors, float* out, int n_actors, const ActorNetWeights& w, cudaStream_t st);
+
+// ---- scene descriptor table (device) -------------------------------------------------------
+struct SceneDesc {
+    int32_t actor_off, lane_off;   // offsets into the compact actor / lane arrays
+    int32_t n_actor, n_lane;       // N = n_actor + n_lane + 1 tokens
+    int32_t geom_off;              // offset into ctrs/vecs (= actor_off + lane_off)
+    int32_t pad_;
+    const float* rpe;              // dev [5, M, M] or null
+};
+
+// tokens x [B, Nmax, 128]: scatter projected actors / lanes, zero cls + padding rows
+void launch_scatter_tokens(const float* actors_p, const float* lanes_p, const SceneDesc* sd, float* x,
+                           int B, int Nmax, cudaStream_t st);
+// gather fused actor tokens -> [sumNa,128] and cls tokens -> [B,128]
+void launch_gather_tokens(const float* x, const SceneDesc* sd, float* actors, float* cls, int B, int Nmax,
+                          cudaStream_t st);
+
+// edge0[b,i,j,:] = ReLU(LN(W5 . rpe[b,:,i,j] + b)) for i,j < M_b, zero elsewhere (network.py:326-330)
+// OutT = float (exact path) or __half (tensor-core path)
+void launch_edge_init_f32(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
+                          const float* g, const float* be, float* edge, int b0, int nb, int Nmax, cudaStream_t st);
+void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
+                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, cudaStream_t st);
+
+// exact-path pair epilogues on rows r = ((b*Nmax + i)*Nmax + j)
+// memory = ReLU(LN(tmp + S[b,j] + T[b,i]))   with STQ [B*Nmax, 384] = [S | T | q]
+void launch_pair_memory_epi(const float* tmp, const float* stq, const float* g, const float* be, float* memory,
+                            int b0, int nb, int Nmax, cudaStream_t st);
+// edge = LN_e(edge + ReLU(LN_p(tmp)))
+void launch_pair_edge_epi(const float* tmp, const float* gp, const float* bp, const float* ge, const float* bee,
+                          float* edge, int64_t rows, cudaStream_t st);
+// attn[b,j,:] = sum_i softmax_i(q[b,j,h].K[b,i,j,h]) V[b,i,j,h]   (KV [rows,256] = [K|V]; q pre-scaled)
+void launch_pair_attention(const float* kv, const float* stq, const SceneDesc* sd, float* attn, int b0, int nb,
+                           int Nmax, cudaStream_t st);
+
+// ---- decoder pieces (reference network.py:483-556) -----------------------------------------
+// self attention over the 6 modes of each scene: qkv [B*6,384] -> out [B*6,128], 4 heads
+void launch_mode_attention(const float* qkv, float* out, int B, cudaStream_t st);
+// embed[a*6+m] = ce[scene(a)*6+m] + ae[a*6+m] + (m==0 ? tgt[scene(a)] : 0)
+void launch_embed_combine(const float* ce, const float* ae, const float* tgt, const int32_t* actor_scene,
+                          float* embed, int n_actors, cudaStream_t st);
+void launch_softmax6(const float* logits, float* cls, int B, cudaStream_t st);
+void launch_bezier(const float* param, const float* T, const float* Tp, float* reg, float* vel, float* cov_vel,
+                   int n_rows /* sumNa*6 */, cudaStream_t st);
+
+}  // namespace mind

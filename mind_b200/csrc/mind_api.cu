@@ -1,0 +1,629 @@
+// C ABI of libmind_b200.so (see include/mind_b200.h).  Host-side orchestration only: weight
+// packing, workspace carving, launch sequence of the scene-prediction forward pass
+// (reference planners/mind/networks/network.py:582-595).
+#include "../../include/mind_b200.h"
+#include "kernels.h"
+#include "fusion_tc.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mind;
+
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CUDA_OK(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct FusionLayerW {
+    const float *We; int ldWe;                    // [128, 128] view of proj_memory.0.weight[:, :128]
+    const float *Wstq, *bstq;                     // [384,128], [384]: S | T(+b_mem) | q*0.25
+    const float *mem_g, *mem_b;                   // proj_memory.1
+    const float *Wpe, *bpe, *pe_g, *pe_b, *ne_g, *ne_b;   // proj_edge / norm_edge (null on last layer)
+    const float *Wkv, *bkv;                       // [256,128] rows k|v of in_proj
+    const float *Wo, *bo, *n2_g, *n2_b, *W1, *b1, *W2, *b2, *n3_g, *n3_b;
+};
+
+struct MindCtx {
+    int device = 0;
+    std::map<std::string, std::vector<float>> host_w;
+    float* arena = nullptr;
+    size_t arena_floats = 0;
+    std::map<std::string, const float*> dev_w;
+    bool finalized = false;
+    int precision = MIND_PREC_FP32;
+    int chunk_scenes = 32;
+    ActorNetWeights an{};
+    FusionLayerW fl[6]{};
+    TcWeights tc{};               // fp16 packed weights / per-layer params for the tensor-core path
+    // descriptor tables
+    SceneDesc* d_sd = nullptr; int sd_cap = 0;
+    int32_t* d_actor_scene = nullptr; int as_cap = 0;
+    // last forward bookkeeping for debug taps
+    std::map<std::string, std::pair<const float*, int64_t>> taps;
+    int sm_count = 148;
+};
+
+extern "C" const char* mind_last_error(void) { return g_err; }
+extern "C" const char* mind_build_info(void) { return "libmind_b200 sm_100a (fp32 SIMT + tcgen05 f16 rela-fusion)"; }
+
+extern "C" int mind_create(MindCtx** out, int device) {
+    if (!out) return fail("mind_create: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail("mind_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("mind_create: device %d out of range (%d devices)", device, n);
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("mind_create: device sm_%d%d is not Blackwell (sm_100a required)", prop.major, prop.minor);
+    MindCtx* c = new MindCtx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+extern "C" void mind_destroy(MindCtx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->arena) cudaFree(c->arena);
+    if (c->d_sd) cudaFree(c->d_sd);
+    if (c->d_actor_scene) cudaFree(c->d_actor_scene);
+    tc_free(c->tc);
+    delete c;
+}
+
+extern "C" int mind_set_weight(MindCtx* c, const char* key, const float* host, int64_t numel) {
+    if (!c || !key || !host || numel <= 0) return fail("mind_set_weight: bad argument");
+    c->host_w[key].assign(host, host + numel);
+    c->finalized = false;
+    return 0;
+}
+
+extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
+    if (!c || !name) return fail("mind_set_option: bad argument");
+    if (!strcmp(name, "precision")) {
+        if (value != MIND_PREC_FP32 && value != MIND_PREC_F16TC) return fail("precision must be 0 or 1");
+        c->precision = (int)value;
+    } else if (!strcmp(name, "chunk_scenes")) {
+        if (value < 1) return fail("chunk_scenes must be >= 1");
+        c->chunk_scenes = (int)value;
+    } else {
+        return fail("unknown option %s", name);
+    }
+    return 0;
+}
+
+extern "C" int64_t mind_launch_count(MindCtx*) { return g_launches; }
+
+// ------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Builder {
+    std::vector<float> flat;
+    std::map<std::string, size_t> off;
+    size_t add(const std::string& name, const std::vector<float>& v) {
+        size_t o = (flat.size() + 63) & ~size_t(63);   // 256 B alignment
+        flat.resize(o);
+        flat.insert(flat.end(), v.begin(), v.end());
+        off[name] = o;
+        return o;
+    }
+};
+}  // namespace
+
+static const std::vector<float>* find(MindCtx* c, const std::string& k) {
+    auto it = c->host_w.find(k);
+    return it == c->host_w.end() ? nullptr : &it->second;
+}
+
+extern "C" int mind_finalize_weights(MindCtx* c) {
+    if (!c) return fail("mind_finalize_weights: null ctx");
+    CUDA_OK(cudaSetDevice(c->device));
+    Builder b;
+    for (auto& kv : c->host_w) b.add(kv.first, kv.second);
+
+    auto need = [&](const std::string& k, size_t numel) -> const std::vector<float>* {
+        const std::vector<float>* v = find(c, k);
+        if (!v) { fail("missing weight '%s'", k.c_str()); return nullptr; }
+        if (v->size() != numel) { fail("weight '%s' has %zu elements, expected %zu", k.c_str(), v->size(), numel); return nullptr; }
+        return v;
+    };
+    // transposed conv filters: [co][ci][k] -> [ci][k][co]
+    auto conv_t = [&](const std::string& k, int co, int ci, int ks) -> bool {
+        const std::vector<float>* v = need(k, (size_t)co * ci * ks);
+        if (!v) return false;
+        std::vector<float> t((size_t)co * ci * ks);
+        for (int o = 0; o < co; ++o)
+            for (int i = 0; i < ci; ++i)
+                for (int kk = 0; kk < ks; ++kk) t[((size_t)i * ks + kk) * co + o] = (*v)[((size_t)o * ci + i) * ks + kk];
+        b.add(k + "#T", t);
+        return true;
+    };
+    const int Cg[4] = {32, 64, 128, 256};
+    int cin = 14;
+    for (int g = 0; g < 4; ++g) {
+        char p[64];
+        snprintf(p, sizeof p, "actor_net.groups.%d.", g);
+        std::string P(p);
+        if (!conv_t(P + "0.conv1.weight", Cg[g], cin, 3)) return 1;
+        if (!conv_t(P + "0.conv2.weight", Cg[g], Cg[g], 3)) return 1;
+        if (!conv_t(P + "0.downsample.0.weight", Cg[g], cin, 1)) return 1;
+        if (!conv_t(P + "1.conv1.weight", Cg[g], Cg[g], 3)) return 1;
+        if (!conv_t(P + "1.conv2.weight", Cg[g], Cg[g], 3)) return 1;
+        snprintf(p, sizeof p, "actor_net.lateral.%d.conv.weight", g);
+        if (!conv_t(p, 128, Cg[g], 3)) return 1;
+        cin = Cg[g];
+    }
+    if (!conv_t("actor_net.output.conv1.weight", 128, 128, 3)) return 1;
+    if (!conv_t("actor_net.output.conv2.weight", 128, 128, 3)) return 1;
+
+    // fused node-side projection per fusion layer: rows [Ws ; Wt ; 0.25*Wq], bias [0 ; b_mem ; 0.25*bq]
+    for (int l = 0; l < 6; ++l) {
+        char p[96];
+        snprintf(p, sizeof p, "fusion_net.fuse_scene.fusion.%d.", l);
+        std::string P(p);
+        const auto* Wm = need(P + "proj_memory.0.weight", 128 * 384);
+        const auto* bm = need(P + "proj_memory.0.bias", 128);
+        const auto* Win = need(P + "multihead_attn.in_proj_weight", 384 * 128);
+        const auto* bin = need(P + "multihead_attn.in_proj_bias", 384);
+        if (!Wm || !bm || !Win || !bin) return 1;
+        std::vector<float> W(384 * 128), bb(384, 0.f);
+        for (int o = 0; o < 128; ++o)
+            for (int k = 0; k < 128; ++k) {
+                W[(size_t)o * 128 + k] = (*Wm)[(size_t)o * 384 + 128 + k];
+                W[(size_t)(128 + o) * 128 + k] = (*Wm)[(size_t)o * 384 + 256 + k];
+                W[(size_t)(256 + o) * 128 + k] = 0.25f * (*Win)[(size_t)o * 128 + k];
+            }
+        for (int o = 0; o < 128; ++o) { bb[128 + o] = (*bm)[o]; bb[256 + o] = 0.25f * (*bin)[o]; }
+        b.add(P + "#Wstq", W);
+        b.add(P + "#bstq", bb);
+    }
+    if (!need("__bezier_T", 60 * 8) || !need("__bezier_Tp", 60 * 7)) return 1;
+
+    if (c->arena) { cudaFree(c->arena); c->arena = nullptr; }
+    c->arena_floats = b.flat.size();
+    CUDA_OK(cudaMalloc(&c->arena, c->arena_floats * sizeof(float)));
+    CUDA_OK(cudaMemcpy(c->arena, b.flat.data(), c->arena_floats * sizeof(float), cudaMemcpyHostToDevice));
+    c->dev_w.clear();
+    for (auto& kv : b.off) c->dev_w[kv.first] = c->arena + kv.second;
+
+    bool ok = true;
+    auto D = [&](const std::string& k) -> const float* {
+        auto it = c->dev_w.find(k);
+        if (it == c->dev_w.end()) { if (ok) fail("missing weight '%s'", k.c_str()); ok = false; return nullptr; }
+        return it->second;
+    };
+    ActorNetWeights& an = c->an;
+    for (int g = 0; g < 4; ++g) {
+        for (int j = 0; j < 2; ++j) {
+            char p[64];
+            snprintf(p, sizeof p, "actor_net.groups.%d.%d.", g, j);
+            std::string P(p);
+            an.g_conv1[g][j] = D(P + "conv1.weight#T");
+            an.g_conv2[g][j] = D(P + "conv2.weight#T");
+            an.g_bn1w[g][j] = D(P + "bn1.weight"); an.g_bn1b[g][j] = D(P + "bn1.bias");
+            an.g_bn2w[g][j] = D(P + "bn2.weight"); an.g_bn2b[g][j] = D(P + "bn2.bias");
+        }
+        char p[64];
+        snprintf(p, sizeof p, "actor_net.groups.%d.0.downsample.", g);
+        std::string P(p);
+        an.g_ds[g] = D(P + "0.weight#T"); an.g_dsw[g] = D(P + "1.weight"); an.g_dsb[g] = D(P + "1.bias");
+        snprintf(p, sizeof p, "actor_net.lateral.%d.", g);
+        P = p;
+        an.lat_conv[g] = D(P + "conv.weight#T"); an.lat_w[g] = D(P + "norm.weight"); an.lat_b[g] = D(P + "norm.bias");
+    }
+    an.out_conv1 = D("actor_net.output.conv1.weight#T"); an.out_conv2 = D("actor_net.output.conv2.weight#T");
+    an.out_bn1w = D("actor_net.output.bn1.weight"); an.out_bn1b = D("actor_net.output.bn1.bias");
+    an.out_bn2w = D("actor_net.output.bn2.weight"); an.out_bn2b = D("actor_net.output.bn2.bias");
+
+    for (int l = 0; l < 6; ++l) {
+        char p[96];
+        snprintf(p, sizeof p, "fusion_net.fuse_scene.fusion.%d.", l);
+        std::string P(p);
+        FusionLayerW& f = c->fl[l];
+        f.We = D(P + "proj_memory.0.weight"); f.ldWe = 384;
+        f.Wstq = D(P + "#Wstq"); f.bstq = D(P + "#bstq");
+        f.mem_g = D(P + "proj_memory.1.weight"); f.mem_b = D(P + "proj_memory.1.bias");
+        if (l < 5) {
+            f.Wpe = D(P + "proj_edge.0.weight"); f.bpe = D(P + "proj_edge.0.bias");
+            f.pe_g = D(P + "proj_edge.1.weight"); f.pe_b = D(P + "proj_edge.1.bias");
+            f.ne_g = D(P + "norm_edge.weight"); f.ne_b = D(P + "norm_edge.bias");
+        } else {
+            f.Wpe = f.bpe = f.pe_g = f.pe_b = f.ne_g = f.ne_b = nullptr;
+        }
+        const float* Win = D(P + "multihead_attn.in_proj_weight");
+        const float* bin = D(P + "multihead_attn.in_proj_bias");
+        f.Wkv = Win ? Win + 128 * 128 : nullptr; f.bkv = bin ? bin + 128 : nullptr;
+        f.Wo = D(P + "multihead_attn.out_proj.weight"); f.bo = D(P + "multihead_attn.out_proj.bias");
+        f.n2_g = D(P + "norm2.weight"); f.n2_b = D(P + "norm2.bias");
+        f.W1 = D(P + "linear1.weight"); f.b1 = D(P + "linear1.bias");
+        f.W2 = D(P + "linear2.weight"); f.b2 = D(P + "linear2.bias");
+        f.n3_g = D(P + "norm3.weight"); f.n3_b = D(P + "norm3.bias");
+    }
+    if (!ok) return 1;
+
+    // tensor-core path: fp16 operand copies + per-layer parameter blocks
+    {
+        TcHostLayer hl[6];
+        for (int l = 0; l < 6; ++l) {
+            char p[96];
+            snprintf(p, sizeof p, "fusion_net.fuse_scene.fusion.%d.", l);
+            std::string P(p);
+            hl[l].Wmem = find(c, P + "proj_memory.0.weight")->data();
+            hl[l].mem_g = find(c, P + "proj_memory.1.weight")->data();
+            hl[l].mem_b = find(c, P + "proj_memory.1.bias")->data();
+            hl[l].Win = find(c, P + "multihead_attn.in_proj_weight")->data();
+            hl[l].bin = find(c, P + "multihead_attn.in_proj_bias")->data();
+            if (l < 5) {
+                hl[l].Wpe = find(c, P + "proj_edge.0.weight")->data();
+                hl[l].bpe = find(c, P + "proj_edge.0.bias")->data();
+                hl[l].pe_g = find(c, P + "proj_edge.1.weight")->data();
+                hl[l].pe_b = find(c, P + "proj_edge.1.bias")->data();
+                hl[l].ne_g = find(c, P + "norm_edge.weight")->data();
+                hl[l].ne_b = find(c, P + "norm_edge.bias")->data();
+            } else {
+                hl[l].Wpe = hl[l].bpe = hl[l].pe_g = hl[l].pe_b = hl[l].ne_g = hl[l].ne_b = nullptr;
+            }
+        }
+        const char* err = tc_pack_weights(c->tc, hl);
+        if (err) return fail("tc_pack_weights: %s", err);
+    }
+    c->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace carving (identical code path for sizing and for the real run)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Carver {
+    char* base;
+    int64_t off = 0;
+    explicit Carver(void* b) : base((char*)b) {}
+    template <typename T>
+    T* take(int64_t n) {
+        off = (off + 255) & ~int64_t(255);
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * (int64_t)sizeof(T);
+        return p;
+    }
+};
+
+struct Ws {
+    // encoders
+    float *actor_feat, *lane_in, *lx, *la, *ly, *lm, *lgb, *lane_feat;
+    float *actor_p, *lane_p;
+    // tokens
+    float *x, *stq, *attn, *xo, *ffn;
+    // exact path chunk buffers
+    float *edge, *tmp, *memory, *kv;
+    // tensor-core path
+    __half* edge16;
+    // decoder
+    float *actors_f, *cls_tok, *tr, *tg1, *tgt, *c1, *ce, *qkv, *att, *co, *f1, *f2, *a1, *ae, *embed, *h1, *h2, *param;
+    float *k1, *k2, *logit;
+};
+
+int chunk_for(const MindCtx* c, int B) { return std::max(1, std::min(B, c->chunk_scenes)); }
+
+int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w) {
+    Carver cv(base);
+    const int64_t Lp = (int64_t)L + B, R = Lp * 10, TOK = (int64_t)B * Nmax;
+    w.actor_feat = cv.take<float>((int64_t)A * 128);
+    w.lane_in = cv.take<float>(R * 16);
+    w.lx = cv.take<float>(R * 128);
+    w.la = cv.take<float>(R * 128);
+    w.ly = cv.take<float>(R * 128);
+    w.lm = cv.take<float>(Lp * 128);
+    w.lgb = cv.take<float>(Lp * 128);
+    w.lane_feat = cv.take<float>(Lp * 128);
+    w.actor_p = cv.take<float>((int64_t)A * 128);
+    w.lane_p = cv.take<float>((int64_t)std::max(L, 1) * 128);
+    w.x = cv.take<float>(TOK * 128);
+    w.stq = cv.take<float>(TOK * 384);
+    w.attn = cv.take<float>(TOK * 128);
+    w.xo = cv.take<float>(TOK * 128);
+    w.ffn = cv.take<float>(TOK * 256);
+    const int64_t pairs = (int64_t)Nmax * Nmax;
+    if (c->precision == MIND_PREC_FP32) {
+        const int64_t C = chunk_for(c, B);
+        w.edge = cv.take<float>(C * pairs * 128);
+        w.tmp = cv.take<float>(C * pairs * 128);
+        w.memory = cv.take<float>(C * pairs * 128);
+        w.kv = cv.take<float>(C * pairs * 256);
+        w.edge16 = nullptr;
+    } else {
+        w.edge = w.tmp = w.memory = w.kv = nullptr;
+        w.edge16 = cv.take<__half>((int64_t)B * pairs * 128);
+    }
+    w.actors_f = cv.take<float>((int64_t)A * 128);
+    w.cls_tok = cv.take<float>((int64_t)B * 128);
+    w.tr = cv.take<float>((int64_t)B * 128);
+    w.tg1 = cv.take<float>((int64_t)B * 128);
+    w.tgt = cv.take<float>((int64_t)B * 128);
+    w.c1 = cv.take<float>((int64_t)B * 384);
+    w.ce = cv.take<float>((int64_t)B * 768);
+    w.qkv = cv.take<float>((int64_t)B * 6 * 384);
+    w.att = cv.take<float>((int64_t)B * 768);
+    w.co = cv.take<float>((int64_t)B * 768);
+    w.f1 = cv.take<float>((int64_t)B * 6 * 1536);
+    w.f2 = cv.take<float>((int64_t)B * 768);
+    w.a1 = cv.take<float>((int64_t)A * 384);
+    w.ae = cv.take<float>((int64_t)A * 768);
+    w.embed = cv.take<float>((int64_t)A * 768);
+    w.h1 = cv.take<float>((int64_t)A * 768);
+    w.h2 = cv.take<float>((int64_t)A * 768);
+    w.param = cv.take<float>((int64_t)A * 6 * 40);
+    w.k1 = cv.take<float>((int64_t)B * 768);
+    w.k2 = cv.take<float>((int64_t)B * 768);
+    w.logit = cv.take<float>((int64_t)B * 6);
+    return (cv.off + 255) & ~int64_t(255);
+}
+}  // namespace
+
+extern "C" int64_t mind_workspace_bytes(MindCtx* c, int32_t B, int32_t A, int32_t L, int32_t Nmax) {
+    if (!c || B <= 0 || A < 0 || L < 0 || Nmax <= 0) { fail("mind_workspace_bytes: bad argument"); return -1; }
+    Ws w;
+    return carve(c, nullptr, B, A, L, Nmax, w);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Lin {   // Linear (+ optional LayerNorm + ReLU) helper
+    MindCtx* c;
+    cudaStream_t st;
+    const float* W(const std::string& k) const { return c->dev_w.at(k); }
+    void gemm(const float* A, int lda, const float* Wp, int ldw, const float* bias, float* C, int ldc, int64_t M, int N,
+              int K, int relu = 0, const float* gbias = nullptr, int gsize = 1, int ldg = 0) const {
+        GemmArgs g;
+        g.A = A; g.lda = lda; g.W = Wp; g.ldw = ldw; g.bias = bias; g.C = C; g.ldc = ldc;
+        g.M = (int)M; g.N = N; g.K = K; g.relu = relu; g.gbias = gbias; g.gsize = gsize; g.ldg = ldg;
+        launch_gemm(g, st);
+    }
+    // y = ReLU(LN(x W^T + b)) with keys  <p><i>.weight/.bias and <p><i+1>.weight/.bias
+    void lin_ln_relu(const std::string& p, int i, const float* x, int K, float* y, int N, int64_t M) const {
+        const std::string a = p + std::to_string(i), n = p + std::to_string(i + 1);
+        gemm(x, K, W(a + ".weight"), K, W(a + ".bias"), y, N, M, N, K);
+        launch_layernorm(y, nullptr, W(n + ".weight"), W(n + ".bias"), y, M, N, 1, st);
+    }
+};
+}  // namespace
+
+static void run_lane_net(MindCtx* c, const Ws& w, int64_t Lp, cudaStream_t st) {
+    Lin L{c, st};
+    const int64_t R = Lp * 10;
+    L.lin_ln_relu("lane_net.proj.", 0, w.lane_in, 16, w.lx, 128, R);             // network.py:108-112,118
+    for (int blk = 1; blk <= 2; ++blk) {                                         // PointAggregateBlock :90-99
+        const std::string P = "lane_net.aggre" + std::to_string(blk) + ".";
+        L.lin_ln_relu(P + "fc1.", 0, w.lx, 128, w.la, 128, R);
+        L.lin_ln_relu(P + "fc1.", 3, w.la, 128, w.ly, 128, R);                   // ly = fc1(x)
+        launch_group_max(w.ly, w.lm, Lp, 10, 128, st);                           // max over the 10 nodes
+        // fc2.0 on cat[h, max]: W = [Wa | Wb];  Wb.max (+bias) is a per-polyline row-group bias
+        const float* W20 = L.W(P + "fc2.0.weight");
+        L.gemm(w.lm, 128, W20 + 128, 256, L.W(P + "fc2.0.bias"), w.lgb, 128, Lp, 128, 128);
+        L.gemm(w.ly, 128, W20, 256, nullptr, w.la, 128, R, 128, 128, 0, w.lgb, 10, 128);
+        launch_layernorm(w.la, nullptr, L.W(P + "fc2.1.weight"), L.W(P + "fc2.1.bias"), w.la, R, 128, 1, st);
+        L.lin_ln_relu(P + "fc2.", 3, w.la, 128, w.ly, 128, R);
+        if (blk == 1) {
+            launch_layernorm(w.lx, w.ly, L.W(P + "norm.weight"), L.W(P + "norm.bias"), w.lx, R, 128, 0, st);
+        } else {
+            launch_layernorm(w.lx, w.ly, L.W(P + "norm.weight"), L.W(P + "norm.bias"), w.la, R, 128, 0, st);
+            launch_group_max(w.la, w.lane_feat, Lp, 10, 128, st);
+        }
+    }
+}
+
+// node-side tail of a rela-fusion layer on token rows [r0, r0+rows): out-proj, LN2, FFN, LN3
+// (network.py:178-179,222-232).  x is updated in place.
+static void run_node_post(MindCtx* c, const FusionLayerW& f, const Ws& w, int64_t r0, int64_t rows, cudaStream_t st) {
+    Lin L{c, st};
+    float* x = w.x + r0 * 128;
+    float* attn = w.attn + r0 * 128;
+    float* xo = w.xo + r0 * 128;
+    float* ffn = w.ffn + r0 * 256;
+    L.gemm(attn, 128, f.Wo, 128, f.bo, xo, 128, rows, 128, 128);
+    launch_layernorm(x, xo, f.n2_g, f.n2_b, x, rows, 128, 0, st);
+    L.gemm(x, 128, f.W1, 128, f.b1, ffn, 256, rows, 256, 128, 1);
+    L.gemm(ffn, 256, f.W2, 256, f.b2, xo, 128, rows, 128, 256);
+    launch_layernorm(x, xo, f.n3_g, f.n3_b, x, rows, 128, 0, st);
+}
+
+static void run_decoder(MindCtx* c, const Ws& w, const MindBatch* bt, const MindOutputs* out, int B, int A,
+                        const float* tgt_feat, cudaStream_t st) {
+    Lin L{c, st};
+    const std::string P = "pred_scene.";
+    // tgt = proj_tgt(cat[tgt_feat, proj_rpe(tgt_rpe)])   (network.py:491-495)
+    L.lin_ln_relu(P + "proj_rpe.", 0, bt->tgt_rpe, 20, w.tr, 128, B);
+    const float* Wt0 = L.W(P + "proj_tgt.0.weight");
+    L.gemm(w.tr, 128, Wt0 + 128, 256, L.W(P + "proj_tgt.0.bias"), w.tg1, 128, B, 128, 128);
+    L.gemm(tgt_feat, 128, Wt0, 256, nullptr, w.tgt, 128, B, 128, 128, 0, w.tg1, 1, 128);
+    launch_layernorm(w.tgt, nullptr, L.W(P + "proj_tgt.1.weight"), L.W(P + "proj_tgt.1.bias"), w.tgt, B, 128, 1, st);
+    L.lin_ln_relu(P + "proj_tgt.", 3, w.tgt, 128, w.tg1, 128, B);            // tg1 = tgt [B,128]
+    // cls_embed = ctx_sat(ctx_proj(cls).view(6,1,128))   (:501-502)
+    L.lin_ln_relu(P + "ctx_proj.", 0, w.cls_tok, 128, w.c1, 384, B);
+    L.lin_ln_relu(P + "ctx_proj.", 3, w.c1, 384, w.ce, 768, B);              // ce rows = [B*6,128]
+    for (int l = 0; l < 2; ++l) {
+        const std::string Q = P + "ctx_sat.layers." + std::to_string(l) + ".";
+        L.gemm(w.ce, 128, L.W(Q + "self_attn.in_proj_weight"), 128, L.W(Q + "self_attn.in_proj_bias"), w.qkv, 384,
+               (int64_t)B * 6, 384, 128);
+        launch_mode_attention(w.qkv, w.att, B, st);
+        L.gemm(w.att, 128, L.W(Q + "self_attn.out_proj.weight"), 128, L.W(Q + "self_attn.out_proj.bias"), w.co, 128,
+               (int64_t)B * 6, 128, 128);
+        launch_layernorm(w.ce, w.co, L.W(Q + "norm1.weight"), L.W(Q + "norm1.bias"), w.ce, (int64_t)B * 6, 128, 0, st);
+        L.gemm(w.ce, 128, L.W(Q + "linear1.weight"), 128, L.W(Q + "linear1.bias"), w.f1, 1536, (int64_t)B * 6, 1536, 128, 1);
+        L.gemm(w.f1, 1536, L.W(Q + "linear2.weight"), 1536, L.W(Q + "linear2.bias"), w.f2, 128, (int64_t)B * 6, 128, 1536);
+        launch_layernorm(w.ce, w.f2, L.W(Q + "norm2.weight"), L.W(Q + "norm2.bias"), w.ce, (int64_t)B * 6, 128, 0, st);
+    }
+    // actor_embed = actor_proj(actors).view(Na,6,128)   (:504)
+    L.lin_ln_relu(P + "actor_proj.", 0, w.actors_f, 128, w.a1, 384, A);
+    L.lin_ln_relu(P + "actor_proj.", 3, w.a1, 384, w.ae, 768, A);
+    launch_embed_combine(w.ce, w.ae, w.tg1, c->d_actor_scene, w.embed, A, st);   // (:506-510)
+    // cls head (:512,547-548)
+    L.lin_ln_relu(P + "cls.", 0, w.ce, 128, w.k1, 128, (int64_t)B * 6);
+    L.lin_ln_relu(P + "cls.", 3, w.k1, 128, w.k2, 128, (int64_t)B * 6);
+    L.gemm(w.k2, 128, L.W(P + "cls.6.weight"), 128, L.W(P + "cls.6.bias"), w.logit, 1, (int64_t)B * 6, 1, 128);
+    launch_softmax6(w.logit, out->cls, B, st);
+    // reg head + Bezier (:515-523,545)
+    L.lin_ln_relu(P + "reg.", 0, w.embed, 128, w.h1, 128, (int64_t)A * 6);
+    L.lin_ln_relu(P + "reg.", 3, w.h1, 128, w.h2, 128, (int64_t)A * 6);
+    float* param = out->param ? out->param : w.param;
+    L.gemm(w.h2, 128, L.W(P + "reg.6.weight"), 128, L.W(P + "reg.6.bias"), param, 40, (int64_t)A * 6, 40, 128);
+    launch_bezier(param, L.W("__bezier_T"), L.W("__bezier_Tp"), out->reg, out->vel, out->cov_vel, A * 6, st);
+}
+
+extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* out, void* workspace,
+                            int64_t workspace_bytes, void* cuda_stream) {
+    if (!c || !bt || !out || !workspace) return fail("mind_forward: null argument");
+    if (!c->finalized) return fail("mind_forward: weights not finalized (call mind_finalize_weights)");
+    const int B = bt->n_scenes;
+    if (B <= 0 || !bt->actor_off || !bt->lane_off) return fail("mind_forward: empty batch or missing offsets");
+    if (!bt->rpe && !(bt->ctrs && bt->vecs)) return fail("mind_forward: need rpe pointers or ctrs+vecs");
+    if (!out->cls || !out->reg || !out->vel) return fail("mind_forward: cls/reg/vel outputs are required");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    const int A = bt->actor_off[B] - bt->actor_off[0];
+    const int Ltot = bt->lane_off[B] - bt->lane_off[0];
+    if (bt->actor_off[0] != 0 || bt->lane_off[0] != 0) return fail("mind_forward: offsets must start at 0");
+    int Nmax = 0;
+    std::vector<SceneDesc> sd(B);
+    std::vector<int32_t> actor_scene((size_t)std::max(A, 1));
+    for (int b = 0; b < B; ++b) {
+        const int na = bt->actor_off[b + 1] - bt->actor_off[b], nl = bt->lane_off[b + 1] - bt->lane_off[b];
+        if (na <= 0 || nl < 0) return fail("mind_forward: scene %d has %d actors / %d lanes", b, na, nl);
+        sd[b].actor_off = bt->actor_off[b]; sd[b].lane_off = bt->lane_off[b];
+        sd[b].n_actor = na; sd[b].n_lane = nl;
+        sd[b].geom_off = bt->actor_off[b] + bt->lane_off[b];
+        sd[b].pad_ = 0;
+        sd[b].rpe = bt->rpe ? bt->rpe[b] : nullptr;
+        if (bt->rpe && !bt->rpe[b]) return fail("mind_forward: rpe[%d] is null", b);
+        Nmax = std::max(Nmax, na + nl + 1);
+        for (int a = 0; a < na; ++a) actor_scene[(size_t)bt->actor_off[b] + a] = b;
+    }
+    Ws w;
+    const int64_t needb = carve(c, workspace, B, A, Ltot, Nmax, w);
+    if (needb > workspace_bytes) return fail("mind_forward: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)needb);
+    if ((((uintptr_t)workspace) & 255) != 0) return fail("mind_forward: workspace must be 256-byte aligned");
+
+    if (c->sd_cap < B) {
+        if (c->d_sd) cudaFree(c->d_sd);
+        CUDA_OK(cudaMalloc(&c->d_sd, sizeof(SceneDesc) * (size_t)B));
+        c->sd_cap = B;
+    }
+    if (c->as_cap < A) {
+        if (c->d_actor_scene) cudaFree(c->d_actor_scene);
+        CUDA_OK(cudaMalloc(&c->d_actor_scene, sizeof(int32_t) * (size_t)A));
+        c->as_cap = A;
+    }
+    CUDA_OK(cudaMemcpyAsync(c->d_sd, sd.data(), sizeof(SceneDesc) * (size_t)B, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_actor_scene, actor_scene.data(), sizeof(int32_t) * (size_t)A, cudaMemcpyHostToDevice, st));
+
+    Lin L{c, st};
+    // ---- encoders -------------------------------------------------------------------------
+    launch_actor_net(bt->actors, w.actor_feat, A, c->an, st);                               // network.py:586
+    const int64_t Lp = (int64_t)Ltot + B;
+    if (Ltot > 0)
+        CUDA_OK(cudaMemcpyAsync(w.lane_in, bt->lanes, sizeof(float) * (size_t)Ltot * 160, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(w.lane_in + (int64_t)Ltot * 160, bt->tgt_nodes, sizeof(float) * (size_t)B * 160,
+                            cudaMemcpyDeviceToDevice, st));
+    run_lane_net(c, w, Lp, st);                                                             // :587,589
+    const float* tgt_feat = w.lane_feat + (int64_t)Ltot * 128;
+    // ---- fusion ---------------------------------------------------------------------------
+    L.lin_ln_relu("fusion_net.proj_actor.", 0, w.actor_feat, 128, w.actor_p, 128, A);       // :313
+    L.lin_ln_relu("fusion_net.proj_lane.", 0, w.lane_feat, 128, w.lane_p, 128, Ltot);       // :314
+    launch_scatter_tokens(w.actor_p, w.lane_p, c->d_sd, w.x, B, Nmax, st);                  // :320-324
+    const float* Wr = L.W("fusion_net.proj_rpe_scene.0.weight");
+    const float* br = L.W("fusion_net.proj_rpe_scene.0.bias");
+    const float* gr = L.W("fusion_net.proj_rpe_scene.1.weight");
+    const float* ber = L.W("fusion_net.proj_rpe_scene.1.bias");
+    const int64_t pairs = (int64_t)Nmax * Nmax;
+    if (c->precision == MIND_PREC_FP32) {
+        const int C = chunk_for(c, B);
+        for (int b0 = 0; b0 < B; b0 += C) {
+            const int nb = std::min(C, B - b0);
+            const int64_t r0 = (int64_t)b0 * Nmax, rows = (int64_t)nb * Nmax, prow = (int64_t)nb * pairs;
+            launch_edge_init_f32(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge, b0, nb, Nmax, st);
+            for (int l = 0; l < 6; ++l) {
+                const FusionLayerW& f = c->fl[l];
+                L.gemm(w.x + r0 * 128, 128, f.Wstq, 128, f.bstq, w.stq + r0 * 384, 384, rows, 384, 128);
+                L.gemm(w.edge, 128, f.We, f.ldWe, nullptr, w.tmp, 128, prow, 128, 128);
+                launch_pair_memory_epi(w.tmp, w.stq, f.mem_g, f.mem_b, w.memory, b0, nb, Nmax, st);
+                if (f.Wpe) {
+                    L.gemm(w.memory, 128, f.Wpe, 128, f.bpe, w.tmp, 128, prow, 128, 128);
+                    launch_pair_edge_epi(w.tmp, f.pe_g, f.pe_b, f.ne_g, f.ne_b, w.edge, prow, st);
+                }
+                L.gemm(w.memory, 128, f.Wkv, 128, f.bkv, w.kv, 256, prow, 256, 128);
+                launch_pair_attention(w.kv, w.stq, c->d_sd, w.attn, b0, nb, Nmax, st);
+                run_node_post(c, f, w, r0, rows, st);
+            }
+        }
+    } else {
+        launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, st);
+        if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, w.edge16, st)) return fail("tc_prepare: %s", perr);
+        for (int l = 0; l < 6; ++l) {
+            const FusionLayerW& f = c->fl[l];
+            L.gemm(w.x, 128, f.Wstq, 128, f.bstq, w.stq, 384, (int64_t)B * Nmax, 384, 128);
+            const char* err = tc_fusion_layer(c->tc, l, w.stq, w.attn, c->sm_count, st);
+            if (err) return fail("tc_fusion_layer(%d): %s", l, err);
+            run_node_post(c, f, w, 0, (int64_t)B * Nmax, st);
+        }
+    }
+    launch_gather_tokens(w.x, c->d_sd, w.actors_f, w.cls_tok, B, Nmax, st);                 // :334-336
+    // ---- decoder --------------------------------------------------------------------------
+    run_decoder(c, w, bt, out, B, A, tgt_feat, st);
+    CUDA_OK(cudaGetLastError());
+    c->taps.clear();
+    c->taps["actor_feat"] = {w.actor_feat, (int64_t)A * 128};
+    c->taps["lane_feat"] = {w.lane_feat, Lp * 128};
+    c->taps["actors_fused"] = {w.actors_f, (int64_t)A * 128};
+    c->taps["cls_tok"] = {w.cls_tok, (int64_t)B * 128};
+    c->taps["tokens"] = {w.x, (int64_t)B * Nmax * 128};
+    return 0;
+}
+
+extern "C" int64_t mind_debug_tap(MindCtx* c, const char* name, float* dst, int64_t capacity, void* cuda_stream) {
+    if (!c || !name || !dst) { fail("mind_debug_tap: bad argument"); return -1; }
+    auto it = c->taps.find(name);
+    if (it == c->taps.end()) { fail("mind_debug_tap: unknown tap '%s'", name); return -1; }
+    if (it->second.second > capacity) { fail("mind_debug_tap: capacity %lld < %lld", (long long)capacity, (long long)it->second.second); return -1; }
+    if (cudaMemcpyAsync(dst, it->second.first, sizeof(float) * (size_t)it->second.second, cudaMemcpyDeviceToDevice,
+                        (cudaStream_t)cuda_stream) != cudaSuccess) { fail("mind_debug_tap: copy failed"); return -1; }
+    return it->second.second;
+}
+
+// bring-up / diagnostics -----------------------------------------------------------------------
+extern "C" int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host) {
+    const char* e = tc_selftest(A_host, W_host, D_host);
+    if (e) return fail("tc_selftest: %s", e);
+    return 0;
+}
+
+// synchronise the device and report a kernel-side protocol error code (0 = none)
+extern "C" int mind_sync_check(MindCtx* c) {
+    if (!c) return fail("mind_sync_check: null ctx");
+    cudaError_t e = cudaDeviceSynchronize();
+    int code = 0;
+    if (c->tc.d_err) cudaMemcpy(&code, c->tc.d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail("device error: %s (kernel code %d)", cudaGetErrorString(e), code);
+    if (code) return fail("kernel reported protocol error code %d", code);
+    return 0;
+}

@@ -1,0 +1,83 @@
+"""ctypes binding of libmind_b200.so (C ABI in include/mind_b200.h).
+
+The library is mandatory: there is no CPU or PyTorch fallback.  If it cannot be loaded the
+import of mind_b200.predictor fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmind_b200.so")
+
+PREC_FP32 = 0
+PREC_F16TC = 1
+
+
+class MindBatch(C.Structure):
+    _fields_ = [("n_scenes", C.c_int32),
+                ("actor_off", C.POINTER(C.c_int32)),
+                ("lane_off", C.POINTER(C.c_int32)),
+                ("actors", C.c_void_p),
+                ("lanes", C.c_void_p),
+                ("rpe", C.POINTER(C.c_void_p)),
+                ("ctrs", C.c_void_p),
+                ("vecs", C.c_void_p),
+                ("tgt_nodes", C.c_void_p),
+                ("tgt_rpe", C.c_void_p)]
+
+
+class MindOutputs(C.Structure):
+    _fields_ = [("cls", C.c_void_p), ("reg", C.c_void_p), ("vel", C.c_void_p),
+                ("cov_vel", C.c_void_p), ("param", C.c_void_p)]
+
+
+# every symbol include/mind_b200.h declares (tests check that all of them are exported)
+SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
+           "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
+           "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check"]
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError("libmind_b200.so not built (python -m mind_b200.build)")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    lib.mind_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.mind_create.restype = C.c_int
+    lib.mind_destroy.argtypes = [C.c_void_p]
+    lib.mind_destroy.restype = None
+    lib.mind_last_error.restype = C.c_char_p
+    lib.mind_build_info.restype = C.c_char_p
+    lib.mind_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    lib.mind_set_weight.restype = C.c_int
+    lib.mind_finalize_weights.argtypes = [C.c_void_p]
+    lib.mind_finalize_weights.restype = C.c_int
+    lib.mind_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.mind_set_option.restype = C.c_int
+    lib.mind_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.mind_workspace_bytes.restype = C.c_int64
+    lib.mind_forward.argtypes = [C.c_void_p, C.POINTER(MindBatch), C.POINTER(MindOutputs), C.c_void_p,
+                                 C.c_int64, C.c_void_p]
+    lib.mind_forward.restype = C.c_int
+    lib.mind_debug_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mind_debug_tap.restype = C.c_int64
+    lib.mind_launch_count.argtypes = [C.c_void_p]
+    lib.mind_launch_count.restype = C.c_int64
+    lib.mind_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mind_tc_selftest.restype = C.c_int
+    lib.mind_sync_check.argtypes = [C.c_void_p]
+    lib.mind_sync_check.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise RuntimeError("libmind_b200 %s failed: %s" % (what, load().mind_last_error().decode()))

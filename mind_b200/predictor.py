@@ -1,0 +1,205 @@
+"""Drop-in scene predictor: the class MIND imports by string.
+
+    net_cfg["network"] = "mind_b200.predictor:ScenePredNetB200"
+
+mirrors the call surface MINDPlanner and ScenarioTreeGenerator use on the reference's
+ScenePredNet (reference planners/mind/planner.py:42-49, planners/mind/scenario_tree.py:69-71,
+planners/mind/networks/network.py:559-606): __init__(cfg, device), load_state_dict, to, eval,
+pre_process(data) -> 7-tuple, __call__(data_in) -> (res_cls, res_reg, res_aux).
+
+All arithmetic runs in libmind_b200.so (hand-written sm_100a CUDA); torch is used for device
+memory, streams and host<->device copies only.  No CPU fallback: a non-CUDA device raises.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+_EXPECTED_CFG = dict(in_actor=14, d_actor=128, n_fpn_scale=4, in_lane=16, d_lane=128, d_rpe_in=5, d_rpe=128,
+                     d_embed=128, n_scene_layer=6, n_scene_head=8, g_num_modes=6, g_pred_len=60,
+                     param_out="bezier", update_edge=True)
+
+
+def _bezier_bases(n_order=7, n_step=60):
+    """Same construction as the reference (network.py:449-464): float64 numpy, cast to fp32."""
+    ts = np.linspace(0.0, 1.0, n_step, endpoint=True)
+    T = np.array([math.comb(n_order, i) * (1.0 - ts) ** (n_order - i) * ts ** i for i in range(n_order + 1)]).T
+    Tp = np.array([n_order * math.comb(n_order - 1, i) * (1.0 - ts) ** (n_order - 1 - i) * ts ** i
+                   for i in range(n_order)]).T
+    return np.ascontiguousarray(T, dtype=np.float32), np.ascontiguousarray(Tp, dtype=np.float32)
+
+
+def _to_device(data, device):
+    """Recursive transfer, same contract as the reference's gpu() (planners/mind/utils.py:9-20)."""
+    if isinstance(data, (list, tuple)):
+        return [_to_device(x, device) for x in data]
+    if isinstance(data, dict):
+        return {k: _to_device(v, device) for k, v in data.items()}
+    if isinstance(data, torch.Tensor):
+        return data.contiguous().to(device, non_blocking=True)
+    return data
+
+
+class ScenePredNetB200:
+    def __init__(self, cfg: Optional[dict], device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ScenePredNetB200 runs on a CUDA device only (no CPU fallback); got %s" % (self.device,))
+        if cfg is not None:
+            for k, v in _EXPECTED_CFG.items():
+                if k in cfg and cfg[k] != v:
+                    raise ValueError("unsupported net_cfg[%r]=%r (this build is specialised to %r)" % (k, cfg[k], v))
+        self.cfg = cfg
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(self._lib.mind_create(C.byref(h), idx), "mind_create")
+        self._h = h
+        self._dev_index = idx
+        self._sd: Dict[str, torch.Tensor] = {}
+        self._ws = None
+        self.training = False
+        self.precision = _lib.PREC_FP32
+
+    # ---- nn.Module-like surface used by planners/mind/planner.py:46-49 ----
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
+        for k, v in self._sd.items():
+            _lib.check(self._lib.mind_set_weight(self._h, k.encode(), C.c_void_p(v.data_ptr()), v.numel()), k)
+        T, Tp = _bezier_bases()
+        _lib.check(self._lib.mind_set_weight(self._h, b"__bezier_T", T.ctypes.data_as(C.c_void_p), T.size), "T")
+        _lib.check(self._lib.mind_set_weight(self._h, b"__bezier_Tp", Tp.ctypes.data_as(C.c_void_p), Tp.size), "Tp")
+        _lib.check(self._lib.mind_finalize_weights(self._h), "mind_finalize_weights")
+        return self
+
+    def state_dict(self):
+        return dict(self._sd)
+
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("ScenePredNetB200 cannot be moved off the GPU")
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def set_precision(self, mode: str):
+        """'fp32' = exact SIMT path; 'f16tc' = tcgen05 fp16-operand path (fp32 accumulate)."""
+        self.precision = {"fp32": _lib.PREC_FP32, "f16tc": _lib.PREC_F16TC}[mode]
+        _lib.check(self._lib.mind_set_option(self._h, b"precision", self.precision), "precision")
+        return self
+
+    def set_option(self, name: str, value: int):
+        _lib.check(self._lib.mind_set_option(self._h, name.encode(), int(value)), name)
+        return self
+
+    def launch_count(self) -> int:
+        return int(self._lib.mind_launch_count(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.mind_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- reference network.py:597-606 ----
+    def pre_process(self, data):
+        keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+        return tuple(_to_device(data[k], self.device) for k in keys)
+
+    # ---- reference network.py:582-595 ----
+    def forward(self, data):
+        packed = self.forward_packed(data)
+        cls, reg, vel, cov_vel, param, a_off = packed
+        B = cls.shape[0]
+        res_cls, res_reg, res_aux = [], [], []
+        for b in range(B):
+            s, e = a_off[b], a_off[b + 1]
+            res_cls.append(cls[b:b + 1])
+            res_reg.append(reg[s:e])
+            res_aux.append((vel[s:e], cov_vel[s:e], param[s:e].permute(1, 0, 2, 3)))
+        return res_cls, res_reg, res_aux
+
+    __call__ = forward
+
+    def _workspace(self, nbytes: int):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward_packed(self, data, geom=None):
+        """Runs the library; returns packed (cls [B,6], reg [A,6,60,5], vel [A,6,60,2],
+        cov_vel [A,6,60,3], param [A,6,8,5], actor_offsets list).  `geom` = (ctrs, vecs) device
+        tensors [sum M_b, 2] switches RPE evaluation to the device (the 'rpe' entry is ignored)."""
+        actors, actor_idcs, lanes, lane_idcs, rpe, tgt_nodes, tgt_rpe = data[:7]
+        dev = self.device
+        B = len(actor_idcs)
+        f32 = lambda t: t.to(dev, torch.float32).contiguous()
+        actors, lanes, tgt_nodes, tgt_rpe = f32(actors), f32(lanes), f32(tgt_nodes), f32(tgt_rpe)
+        a_off = [0] * (B + 1)
+        l_off = [0] * (B + 1)
+        for b in range(B):
+            a_off[b + 1] = a_off[b] + len(actor_idcs[b])
+            l_off[b + 1] = l_off[b] + len(lane_idcs[b])
+        A, L = a_off[B], l_off[B]
+        if actors.shape[0] != A or lanes.shape[0] != L:
+            raise ValueError("index lists do not cover ACTORS/LANES contiguously")
+        if tgt_nodes.shape[0] != B or tgt_rpe.reshape(B, -1).shape[1] != 20:
+            raise ValueError("TGT_NODES / TGT_RPE batch mismatch")
+        nmax = max((a_off[b + 1] - a_off[b]) + (l_off[b + 1] - l_off[b]) + 1 for b in range(B))
+        bt = _lib.MindBatch()
+        bt.n_scenes = B
+        ao = (C.c_int32 * (B + 1))(*a_off)
+        lo = (C.c_int32 * (B + 1))(*l_off)
+        bt.actor_off, bt.lane_off = ao, lo
+        bt.actors, bt.lanes = actors.data_ptr(), lanes.data_ptr() if L > 0 else 0
+        keep = []
+        if geom is not None:
+            ctrs, vecs = f32(geom[0]), f32(geom[1])
+            keep += [ctrs, vecs]
+            bt.ctrs, bt.vecs = ctrs.data_ptr(), vecs.data_ptr()
+            bt.rpe = None
+        else:
+            ptrs = (C.c_void_p * B)()
+            for b in range(B):
+                r = rpe[b]["scene"] if isinstance(rpe[b], dict) else rpe[b]
+                r = f32(r)
+                m = (a_off[b + 1] - a_off[b]) + (l_off[b + 1] - l_off[b])
+                if tuple(r.shape) != (5, m, m):
+                    raise ValueError("RPE[%d] has shape %s, expected (5,%d,%d)" % (b, tuple(r.shape), m, m))
+                keep.append(r)
+                ptrs[b] = r.data_ptr()
+            bt.rpe = ptrs
+        bt.tgt_nodes, bt.tgt_rpe = tgt_nodes.data_ptr(), tgt_rpe.data_ptr()
+        cls = torch.empty(B, 6, device=dev)
+        reg = torch.empty(A, 6, 60, 5, device=dev)
+        vel = torch.empty(A, 6, 60, 2, device=dev)
+        cov_vel = torch.empty(A, 6, 60, 3, device=dev)
+        param = torch.empty(A, 6, 8, 5, device=dev)
+        out = _lib.MindOutputs(cls.data_ptr(), reg.data_ptr(), vel.data_ptr(), cov_vel.data_ptr(), param.data_ptr())
+        need = self._lib.mind_workspace_bytes(self._h, B, A, L, nmax)
+        if need < 0:
+            _lib.check(1, "mind_workspace_bytes")
+        ws = self._workspace(need)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.mind_forward(self._h, C.byref(bt), C.byref(out), C.c_void_p(ws.data_ptr()),
+                                              ws.numel(), C.c_void_p(stream)), "mind_forward")
+        self._keep = keep   # inputs must outlive the asynchronous launches
+        return cls, reg, vel, cov_vel, param, a_off
+
+    def debug_tap(self, name: str, numel: int):
+        buf = torch.empty(numel, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        n = self._lib.mind_debug_tap(self._h, name.encode(), C.c_void_p(buf.data_ptr()), numel, C.c_void_p(stream))
+        if n < 0:
+            _lib.check(1, "mind_debug_tap")
+        return buf[:n]

@@ -1,0 +1,140 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs golden vectors from the reference and vs
+the oracle on seeded inputs.  Tolerances: exact fp32 path 2e-5; tensor-core (fp16-operand) path
+1e-3 relative (north_star), mode order bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 5e-5
+TOL_TC = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def make_net(sd, dev, prec):
+    from mind_b200.predictor import ScenePredNetB200
+    net = ScenePredNetB200(None, dev)
+    net.load_state_dict(sd)
+    net.set_precision(prec)
+    return net.to(dev).eval()
+
+
+def to_dev(data, dev):
+    a, ai, l, li, rpe, tn, tr = data
+    return (a.to(dev), [x.to(dev) for x in ai], l.to(dev), [x.to(dev) for x in li],
+            [{"scene": r["scene"].to(dev), "scene_mask": None} for r in rpe], tn.to(dev), tr.to(dev))
+
+
+def check_vs_golden(net, data, gold, tol, dev):
+    cls, reg, aux = net(to_dev(data, dev))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for b in range(len(cls)):
+        g = gold["cls_%d" % b]
+        assert tuple(cls[b].shape) == (1, 6)
+        assert np.abs(cls[b].cpu().numpy() - g).max() < max(tol, 2e-6) * 1.0
+        assert (np.argsort(-cls[b].cpu().numpy()[0]) == np.argsort(-g[0])).all(), "mode order differs"
+        for t, k in [(reg[b], "reg"), (aux[b][0], "vel"), (aux[b][1], "covvel"), (aux[b][2], "param")]:
+            assert tuple(t.shape) == gold["%s_%d" % (k, b)].shape, k
+            e = rel_err(t, gold["%s_%d" % (k, b)])
+            worst = max(worst, e)
+            assert e < tol, (k, b, e)
+    return worst
+
+
+def test_tc_selftest(dev):
+    """TMA + tcgen05 + TMEM plumbing and the software swizzle on one 128^3 product."""
+    from mind_b200 import lib
+    L = lib.load()
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 128, generator=g)
+    W = torch.randn(128, 128, generator=g)
+    D = torch.zeros(2, 128, 128)
+    rc = L.mind_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(D.data_ptr()))
+    assert rc == 0, L.mind_last_error()
+    Ah, Wh = A.half().float(), W.half().float()
+    assert torch.equal(D[1], Ah), "software swizzle does not match the TMA 128B swizzle"
+    ref = Ah.double() @ Wh.double().t()
+    assert (D[0].double() - ref).abs().max() < 1e-3 * ref.abs().max()
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", TOL_FP32), ("f16tc", TOL_TC)])
+def test_s1_golden(ckpt_sd, dev, prec, tol):
+    from mind_b200 import synth
+    net = make_net(ckpt_sd, dev, prec)
+    w = check_vs_golden(net, synth.batch_from_scenes([synth.scene_s1(1234)]), load_golden("s1_ckpt.npz"), tol, dev)
+    print("S1 %s worst rel err %.3e" % (prec, w))
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", TOL_FP32), ("f16tc", TOL_TC)])
+def test_ragged_golden(ckpt_sd, rand_sd, dev, prec, tol):
+    from oracle.make_golden import ragged_batch
+    w1 = check_vs_golden(make_net(ckpt_sd, dev, prec), ragged_batch(), load_golden("ragged_ckpt.npz"), tol, dev)
+    w2 = check_vs_golden(make_net(rand_sd, dev, prec), ragged_batch(), load_golden("ragged_rand.npz"), tol, dev)
+    print("ragged %s worst rel err ckpt %.3e rand %.3e" % (prec, w1, w2))
+
+
+def test_stage_taps_fp32(ckpt_sd, dev):
+    from mind_b200 import synth
+    gold = load_golden("s1_ckpt.npz")
+    net = make_net(ckpt_sd, dev, "fp32")
+    net(to_dev(synth.batch_from_scenes([synth.scene_s1(1234)]), dev))
+    af = net.debug_tap("actor_feat", 32 * 128).view(32, 128)
+    lf = net.debug_tap("lane_feat", 129 * 128).view(129, 128)
+    fa = net.debug_tap("actors_fused", 32 * 128).view(32, 128)
+    ct = net.debug_tap("cls_tok", 128).view(1, 128)
+    torch.cuda.synchronize()
+    assert rel_err(af, gold["actor_feat"]) < 2e-5
+    assert rel_err(lf[:128], gold["lane_feat"]) < 2e-5 and rel_err(lf[128:], gold["tgt_feat"]) < 2e-5
+    assert rel_err(fa, gold["actors"]) < TOL_FP32 and rel_err(ct, gold["cls_tok"]) < TOL_FP32
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", TOL_FP32), ("f16tc", TOL_TC)])
+def test_batch_vs_oracle_and_geom_mode(ckpt_sd, dev, prec, tol):
+    """ragged multi-scene batch vs the oracle; device-side get_rpe (ctrs/vecs) agrees with dense RPE."""
+    from mind_b200 import synth
+    from oracle.scene_pred_oracle import ScenePredOracle
+    scenes = [synth.scene_s1(300 + i, na, nl, with_geom=True) for i, (na, nl) in enumerate([(5, 20), (17, 40), (1, 3), (8, 33)])]
+    data = synth.batch_from_scenes(scenes)
+    oc, orr, oa = ScenePredOracle(ckpt_sd)(data)
+    net = make_net(ckpt_sd, dev, prec)
+    cls, reg, aux = net(to_dev(data, dev))
+    for b in range(4):
+        assert (cls[b].cpu() - oc[b]).abs().max() < max(tol, 1e-5)
+        assert rel_err(reg[b], orr[b]) < tol and rel_err(aux[b][0], oa[b][0]) < tol
+    ctrs = torch.cat([s["ctrs"] for s in scenes]).to(dev)
+    vecs = torch.cat([s["vecs"] for s in scenes]).to(dev)
+    p = net.forward_packed(to_dev(data, dev), geom=(ctrs, vecs))
+    assert rel_err(p[1], torch.cat(orr)) < tol and (p[0].cpu() - torch.cat(oc)).abs().max() < max(tol, 1e-5)
+
+
+def test_tc_vs_fp32_large(ckpt_sd, dev):
+    """config-2 shaped scenes (32 actors x 128 lanes): tensor-core path vs exact path on device."""
+    from mind_b200 import synth
+    data = to_dev(synth.batch_s2(batch=6), dev)
+    a = make_net(ckpt_sd, dev, "fp32").forward_packed(data)
+    b = make_net(ckpt_sd, dev, "f16tc").forward_packed(data)
+    torch.cuda.synchronize()
+    assert rel_err(b[1], a[1]) < TOL_TC and rel_err(b[2], a[2]) < TOL_TC
+    assert (a[0] - b[0]).abs().max() < 1e-3
+    assert torch.equal(a[0].argsort(dim=1, descending=True), b[0].argsort(dim=1, descending=True))
+
+
+def test_outputs_are_writable_views(ckpt_sd, dev):
+    """prune_merge mutates res_reg / res_vel through views (reference scenario_tree.py:323-334)."""
+    from mind_b200 import synth
+    net = make_net(ckpt_sd, dev, "fp32")
+    cls, reg, aux = net(to_dev(synth.batch_from_scenes([synth.scene_s1(1, 3, 5)]), dev))
+    reg[0][:, 0, :, :2] += 1.0
+    aux[0][0][:, 0] *= 2.0
+    assert reg[0].detach().is_cuda and aux[0][2].shape == (6, 3, 8, 5)
