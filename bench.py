@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- scene-predictions/sec (K=6 modes) of the MIND scenario-prediction hot path.
+
+Workload (BASELINE.json configs[1]): batch=256 synthetic scenes per GPU, 32 actors x 128 lane
+polylines (N=161 tokens), K=6 modes, seeded inputs (mind_b200/synth.py), weights = the reference's
+shipped checkpoint (tests/golden/weights_*.pt).  One "step" = one batched forward of the whole
+batch: encoders + 6 rela-fusion layers + decoder, outputs in the reference layout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+N>1 is launched by torchrun (one rank per GPU); every rank predicts its own 256 scenes (weak
+scaling) and the step ends with one NCCL all-gather of the decoded trajectories (configs[3]).
+`--impl reference` times the reference algorithm's CPU port (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scene-predictions/sec (K=6 modes)"
+UNIT = "scenes/s"
+NA, NL, D = 32, 128, 128
+N_TOK = NA + NL + 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def load_weights():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "weights_20240121-172745.pt"), map_location="cpu")
+
+
+def make_batch(batch, seed0):
+    from mind_b200 import synth
+    return synth.batch_s2(batch=batch, n_actor=NA, n_lane=NL, seed0=seed0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fusion_flops_per_scene(update_edge=True):
+    """canonical (concat-split) algorithmic FLOPs of the N^2 part of one layer, SURVEY.md 8d:
+    2 N^2 D^2 (3+u) + 4 N^2 D   (W_e, W_pe, K, V on N^2 rows; QK^T and PV)."""
+    u = 1 if update_edge else 0
+    return 2.0 * N_TOK * N_TOK * D * D * (3 + u) + 4.0 * N_TOK * N_TOK * D
+
+
+def fusion_bytes_per_scene(update_edge=True):
+    """fp16 edge stream: read N^2*128*2 B, write the same when the layer updates the edge."""
+    return N_TOK * N_TOK * D * 2.0 * (2 if update_edge else 1)
+
+
+def cpu_port_rate(sd, seconds_target=12.0, chunk=4, seed0=5000):
+    """Reference algorithm on the host cores: the oracle port (torch CPU, all threads), bounded
+    sample of the same workload (S2 scenes 32x128)."""
+    from oracle.scene_pred_oracle import ScenePredOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = ScenePredOracle(sd)
+    data = make_batch(chunk, seed0)
+    orc(data)   # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        orc(data)
+        n += chunk
+        el = time.perf_counter() - t0
+        if el >= seconds_target:
+            break
+    return n / el, cores, "%d S2 scenes (32 actors x 128 lanes) in %.1f s, batches of %d" % (n, el, chunk)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sd = load_weights()
+    from oracle.scene_pred_oracle import ScenePredOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = ScenePredOracle(sd)
+    per_step = 4      # bounded sample: each step predicts 4 of the 256 scenes of the workload
+    data = make_batch(per_step, 1000)
+    for _ in range(args.warmup):
+        orc(data)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc(data)
+    el = time.perf_counter() - t0
+    v = per_step * args.steps / el
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "S2: 32 actors x 128 lanes, K=6; CPU sample of %d scenes/step" % per_step},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d scenes/step x %d steps, oracle port (torch CPU fp32)" % (per_step, args.steps)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_native(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mind_b200.predictor import ScenePredNetB200
+    sd = load_weights()
+    net = ScenePredNetB200(None, dev)
+    net.load_state_dict(sd)
+    net.set_precision(args.precision)
+    B = args.batch
+    host = make_batch(B, 1000 + rank * B)
+    keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+
+    def pin(x):
+        if isinstance(x, torch.Tensor):
+            return x.pin_memory()
+        if isinstance(x, list):
+            return [pin(v) for v in x]
+        if isinstance(x, dict):
+            return {k: pin(v) for k, v in x.items()}
+        return x
+    host_dict = {k: pin(v) for k, v in zip(keys, host)}
+    data_dev = net.pre_process(host_dict)
+    torch.cuda.synchronize()
+    gather_bufs = None
+
+    def step_device():
+        out = net.forward_packed(data_dev)
+        if world > 1:
+            nonlocal gather_bufs
+            if gather_bufs is None:
+                gather_bufs = [torch.empty((world,) + tuple(t.shape), device=dev) for t in out[:3]]
+            for g, t in zip(gather_bufs, out[:3]):   # cls, reg, vel : what prune_merge consumes
+                dist.all_gather_into_tensor(g, t)
+        return out
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    net.profile(True)
+    net.profile_read()
+    l0 = net.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = net.launch_count() - l0
+    prof = net.profile_read()
+    net.profile(False)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    if args.kernel_only:      # profiling runs (ncu): device-resident leg only
+        if rank == 0:
+            print(json.dumps({"kernel_only": True, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": launches,
+                              "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- end to end through the reference-facing plugin call, host buffers in, host result out ----
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        data_in = net.pre_process(host_dict)                    # H2D of this step's inputs (pinned)
+        cls, reg, aux = net(data_in)                            # the call scenario_tree.py:71 makes
+        pk = net._last_packed
+        if out_host is None:
+            out_host = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in pk[:3]]
+        for h, d in zip(out_host, pk[:3]):
+            h.copy_(d, non_blocking=True)                       # D2H of cls, reg, vel
+        if world > 1:
+            for g, x in zip(gather_bufs, pk[:3]):
+                dist.all_gather_into_tensor(g, x)
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1)
+    t = torch.tensor([ms2], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t.item())
+    e2e = world * B * args.steps / (ms2 * 1e-3)
+    h2d = sum(x.numel() * 4 for x in (host[0], host[2], host[5], host[6])) + sum(r["scene"].numel() * 4 for r in host[4])
+    d2h = sum(x.numel() * 4 for x in out_host)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    f_ms, f_n = prof.get("fusion_tc", (0.0, 0))
+    roof = None
+    if f_n:
+        per_launch_s = f_ms / f_n * 1e-3
+        flops = B * fusion_flops_per_scene(True)
+        ach = flops / per_launch_s / 1e12
+        hb = B * fusion_bytes_per_scene(True) / per_launch_s / 1e9
+        roof = {"kernel": "k_rela_fusion_tc (layers 0-4)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
+                "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + ", sustained bf16/fp16 dense",
+                "ms_per_launch": f_ms / f_n, "launches_timed": f_n,
+                "hbm_algorithmic_gbs": hb, "hbm_frac_of_measured": hb / pk["hbm"],
+                "flops_per_launch": flops, "bytes_per_launch": B * fusion_bytes_per_scene(True)}
+    cpu_v, cores, sample = cpu_port_rate(sd)
+    stage_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16" if args.precision == "f16tc" else "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch=%d synthetic scenes per GPU, 32 actors x 128 lane polylines, K=6" % B,
+                       "global_batch": world * B, "precision": args.precision,
+                       "l2": "inputs larger than L2 (fp16 edge stream %.2f GB per step)" % (B * N_TOK * N_TOK * 256 / 1e9),
+                       "collective": "all_gather(cls,reg,vel) per step" if world > 1 else "none",
+                       "weights": "reference checkpoint 20240121-172745"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms2 / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "stage_ms_per_step": stage_ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precision", default="f16tc", choices=["f16tc", "fp32"])
+    ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (for ncu runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,7 @@ const char* mind_build_info(void);
 int mind_set_weight(MindCtx* ctx, const char* key, const float* host, int64_t numel);
 int mind_finalize_weights(MindCtx* ctx);
 
-/* options: "precision" (MIND_PREC_*), "chunk_scenes" (exact path workspace bound) */
+/* options: "precision" (MIND_PREC_*), "chunk_scenes" (exact path workspace bound), "profile" (0/1) */
 int mind_set_option(MindCtx* ctx, const char* name, int64_t value);
 
 /* ---- one batched forward:  network(data_in)   planners/mind/networks/network.py:582-595 ----
@@ -118,6 +118,12 @@ int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host);
 
 /* cudaDeviceSynchronize + kernel-side protocol error flag (0 = clean) */
 int mind_sync_check(MindCtx* ctx);
+
+/* per-stage device timing: with option "profile"=1 every forward records CUDA events around its
+ * stages on the caller's stream; this call synchronises and drains them as text lines
+ * "tag total_ms count" (tags: actor_net lane_net tokens edge_init node_pre fusion_tc
+ * fusion_tc_last node_post fusion_other decoder). */
+int mind_profile_read(MindCtx* ctx, char* buf, int64_t capacity);
 
 /* number of kernels the library launched since creation (bench.py's gpu_launches) */
 int64_t mind_launch_count(MindCtx* ctx);

@@ -38,7 +38,23 @@ struct FusionLayerW {
     const float *Wo, *bo, *n2_g, *n2_b, *W1, *b1, *W2, *b2, *n3_g, *n3_b;
 };
 
+// CUDA-event ranges per stage tag, recorded on the caller's stream when option "profile" is on
+struct Profiler {
+    bool on = false;
+    std::map<std::string, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> ranges;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    cudaEvent_t begin(cudaStream_t st) { cudaEvent_t e = get(); cudaEventRecord(e, st); return e; }
+    void end(const char* tag, cudaEvent_t b, cudaStream_t st) { cudaEvent_t e = get(); cudaEventRecord(e, st); ranges[tag].push_back({b, e}); }
+};
+#define PROF_BEGIN() cudaEvent_t pb_ = c->prof.on ? c->prof.begin(st) : nullptr
+#define PROF_NEXT(tag) do { if (c->prof.on) { c->prof.end(tag, pb_, st); pb_ = c->prof.begin(st); } } while (0)
+
 struct MindCtx {
+    Profiler prof;
     int device = 0;
     std::map<std::string, std::vector<float>> host_w;
     float* arena = nullptr;
@@ -101,6 +117,8 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
     if (!strcmp(name, "precision")) {
         if (value != MIND_PREC_FP32 && value != MIND_PREC_F16TC) return fail("precision must be 0 or 1");
         c->precision = (int)value;
+    } else if (!strcmp(name, "profile")) {
+        c->prof.on = value != 0;
     } else if (!strcmp(name, "chunk_scenes")) {
         if (value < 1) return fail("chunk_scenes must be >= 1");
         c->chunk_scenes = (int)value;
@@ -538,14 +556,17 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     CUDA_OK(cudaMemcpyAsync(c->d_actor_scene, actor_scene.data(), sizeof(int32_t) * (size_t)A, cudaMemcpyHostToDevice, st));
 
     Lin L{c, st};
+    PROF_BEGIN();
     // ---- encoders -------------------------------------------------------------------------
     launch_actor_net(bt->actors, w.actor_feat, A, c->an, st);                               // network.py:586
+    PROF_NEXT("actor_net");
     const int64_t Lp = (int64_t)Ltot + B;
     if (Ltot > 0)
         CUDA_OK(cudaMemcpyAsync(w.lane_in, bt->lanes, sizeof(float) * (size_t)Ltot * 160, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemcpyAsync(w.lane_in + (int64_t)Ltot * 160, bt->tgt_nodes, sizeof(float) * (size_t)B * 160,
                             cudaMemcpyDeviceToDevice, st));
     run_lane_net(c, w, Lp, st);                                                             // :587,589
+    PROF_NEXT("lane_net");
     const float* tgt_feat = w.lane_feat + (int64_t)Ltot * 128;
     // ---- fusion ---------------------------------------------------------------------------
     L.lin_ln_relu("fusion_net.proj_actor.", 0, w.actor_feat, 128, w.actor_p, 128, A);       // :313
@@ -556,6 +577,7 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     const float* gr = L.W("fusion_net.proj_rpe_scene.1.weight");
     const float* ber = L.W("fusion_net.proj_rpe_scene.1.bias");
     const int64_t pairs = (int64_t)Nmax * Nmax;
+    PROF_NEXT("tokens");
     if (c->precision == MIND_PREC_FP32) {
         const int C = chunk_for(c, B);
         for (int b0 = 0; b0 < B; b0 += C) {
@@ -579,17 +601,24 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     } else {
         launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, st);
         if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, w.edge16, st)) return fail("tc_prepare: %s", perr);
+        PROF_NEXT("edge_init");
         for (int l = 0; l < 6; ++l) {
             const FusionLayerW& f = c->fl[l];
             L.gemm(w.x, 128, f.Wstq, 128, f.bstq, w.stq, 384, (int64_t)B * Nmax, 384, 128);
+            PROF_NEXT("node_pre");
             const char* err = tc_fusion_layer(c->tc, l, w.stq, w.attn, c->sm_count, st);
             if (err) return fail("tc_fusion_layer(%d): %s", l, err);
+            PROF_NEXT(l < 5 ? "fusion_tc" : "fusion_tc_last");
             run_node_post(c, f, w, 0, (int64_t)B * Nmax, st);
+            PROF_NEXT("node_post");
         }
     }
     launch_gather_tokens(w.x, c->d_sd, w.actors_f, w.cls_tok, B, Nmax, st);                 // :334-336
+    PROF_NEXT("fusion_other");
     // ---- decoder --------------------------------------------------------------------------
     run_decoder(c, w, bt, out, B, A, tgt_feat, st);
+    PROF_NEXT("decoder");
+    if (c->prof.on && pb_) c->prof.pool.push_back(pb_);
     CUDA_OK(cudaGetLastError());
     c->taps.clear();
     c->taps["actor_feat"] = {w.actor_feat, (int64_t)A * 128};
@@ -625,5 +654,31 @@ extern "C" int mind_sync_check(MindCtx* c) {
     if (c->tc.d_err) cudaMemcpy(&code, c->tc.d_err, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail("device error: %s (kernel code %d)", cudaGetErrorString(e), code);
     if (code) return fail("kernel reported protocol error code %d", code);
+    return 0;
+}
+
+// Drain the CUDA-event ranges recorded since the last call (option "profile" = 1).  Writes a
+// text table "tag total_ms count\n" into buf; synchronises the device.
+extern "C" int mind_profile_read(MindCtx* c, char* buf, int64_t cap) {
+    if (!c || !buf || cap <= 0) return fail("mind_profile_read: bad argument");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail("mind_profile_read: %s", cudaGetErrorString(e));
+    std::string out;
+    for (auto& kv : c->prof.ranges) {
+        double tot = 0;
+        for (auto& pr : kv.second) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            tot += ms;
+            c->prof.pool.push_back(pr.first);
+            c->prof.pool.push_back(pr.second);
+        }
+        char line[160];
+        snprintf(line, sizeof line, "%s %.6f %zu\n", kv.first.c_str(), tot, kv.second.size());
+        out += line;
+    }
+    c->prof.ranges.clear();
+    if ((int64_t)out.size() + 1 > cap) return fail("mind_profile_read: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }

@@ -34,7 +34,7 @@ class MindOutputs(C.Structure):
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
-           "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check"]
+           "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check", "mind_profile_read"]
 
 _lib = None
 
@@ -74,6 +74,8 @@ def load(build_if_missing: bool = True):
     lib.mind_tc_selftest.restype = C.c_int
     lib.mind_sync_check.argtypes = [C.c_void_p]
     lib.mind_sync_check.restype = C.c_int
+    lib.mind_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.mind_profile_read.restype = C.c_int
     _lib = lib
     return lib
 

@@ -98,6 +98,22 @@ class ScenePredNetB200:
         _lib.check(self._lib.mind_set_option(self._h, name.encode(), int(value)), name)
         return self
 
+    def profile(self, on: bool = True):
+        return self.set_option("profile", 1 if on else 0)
+
+    def profile_read(self) -> dict:
+        """{tag: (total_ms, count)} of the stage ranges recorded since the last call (synchronises)."""
+        buf = C.create_string_buffer(8192)
+        _lib.check(self._lib.mind_profile_read(self._h, buf, 8192), "mind_profile_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, ms, n = line.split()
+            out[tag] = (float(ms), int(n))
+        return out
+
+    def sync_check(self):
+        _lib.check(self._lib.mind_sync_check(self._h), "mind_sync_check")
+
     def launch_count(self) -> int:
         return int(self._lib.mind_launch_count(self._h))
 
@@ -117,6 +133,7 @@ class ScenePredNetB200:
     # ---- reference network.py:582-595 ----
     def forward(self, data):
         packed = self.forward_packed(data)
+        self._last_packed = packed
         cls, reg, vel, cov_vel, param, a_off = packed
         B = cls.shape[0]
         res_cls, res_reg, res_aux = [], [], []
