@@ -110,11 +110,18 @@ def fusion_bytes_per_scene(update_edge=True):
     return N_TOK * N_TOK * D * 2.0 * (2 if update_edge else 1)
 
 
-def cpu_port_rate(sd, seconds_target=12.0, chunk=4, seed0=5000):
+def cpu_threads():
+    """Threads for the CPU port.  torch's intra-op pool degrades badly past ~16 threads on this
+    workload (measured on the 128-core GPU-box host: 128 threads -> 0.03 scenes/s, 32 s/scene),
+    so the port uses min(host cores, 16) and reports that number as `cores`."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("MIND_CPU_THREADS", "16"))))
+
+
+def cpu_port_rate(sd, seconds_target=10.0, chunk=2, seed0=5000):
     """Reference algorithm on the host cores: the oracle port (torch CPU, all threads), bounded
     sample of the same workload (S2 scenes 32x128)."""
     from oracle.scene_pred_oracle import ScenePredOracle
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     orc = ScenePredOracle(sd)
     data = make_batch(chunk, seed0)
@@ -135,7 +142,7 @@ def run_reference(args):
         return
     sd = load_weights()
     from oracle.scene_pred_oracle import ScenePredOracle
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     orc = ScenePredOracle(sd)
     per_step = 4      # bounded sample: each step predicts 4 of the 256 scenes of the workload
