@@ -1,0 +1,214 @@
+// ActorNet (reference planners/mind/networks/network.py:12-61, layers.py:36-60,140-188) as a chain
+// of tensor-core GEMMs.  Activations are channel-last, zero-padded in time, stored as an fp16
+// (hi, lo) pair; a k=3 conv reads its [3*C] im2col rows as overlapping TMA windows of that buffer.
+// GroupNorm(1 group): the GEMM epilogue emits per-actor partial sums, the apply kernel normalises,
+// adds the shortcut, applies ReLU and re-splits to fp16 hi/lo for the next conv.
+#include "tc_gemm.h"
+#include <cuda_fp16.h>
+#include <cstdio>
+
+namespace mind {
+
+namespace {
+struct Carve {
+    char* base; int64_t off = 0;
+    template <typename T> T* take(int64_t n) {
+        off = (off + 255) & ~int64_t(255);
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * (int64_t)sizeof(T);
+        return p;
+    }
+};
+struct HL { __half* hi; __half* lo; };
+struct Bufs {
+    HL x0, t0, t1, o[4], p;              // padded channel-last activations
+    __half* slack[20]; int n_slack;      // tails that overlapping windows may read (kept finite: zeroed)
+    float *raw1, *raw2, *raw3, *st1, *st2, *st3, *pyr0, *pyr1, *lat, *outf;
+};
+int64_t carve(void* ws, int A, Bufs& b) {
+    Carve c{(char*)ws};
+    const int64_t slack = 1024;   // windows of the last rows may read past the end (zero weights)
+    b.n_slack = 0;
+    auto hl = [&](int64_t per) {
+        HL h;
+        h.hi = c.take<__half>(A * per + slack); h.lo = c.take<__half>(A * per + slack);
+        if (ws) { b.slack[b.n_slack++] = h.hi + A * per; b.slack[b.n_slack++] = h.lo + A * per; }
+        return h;
+    };
+    b.x0 = hl(50 * 16);
+    b.t0 = hl(50 * 128); b.t1 = hl(50 * 128);
+    b.o[0] = hl(50 * 32); b.o[1] = hl(26 * 64); b.o[2] = hl(14 * 128); b.o[3] = hl(8 * 256);
+    b.p = hl(50 * 128);
+    b.raw1 = c.take<float>((int64_t)A * 6144); b.raw2 = c.take<float>((int64_t)A * 6144); b.raw3 = c.take<float>((int64_t)A * 6144);
+    b.st1 = c.take<float>((int64_t)A * 6); b.st2 = c.take<float>((int64_t)A * 6); b.st3 = c.take<float>((int64_t)A * 6);
+    b.pyr0 = c.take<float>((int64_t)A * 6144); b.pyr1 = c.take<float>((int64_t)A * 6144);
+    b.lat = c.take<float>((int64_t)A * 6144); b.outf = c.take<float>((int64_t)A * 6144);
+    return (c.off + 255) & ~int64_t(255);
+}
+char g_aerr[256];
+
+__global__ void k_last_step(const float* __restrict__ x, float* __restrict__ out, int A, int L, int C) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)A * C) return;
+    const int a = (int)(idx / C), c = (int)(idx % C);
+    out[idx] = x[((int64_t)a * L + (L - 1)) * C + c];
+}
+}  // namespace
+
+int64_t actor_tc_ws_bytes(int A) { Bufs b; return carve(nullptr, std::max(A, 1), b); }
+
+void actor_tc_free(ActorTc& a) {
+    for (auto& kv : a.conv) if (kv.second.W) cudaFree(kv.second.W);
+    a.conv.clear();
+    if (a.d_err) cudaFree(a.d_err);
+    a.d_err = nullptr; a.ready = false;
+}
+
+const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<float>>& host,
+                          const std::map<std::string, const float*>& dev) {
+    actor_tc_free(a);
+    auto add = [&](const std::string& key, int Cout, int Cin, int Cin_pad, int ks) -> const char* {
+        auto it = host.find(key);
+        if (it == host.end() || it->second.size() != (size_t)Cout * Cin * ks) return "actor_tc_pack: missing / mis-sized conv weight";
+        ActorTcConv cv;
+        cv.Cout = Cout; cv.Cin_pad = Cin_pad; cv.ksize = ks;
+        cv.Kpad = ((ks * Cin_pad + 63) / 64) * 64;
+        std::vector<__half> W((size_t)Cout * 2 * cv.Kpad, __float2half(0.f));
+        for (int o = 0; o < Cout; ++o)
+            for (int i = 0; i < Cin; ++i)
+                for (int k = 0; k < ks; ++k) {
+                    const float w = it->second[((size_t)o * Cin + i) * ks + k];
+                    const __half h = __float2half_rn(w);
+                    const size_t kk = (size_t)k * Cin_pad + i;
+                    W[(size_t)o * 2 * cv.Kpad + kk] = h;
+                    W[(size_t)o * 2 * cv.Kpad + cv.Kpad + kk] = __float2half_rn(w - __half2float(h));
+                }
+        if (cudaMalloc(&cv.W, W.size() * sizeof(__half)) != cudaSuccess) return "actor_tc_pack: cudaMalloc failed";
+        cudaMemcpy(cv.W, W.data(), W.size() * sizeof(__half), cudaMemcpyHostToDevice);
+        if (const char* e = tcg_encode_w(cv.wmap, cv.W, 2 * cv.Kpad, Cout, Cout)) return e;
+        a.conv[key] = cv;
+        return nullptr;
+    };
+    const int Cg[4] = {32, 64, 128, 256};
+    int cin = 14, cinp = 16;
+    for (int g = 0; g < 4; ++g) {
+        char p[64];
+        snprintf(p, sizeof p, "actor_net.groups.%d.", g);
+        std::string P(p);
+        const char* e;
+        if ((e = add(P + "0.conv1.weight", Cg[g], cin, cinp, 3))) return e;
+        if ((e = add(P + "0.conv2.weight", Cg[g], Cg[g], Cg[g], 3))) return e;
+        if ((e = add(P + "0.downsample.0.weight", Cg[g], cin, cinp, 1))) return e;
+        if ((e = add(P + "1.conv1.weight", Cg[g], Cg[g], Cg[g], 3))) return e;
+        if ((e = add(P + "1.conv2.weight", Cg[g], Cg[g], Cg[g], 3))) return e;
+        snprintf(p, sizeof p, "actor_net.lateral.%d.conv.weight", g);
+        if ((e = add(p, 128, Cg[g], Cg[g], 3))) return e;
+        cin = cinp = Cg[g];
+    }
+    if (const char* e = add("actor_net.output.conv1.weight", 128, 128, 128, 3)) return e;
+    if (const char* e = add("actor_net.output.conv2.weight", 128, 128, 128, 3)) return e;
+    for (auto& kv : dev)
+        if (kv.first.rfind("actor_net.", 0) == 0 && kv.first.find('#') == std::string::npos) a.vec[kv.first] = kv.second;
+    if (cudaMalloc(&a.d_err, sizeof(int)) != cudaSuccess) return "actor_tc_pack: cudaMalloc(err) failed";
+    cudaMemset(a.d_err, 0, sizeof(int));
+    a.ready = true;
+    return nullptr;
+}
+
+const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float* out, int sm_count, cudaStream_t st) {
+    if (!a.ready) return "actor_tc_run: weights not packed";
+    if (A <= 0) return nullptr;
+    Bufs b;
+    carve(ws, A, b);
+    const char* err = nullptr;
+    auto V = [&](const std::string& k) -> const float* {
+        auto it = a.vec.find(k);
+        if (it == a.vec.end()) { snprintf(g_aerr, sizeof g_aerr, "actor_tc_run: missing %s", k.c_str()); err = g_aerr; return nullptr; }
+        return it->second;
+    };
+    // conv over a padded channel-last input [A][Lin+2][Cin_pad]: output raw [A*Lout][Cout] + stats
+    auto conv = [&](const std::string& key, HL in, int Lin, int stride, float* raw, float* stats) {
+        if (err) return;
+        auto it = a.conv.find(key);
+        if (it == a.conv.end()) { err = "actor_tc_run: unknown conv"; return; }
+        const ActorTcConv& cv = it->second;
+        const int Lout = (Lin - 1) / stride + 1;
+        const int r_in = Lout >= 48 ? 16 : Lout / 3;     // 48->16, 24->8, 12->4, 6->2 : always 3 inner tiles
+        const int r_out = 128 / r_in;
+        const int C = cv.Cin_pad;
+        // k=3: window starts at padded row t*stride (original t*stride-1); k=1: padded row t*stride+1
+        const int64_t base_off = (cv.ksize == 1) ? C : 0;
+        alignas(64) unsigned char mh[128], ml[128];
+        if ((err = tcg_encode_a(mh, in.hi + base_off, cv.Kpad, Lout, A, (int64_t)stride * C, (int64_t)(Lin + 2) * C, r_in, r_out))) return;
+        if ((err = tcg_encode_a(ml, in.lo + base_off, cv.Kpad, Lout, A, (int64_t)stride * C, (int64_t)(Lin + 2) * C, r_in, r_out))) return;
+        TcGemm g;
+        g.amap_hi = mh; g.amap_lo = ml; g.wmap = cv.wmap; g.split = 1; g.k_blocks = cv.Kpad / 64;
+        g.r_in = r_in; g.r_out = r_out; g.L_inner = Lout; g.n_outer = A;
+        g.N = cv.Cout; g.n_tile = cv.Cout; g.C = raw; g.ldc = cv.Cout; g.stats = stats; g.err = a.d_err;
+        err = tcg_launch(g, sm_count, st);
+    };
+    auto apply = [&](const float* raw, const float* stats, const std::string& gk, int L, int C, int relu, HL out_hl, float* out_f32,
+                     const float* res_raw = nullptr, const float* res_stats = nullptr, const std::string& rk = "",
+                     const HL* res_hl = nullptr) {
+        if (err) return;
+        TcApply q;
+        q.raw = raw; q.stats = stats; q.gamma = V(gk + ".weight"); q.beta = V(gk + ".bias");
+        if (res_raw) { q.res_raw = res_raw; q.res_stats = res_stats; q.res_gamma = V(rk + ".weight"); q.res_beta = V(rk + ".bias"); }
+        if (res_hl) { q.res_hi = res_hl->hi; q.res_lo = res_hl->lo; }
+        q.out_hi = out_hl.hi; q.out_lo = out_hl.lo; q.out_f32 = out_f32;
+        q.A = A; q.L = L; q.C = C; q.relu = relu;
+        if (!err) tcg_gn_apply(q, st);
+    };
+    const HL none{nullptr, nullptr};
+
+    for (int i = 0; i < b.n_slack; ++i) cudaMemsetAsync(b.slack[i], 0, 1024 * sizeof(__half), st);
+    tcg_actor_prep(actors, b.x0.hi, b.x0.lo, A, st);
+    const int Cg[4] = {32, 64, 128, 256};
+    HL cur = b.x0;
+    int L = 48;
+    for (int g = 0; g < 4 && !err; ++g) {
+        char p[64];
+        snprintf(p, sizeof p, "actor_net.groups.%d.", g);
+        const std::string P(p);
+        const int stride = g == 0 ? 1 : 2, Lo = (L - 1) / stride + 1, C = Cg[g];
+        // block 0 (with conv shortcut)
+        conv(P + "0.conv1.weight", cur, L, stride, b.raw1, b.st1);
+        apply(b.raw1, b.st1, P + "0.bn1", Lo, C, 1, b.t0, nullptr);
+        conv(P + "0.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
+        conv(P + "0.downsample.0.weight", cur, L, stride, b.raw3, b.st3);
+        apply(b.raw2, b.st2, P + "0.bn2", Lo, C, 1, b.t1, nullptr, b.raw3, b.st3, P + "0.downsample.1");
+        // block 1 (identity shortcut)
+        conv(P + "1.conv1.weight", b.t1, Lo, 1, b.raw1, b.st1);
+        apply(b.raw1, b.st1, P + "1.bn1", Lo, C, 1, b.t0, nullptr);
+        conv(P + "1.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
+        apply(b.raw2, b.st2, P + "1.bn2", Lo, C, 1, b.o[g], nullptr, nullptr, nullptr, "", &b.t1);
+        cur = b.o[g];
+        L = Lo;
+    }
+    // FPN top-down
+    const int Ls[4] = {48, 24, 12, 6};
+    conv("actor_net.lateral.3.conv.weight", b.o[3], 6, 1, b.raw1, b.st1);
+    apply(b.raw1, b.st1, "actor_net.lateral.3.norm", 6, 128, 0, none, b.pyr0);
+    float* pyr = b.pyr0; float* nxt = b.pyr1;
+    for (int i = 2; i >= 0 && !err; --i) {
+        char p[64];
+        snprintf(p, sizeof p, "actor_net.lateral.%d", i);
+        conv(std::string(p) + ".conv.weight", b.o[i], Ls[i], 1, b.raw1, b.st1);
+        apply(b.raw1, b.st1, std::string(p) + ".norm", Ls[i], 128, 0, none, b.lat);
+        if (!err) tcg_fpn_up_add(pyr, b.lat, nxt, i == 0 ? b.p.hi : nullptr, i == 0 ? b.p.lo : nullptr, A, Ls[i], 128, st);
+        float* t = pyr; pyr = nxt; nxt = t;
+    }
+    // output Res1d(128,128), identity shortcut = the pyramid top; keep the last time step only
+    conv("actor_net.output.conv1.weight", b.p, 48, 1, b.raw1, b.st1);
+    apply(b.raw1, b.st1, "actor_net.output.bn1", 48, 128, 1, b.t0, nullptr);
+    conv("actor_net.output.conv2.weight", b.t0, 48, 1, b.raw2, b.st2);
+    apply(b.raw2, b.st2, "actor_net.output.bn2", 48, 128, 1, none, b.outf, nullptr, nullptr, "", &b.p);
+    if (!err) {
+        const int64_t n = (int64_t)A * 128;
+        k_last_step<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.outf, out, A, 48, 128);
+        ++g_launches;
+    }
+    return err;
+}
+
+}  // namespace mind

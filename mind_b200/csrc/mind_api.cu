@@ -4,6 +4,7 @@
 #include "../../include/mind_b200.h"
 #include "kernels.h"
 #include "fusion_tc.h"
+#include "tc_gemm.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -66,6 +67,7 @@ struct MindCtx {
     ActorNetWeights an{};
     FusionLayerW fl[6]{};
     TcWeights tc{};               // fp16 packed weights / per-layer params for the tensor-core path
+    ActorTc actor_tc{};           // ActorNet on the tensor-core GEMM engine
     // descriptor tables
     SceneDesc* d_sd = nullptr; int sd_cap = 0;
     int32_t* d_actor_scene = nullptr; int as_cap = 0;
@@ -102,6 +104,7 @@ extern "C" void mind_destroy(MindCtx* c) {
     if (c->d_sd) cudaFree(c->d_sd);
     if (c->d_actor_scene) cudaFree(c->d_actor_scene);
     tc_free(c->tc);
+    actor_tc_free(c->actor_tc);
     delete c;
 }
 
@@ -303,6 +306,8 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
         }
         const char* err = tc_pack_weights(c->tc, hl);
         if (err) return fail("tc_pack_weights: %s", err);
+        err = actor_tc_pack(c->actor_tc, c->host_w, c->dev_w);
+        if (err) return fail("actor_tc_pack: %s", err);
     }
     c->finalized = true;
     return 0;
@@ -335,6 +340,7 @@ struct Ws {
     float *edge, *tmp, *memory, *kv;
     // tensor-core path
     __half* edge16;
+    char* actor_ws;
     // decoder
     float *actors_f, *cls_tok, *tr, *tg1, *tgt, *c1, *ce, *qkv, *att, *co, *f1, *f2, *a1, *ae, *embed, *h1, *h2, *param;
     float *k1, *k2, *logit;
@@ -368,9 +374,11 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w
         w.memory = cv.take<float>(C * pairs * 128);
         w.kv = cv.take<float>(C * pairs * 256);
         w.edge16 = nullptr;
+        w.actor_ws = nullptr;
     } else {
         w.edge = w.tmp = w.memory = w.kv = nullptr;
         w.edge16 = cv.take<__half>((int64_t)B * pairs * 128);
+        w.actor_ws = cv.take<char>(actor_tc_ws_bytes(A));
     }
     w.actors_f = cv.take<float>((int64_t)A * 128);
     w.cls_tok = cv.take<float>((int64_t)B * 128);
@@ -558,7 +566,12 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     Lin L{c, st};
     PROF_BEGIN();
     // ---- encoders -------------------------------------------------------------------------
-    launch_actor_net(bt->actors, w.actor_feat, A, c->an, st);                               // network.py:586
+    if (c->precision == MIND_PREC_F16TC) {                                                  // network.py:586
+        if (const char* e = actor_tc_run(c->actor_tc, bt->actors, A, w.actor_ws, w.actor_feat, c->sm_count, st))
+            return fail("actor_tc_run: %s", e);
+    } else {
+        launch_actor_net(bt->actors, w.actor_feat, A, c->an, st);
+    }
     PROF_NEXT("actor_net");
     const int64_t Lp = (int64_t)Ltot + B;
     if (Ltot > 0)

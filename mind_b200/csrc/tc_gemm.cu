@@ -1,0 +1,444 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:
+//     C[rows, N] (fp32) = sum_terms A_t[rows, K] . W_t[N, K]^T (+bias) (ReLU)  [+ per-group sum / sum^2]
+// A operands are fp16 K-major and arrive through rank-3 TMA tensor maps {K, inner, outer}; the
+// (inner, outer) box is 128 rows, which lets a conv1d(k=3) read its im2col rows straight out of a
+// channel-last zero-padded activation buffer as OVERLAPPING windows (row stride = C elements) --
+// no im2col pass.  With n_terms = 3 the product is evaluated as hi.hi + lo.hi + hi.lo of an
+// (fp16 hi, fp16 lo) split of both operands: fp32-equivalent accuracy (2^-22) at 3 MMAs, fp32
+// accumulation in TMEM.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+// (TMEM -> registers -> global), 4-stage smem ring, two TMEM accumulators.
+#include "tc_gemm.h"
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace mind {
+namespace tcg {
+
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr uint32_t STAGE_A = 16384, STAGE_W = 32768, STAGE = STAGE_A + STAGE_W;
+constexpr uint32_t SM_BAR = kStages * STAGE;
+constexpr uint32_t SM_TMEM = SM_BAR + 128;
+constexpr uint32_t SMEM_BYTES = SM_TMEM + 16 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+#define TCG_LD_X32(taddr, r)                                                                                       \
+    asm volatile(                                                                                                  \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                  \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"  \
+        "%28,%29,%30,%31}, [%32];"                                                                                 \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),         \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),   \
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])  \
+        : "r"(taddr) : "memory")
+
+struct Args {
+    int n_terms, k_blocks;
+    int a_sel[3], w_k_off[3];
+    int tiles_inner, tiles_outer, tiles_n;
+    int r_in, r_out;
+    int L_inner, n_outer;
+    int N, n_tile;
+    float* C; int ldc;
+    const float* bias; int relu;
+    float* stats;
+    int* err;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
+          const __grid_constant__ CUtensorMap wmap, Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
+    const uint32_t bars = sbase + SM_BAR;
+    // full[s] = bars + 8 s ; empty[s] = bars + 32 + 8 s ; tmem_full[a] = bars + 64 + 8 a ; tmem_empty[a] = bars + 80 + 8 a
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 32 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bars + 64 + 8 * a, 1); mbar_init(bars + 80 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_TMEM), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sTmem;
+    const int total_tiles = g.tiles_outer * g.tiles_inner * g.tiles_n;
+    const int nq = g.n_terms * g.k_blocks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % g.tiles_n; const int rest = tile / g.tiles_n;
+                const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
+                for (int q = 0; q < nq; ++q) {
+                    const int term = q / g.k_blocks, kb = q - term * g.k_blocks;
+                    mbar_wait(bars + 32 + 8 * stage, phase ^ 1, g.err, 11);
+                    const uint32_t full = bars + 8 * stage;
+                    mbar_expect_tx(full, STAGE_A + (uint32_t)g.n_tile * 128u);
+                    const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+                    tma_load_3d(sA, g.a_sel[term] ? &amap1 : &amap0, full, kb * 64, c * g.r_in, o * g.r_out);
+                    tma_load_2d(sW, &wmap, full, g.w_k_off[term] + kb * 64, nt * g.n_tile);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t idesc = umma_idesc_f16(g.n_tile);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(bars + 80 + 8 * acc, acc_phase ^ 1, g.err, 12);
+                tc_fence_after();
+                for (int q = 0; q < nq; ++q) {
+                    mbar_wait(bars + 8 * stage, phase, g.err, 13);
+                    tc_fence_after();
+                    const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sW + kk * 32), idesc,
+                                 (q | kk) != 0);
+                    umma_commit(bars + 32 + 8 * stage);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bars + 64 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        int acc = 0; uint32_t acc_phase = 0;
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % g.tiles_n; const int rest = tile / g.tiles_n;
+            const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
+            const int outer = o * g.r_out + row / g.r_in, inner = c * g.r_in + row % g.r_in;
+            const bool valid = outer < g.n_outer && inner < g.L_inner;
+            float* crow = g.C + ((int64_t)outer * g.L_inner + inner) * g.ldc;
+            mbar_wait(bars + 64 + 8 * acc, acc_phase, g.err, 14);
+            tc_fence_after();
+            float s1 = 0.f, s2 = 0.f;
+            for (int n0 = 0; n0 < g.n_tile; n0 += 32) {
+                uint32_t r[32];
+                TCG_LD_X32(tmem + lane_base + acc * 256 + n0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int nb = nt * g.n_tile + n0;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int n = nb + k4 * 4 + e;
+                        float x = __uint_as_float(r[k4 * 4 + e]);
+                        if (n < g.N) {
+                            if (g.bias) x += __ldg(g.bias + n);
+                            if (g.relu) x = fmaxf(x, 0.f);
+                            s1 += x; s2 += x * x;
+                        }
+                        v[e] = x;
+                    }
+                    if (valid) {
+                        const int n = nb + k4 * 4;
+                        if (n + 3 < g.N && ((g.ldc & 3) == 0)) {
+                            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (n + e < g.N) crow[n + e] = v[e];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 80 + 8 * acc);
+            if (g.stats) {   // per-(outer, inner tile) partial sums; r_in is a power of two <= 32
+                if (!valid) { s1 = 0.f; s2 = 0.f; }
+                for (int off = g.r_in >> 1; off > 0; off >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                }
+                if ((row % g.r_in) == 0 && outer < g.n_outer) {
+                    float* sp = g.stats + ((int64_t)outer * g.tiles_inner + c) * 2;
+                    sp[0] = s1; sp[1] = s2;
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise companions of the conv GEMMs (channel-last, zero-padded fp16 hi/lo activations)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, int64_t idx, float x) {
+    const __half h = __float2half_rn(x);
+    hi[idx] = h;
+    lo[idx] = __float2half_rn(x - __half2float(h));
+}
+
+// actors [A,14,48] fp32 (channel-first) -> hi/lo [A][50][16] channel-last with zero pad rows / channels
+__global__ void k_actor_prep(const float* __restrict__ actors, __half* __restrict__ hi, __half* __restrict__ lo, int A) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)A * 50 * 16) return;
+    const int c = (int)(idx & 15);
+    const int t = (int)((idx >> 4) % 50);
+    const int a = (int)(idx / 800);
+    float x = 0.f;
+    if (c < 14 && t >= 1 && t <= 48) x = actors[((int64_t)a * 14 + c) * 48 + (t - 1)];
+    split_store(hi, lo, idx, x);
+}
+
+// y = GN(raw) (+ GN(res_raw) | + (res_hi+res_lo))  (ReLU)  -> hi/lo padded [A][L+2][C] and / or fp32 [A][L][C]
+// stats: [A][3][2] partial (sum, sum^2) over the actor's C*L outputs (3 inner tiles per actor)
+struct ApplyArgs {
+    const float* raw; const float* stats; const float* gamma; const float* beta;
+    const float* res_raw; const float* res_stats; const float* res_gamma; const float* res_beta;
+    const __half* res_hi; const __half* res_lo;     // identity shortcut, padded [A][L+2][C]
+    __half* out_hi; __half* out_lo; float* out_f32;
+    int A, L, C, relu;
+};
+__global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
+    const int a = blockIdx.x;
+    __shared__ float sm[4];
+    if (threadIdx.x == 0) {
+        const float n = (float)(p.L * p.C);
+        const float* s = p.stats + (int64_t)a * 6;
+        const float mean = ((s[0] + s[2]) + s[4]) / n;
+        const float var = fmaxf(((s[1] + s[3]) + s[5]) / n - mean * mean, 0.f);
+        sm[0] = mean; sm[1] = rsqrtf(var + 1e-5f);
+        if (p.res_raw) {
+            const float* r = p.res_stats + (int64_t)a * 6;
+            const float m2 = ((r[0] + r[2]) + r[4]) / n;
+            const float v2 = fmaxf(((r[1] + r[3]) + r[5]) / n - m2 * m2, 0.f);
+            sm[2] = m2; sm[3] = rsqrtf(v2 + 1e-5f);
+        }
+    }
+    __syncthreads();
+    const float mean = sm[0], rstd = sm[1];
+    const int n = p.L * p.C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int t = i / p.C, c = i - t * p.C;
+        float y = (p.raw[(int64_t)a * n + i] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
+        const int64_t pidx = ((int64_t)a * (p.L + 2) + t + 1) * p.C + c;
+        if (p.res_raw) y += (p.res_raw[(int64_t)a * n + i] - sm[2]) * sm[3] * __ldg(p.res_gamma + c) + __ldg(p.res_beta + c);
+        else if (p.res_hi) y += __half2float(p.res_hi[pidx]) + __half2float(p.res_lo[pidx]);
+        if (p.relu) y = fmaxf(y, 0.f);
+        if (p.out_hi) split_store(p.out_hi, p.out_lo, pidx, y);
+        if (p.out_f32) p.out_f32[(int64_t)a * n + i] = y;
+    }
+    if (p.out_hi) {   // zero pad rows t = 0 and t = L+1
+        for (int c = threadIdx.x; c < 2 * p.C; c += blockDim.x) {
+            const int64_t pidx = ((int64_t)a * (p.L + 2) + (c < p.C ? 0 : p.L + 1)) * p.C + (c % p.C);
+            p.out_hi[pidx] = __float2half(0.f);
+            p.out_lo[pidx] = __float2half(0.f);
+        }
+    }
+}
+
+// FPN top-down step (network.py:57-58): out[a,t,c] = lerp_x2(prev)[a,t,c] + lat[a,t,c]; channel-last fp32,
+// optionally also emitted as padded hi/lo (input of the output Res1d) ; last_only extracts t = L-1
+__global__ void __launch_bounds__(256) k_fpn_up_add(const float* __restrict__ prev, const float* __restrict__ lat,
+                                                    float* __restrict__ out, __half* hi, __half* lo, int A, int L, int C) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)A * L * C) return;
+    const int c = (int)(idx % C);
+    const int t = (int)((idx / C) % L);
+    const int a = (int)(idx / ((int64_t)C * L));
+    const int Lp = L >> 1;
+    float src = fmaxf(((float)t + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int i0 = (int)floorf(src);
+    const int i1 = min(i0 + 1, Lp - 1);
+    const float lam = src - (float)i0;
+    const float* pp = prev + (int64_t)a * Lp * C;
+    const float y = pp[i0 * C + c] * (1.f - lam) + pp[i1 * C + c] * lam + lat[idx];
+    out[idx] = y;
+    if (hi) {
+        const int64_t pidx = ((int64_t)a * (L + 2) + t + 1) * C + c;
+        split_store(hi, lo, pidx, y);
+        if (t == 0) { const int64_t z = ((int64_t)a * (L + 2)) * C + c; hi[z] = __float2half(0.f); lo[z] = __float2half(0.f); }
+        if (t == L - 1) { const int64_t z = ((int64_t)a * (L + 2) + L + 1) * C + c; hi[z] = __float2half(0.f); lo[z] = __float2half(0.f); }
+    }
+}
+
+}  // namespace tcg
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+char g_err[256];
+}  // namespace
+
+const char* tcg_encode_a(void* map, const __half* base, int64_t k_extent, int64_t inner, int64_t outer,
+                         int64_t inner_stride_elems, int64_t outer_stride_elems, int r_in, int r_out) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled unavailable";
+    cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[2] = {(cuuint64_t)inner_stride_elems * 2, (cuuint64_t)outer_stride_elems * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)r_in, (cuuint32_t)r_out};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc((CUtensorMap*)map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "encode A map failed (%d): k=%lld in=%lld out=%lld s=%lld/%lld box=%d/%d", (int)r,
+                                      (long long)k_extent, (long long)inner, (long long)outer, (long long)inner_stride_elems,
+                                      (long long)outer_stride_elems, r_in, r_out); return g_err; }
+    return nullptr;
+}
+
+const char* tcg_encode_w(void* map, const __half* base, int64_t k_total, int64_t n_rows, int n_tile) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled unavailable";
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc((CUtensorMap*)map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "encode W map failed (%d)", (int)r); return g_err; }
+    return nullptr;
+}
+
+const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(tcg::k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg::SMEM_BYTES) != cudaSuccess)
+            return "cudaFuncSetAttribute(tc_gemm) failed";
+        attr = true;
+    }
+    if (p.r_in * p.r_out != 128) return "tc_gemm: r_in * r_out must be 128";
+    if (p.n_tile % 32 || p.n_tile > 256 || p.n_tile < 32) return "tc_gemm: n_tile must be a multiple of 32 in [32,256]";
+    tcg::Args g;
+    g.n_terms = p.split ? 3 : 1;
+    g.k_blocks = p.k_blocks;
+    g.a_sel[0] = 0; g.a_sel[1] = 1; g.a_sel[2] = 0;
+    g.w_k_off[0] = 0; g.w_k_off[1] = 0; g.w_k_off[2] = p.k_blocks * 64;
+    g.r_in = p.r_in; g.r_out = p.r_out; g.L_inner = p.L_inner; g.n_outer = p.n_outer;
+    g.tiles_inner = (p.L_inner + p.r_in - 1) / p.r_in;
+    g.tiles_outer = (p.n_outer + p.r_out - 1) / p.r_out;
+    g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
+    g.C = p.C; g.ldc = p.ldc; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
+    const int total = g.tiles_inner * g.tiles_outer * g.tiles_n;
+    if (total <= 0) return nullptr;
+    CUtensorMap a0, a1, w;
+    memcpy(&a0, p.amap_hi, sizeof a0);
+    memcpy(&a1, p.split ? p.amap_lo : p.amap_hi, sizeof a1);
+    memcpy(&w, p.wmap, sizeof w);
+    tcg::k_tc_gemm<<<std::min(total, sm_count), tcg::kThreads, tcg::SMEM_BYTES, st>>>(a0, a1, w, g);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+void tcg_actor_prep(const float* actors, __half* hi, __half* lo, int A, cudaStream_t st) {
+    const int64_t n = (int64_t)A * 800;
+    tcg::k_actor_prep<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(actors, hi, lo, A);
+    ++g_launches;
+}
+void tcg_gn_apply(const TcApply& q, cudaStream_t st) {
+    tcg::ApplyArgs p;
+    p.raw = q.raw; p.stats = q.stats; p.gamma = q.gamma; p.beta = q.beta;
+    p.res_raw = q.res_raw; p.res_stats = q.res_stats; p.res_gamma = q.res_gamma; p.res_beta = q.res_beta;
+    p.res_hi = q.res_hi; p.res_lo = q.res_lo; p.out_hi = q.out_hi; p.out_lo = q.out_lo; p.out_f32 = q.out_f32;
+    p.A = q.A; p.L = q.L; p.C = q.C; p.relu = q.relu;
+    if (q.A <= 0) return;
+    tcg::k_gn_apply<<<q.A, 256, 0, st>>>(p);
+    ++g_launches;
+}
+void tcg_fpn_up_add(const float* prev, const float* lat, float* out, __half* hi, __half* lo, int A, int L, int C, cudaStream_t st) {
+    const int64_t n = (int64_t)A * L * C;
+    if (n <= 0) return;
+    tcg::k_fpn_up_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prev, lat, out, hi, lo, A, L, C);
+    ++g_launches;
+}
+
+}  // namespace mind

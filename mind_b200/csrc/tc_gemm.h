@@ -1,0 +1,61 @@
+// Tensor-core GEMM engine + ActorNet on top of it (see tc_gemm.cu / actor_tc.cu).
+#pragma once
+#include "kernels.h"
+#include <map>
+#include <string>
+#include <vector>
+
+namespace mind {
+
+struct TcGemm {
+    const void* amap_hi = nullptr;   // CUtensorMap (128 B) over the fp16 hi part of A
+    const void* amap_lo = nullptr;   //   "   lo part (only when split)
+    const void* wmap = nullptr;      // CUtensorMap over W [N][k_total] (k_total = 2*k_blocks*64 when split: [hi | lo])
+    int split = 1;                   // 3-term hi/lo product (fp32-equivalent) or plain fp16
+    int k_blocks = 1;                // K / 64 per term
+    int r_in = 128, r_out = 1;       // 128-row tile = r_out outer groups x r_in inner rows
+    int L_inner = 0, n_outer = 1;    // logical extents; output row = outer * L_inner + inner
+    int N = 0, n_tile = 128;
+    float* C = nullptr; int ldc = 0;
+    const float* bias = nullptr; int relu = 0;
+    float* stats = nullptr;          // [n_outer][ceil(L_inner / r_in)][2] partial (sum, sum^2) or null
+    int* err = nullptr;
+};
+
+const char* tcg_encode_a(void* map, const __half* base, int64_t k_extent, int64_t inner, int64_t outer,
+                         int64_t inner_stride_elems, int64_t outer_stride_elems, int r_in, int r_out);
+const char* tcg_encode_w(void* map, const __half* base, int64_t k_total, int64_t n_rows, int n_tile);
+const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st);
+
+struct TcApply {
+    const float* raw = nullptr; const float* stats = nullptr; const float* gamma = nullptr; const float* beta = nullptr;
+    const float* res_raw = nullptr; const float* res_stats = nullptr; const float* res_gamma = nullptr; const float* res_beta = nullptr;
+    const __half* res_hi = nullptr; const __half* res_lo = nullptr;
+    __half* out_hi = nullptr; __half* out_lo = nullptr; float* out_f32 = nullptr;
+    int A = 0, L = 0, C = 0, relu = 0;
+};
+void tcg_actor_prep(const float* actors, __half* hi, __half* lo, int A, cudaStream_t st);
+void tcg_gn_apply(const TcApply& q, cudaStream_t st);
+void tcg_fpn_up_add(const float* prev, const float* lat, float* out, __half* hi, __half* lo, int A, int L, int C, cudaStream_t st);
+
+// ---- ActorNet (reference network.py:12-61) on the GEMM engine --------------------------------
+struct ActorTcConv {
+    __half* W = nullptr;     // [Cout][2*Kpad] fp16 = [hi | lo], k index = tap * Cin_pad + ci
+    int Cout = 0, Cin_pad = 0, ksize = 3, Kpad = 0;
+    alignas(64) unsigned char wmap[128];
+};
+struct ActorTc {
+    std::map<std::string, ActorTcConv> conv;     // keyed by the reference weight name
+    std::map<std::string, const float*> vec;     // GN affine parameters (device fp32, owned by the ctx arena)
+    int* d_err = nullptr;
+    bool ready = false;
+};
+// host fp32 weights by reference key -> packed device copies
+const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<float>>& host,
+                          const std::map<std::string, const float*>& dev);
+void actor_tc_free(ActorTc& a);
+int64_t actor_tc_ws_bytes(int A);
+// actors [A,14,48] fp32 -> out [A,128]
+const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float* out, int sm_count, cudaStream_t st);
+
+}  // namespace mind

@@ -138,3 +138,26 @@ def test_outputs_are_writable_views(ckpt_sd, dev):
     reg[0][:, 0, :, :2] += 1.0
     aux[0][0][:, 0] *= 2.0
     assert reg[0].detach().is_cuda and aux[0][2].shape == (6, 3, 8, 5)
+
+
+def test_actor_net_tensor_core_stage(ckpt_sd, rand_sd, dev):
+    """ActorNet on the tcgen05 GEMM engine (3-term fp16 split) is fp32-equivalent: stage tap vs golden."""
+    from mind_b200 import synth
+    from oracle.make_golden import ragged_batch
+    gold = load_golden("s1_ckpt.npz")
+    net = make_net(ckpt_sd, dev, "f16tc")
+    net(to_dev(synth.batch_from_scenes([synth.scene_s1(1234)]), dev))
+    af = net.debug_tap("actor_feat", 32 * 128).view(32, 128)
+    torch.cuda.synchronize()
+    e = rel_err(af, gold["actor_feat"])
+    print("actor_feat (tc, ckpt) rel err %.3e" % e)
+    assert e < 2e-5
+    gold = load_golden("ragged_rand.npz")
+    net = make_net(rand_sd, dev, "f16tc")
+    data = ragged_batch()
+    net(to_dev(data, dev))
+    n = data[0].shape[0]
+    af = net.debug_tap("actor_feat", n * 128).view(n, 128)
+    e = rel_err(af, gold["actor_feat"])
+    print("actor_feat (tc, rand) rel err %.3e" % e)
+    assert e < 2e-5
