@@ -112,8 +112,9 @@ int mind_forward(MindCtx* ctx, const MindBatch* batch, const MindOutputs* out, v
 int64_t mind_debug_tap(MindCtx* ctx, const char* name, float* dst, int64_t capacity, void* cuda_stream);
 
 /* bring-up self test of the TMA + tcgen05 + TMEM plumbing: D[0:128*128] = A . W^T (fp16 operands,
- * fp32 accumulate) and D[128*128: 2*128*128] = the A tile read back through the software
- * swizzle.  All three are HOST buffers (A, W: 128*128 floats; D: 2*128*128 floats). */
+ * fp32 accumulate), D[128*128: 2*128*128] = the A tile read back through the software swizzle,
+ * D[2*128*128: 3*128*128] = the same product with the A operand staged in tensor memory.
+ * All three are HOST buffers (A, W: 128*128 floats; D: 3*128*128 floats). */
 int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host);
 
 /* cudaDeviceSynchronize + kernel-side protocol error flag (0 = clean) */

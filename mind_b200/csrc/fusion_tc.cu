@@ -147,6 +147,25 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
         : "r"(taddr)                                                                                             \
         : "memory")
+#define TMEM_ST_X32(taddr, r)                                                                                      \
+    asm volatile(                                                                                                  \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "                                                           \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"  \
+        "%28,%29,%30,%31};"                                                                                        \
+        ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),      \
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),          \
+          "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),         \
+          "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)          \
+        : "memory")
+// A operand from tensor memory (lane = row, two fp16 K elements per 32-bit cell), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows x 128 B] block that
@@ -186,6 +205,10 @@ struct LayerArgs {
     int* err;
 };
 
+// TMEM column map (512 columns x 128 lanes, fp32 cells)
+//   [  0,128)  D1 = edge.W_e^T ; after epilogue 1 the same columns hold the A operand of G2:
+//              memory as an fp16 (hi, lo) pair, two K elements per 32-bit cell: hi -> [0,64), lo -> [64,128)
+//   [128,256)  Dpe   [256,384)  Dk   [384,512)  Dv
 __global__ void __launch_bounds__(kThreads, 1)
 k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -197,7 +220,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     float* sP = reinterpret_cast<float*>(sgen + SM_P);
     float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
-    const uint32_t bar_w = sbase + SM_BAR, bar_load = bar_w + 8, bar_m1 = bar_w + 16, bar_m2 = bar_w + 24;
+    const uint32_t bar_w = sbase + SM_BAR, bar_m1 = bar_w + 8, bar_m2 = bar_w + 16, bar_ld0 = bar_w + 24;   // bar_ld0, bar_ld0+8
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = warp >> 2;                  // column half: channels [64*half, 64*half+64)
@@ -205,7 +228,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     const int i_l = row >> 4, j_l = row & 15;
 
     if (tid == 0) {
-        mbar_init(bar_w, 1); mbar_init(bar_load, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1);
+        mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1); mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -226,8 +249,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     }
     mbar_wait(bar_w, 0, a.err, E_LOAD_W);
 
-    uint32_t par = 0;       // phase parity of bar_load / bar_m1 / bar_m2 (each completes once per tile)
-    int cur = 0;            // tile buffer holding the current edge tile; the other one receives `memory`
+    uint32_t par = 0;             // parity of bar_m1 / bar_m2 (one completion per tile)
+    uint32_t lpar0 = 0, lpar1 = 0;   // parity of the two edge-load barriers (one completion per use of the buffer)
+    int cur = 0;                  // edge buffer of the current tile
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t col0 = (uint32_t)half * 64;
     const float* Pm = sP;
@@ -237,10 +261,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         const int N = wk.n, j0 = wk.j0, b = wk.b;
         const int n_chunks = (N + 7) >> 3;
         const int64_t tok0 = (int64_t)b * a.Nmax;
-        if (tid == 0) {   // first edge tile of the work item
-            mbar_expect_tx(bar_load, 32768u);
-            tma_load_4d(sbase + SM_TILE0 + cur * 32768, &emap, bar_load, 0, j0, 0, b);
-            tma_load_4d(sbase + SM_TILE0 + cur * 32768 + 16384, &emap, bar_load, 64, j0, 0, b);
+        if (tid == 0) {   // first edge tile of the work item -> buffer `cur` (free: see end of the loop body)
+            const uint32_t bl = bar_ld0 + 8 * cur;
+            mbar_expect_tx(bl, 32768u);
+            tma_load_4d(sbase + SM_TILE0 + cur * 32768, &emap, bl, 0, j0, 0, b);
+            tma_load_4d(sbase + SM_TILE0 + cur * 32768 + 16384, &emap, bl, 64, j0, 0, b);
         }
         // S (src term, per query j) and q tiles
         for (int idx = tid; idx < 16 * 32; idx += kThreads) {
@@ -263,14 +288,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int i0 = ch * 8;
             const uint32_t tX = sbase + SM_TILE0 + cur * 32768;          // edge tile (in place -> edge')
-            const uint32_t tY = sbase + SM_TILE0 + (cur ^ 1) * 32768;    // memory tile, then prefetch target
+            const uint32_t tN = sbase + SM_TILE0 + (cur ^ 1) * 32768;    // next edge tile (prefetch target)
             {   // T (target term, per key i) tile
                 const int ii = tid >> 5, c4 = tid & 31;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i0 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + ii) * 384 + 128)[c4];
                 *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = t;
             }
-            mbar_wait(bar_load, par, a.err, E_LOAD_EDGE);      // every thread observes the TMA completion
+            mbar_wait(bar_ld0 + 8 * cur, cur ? lpar1 : lpar0, a.err, E_LOAD_EDGE);   // every thread observes the TMA completion
+            if (cur) lpar1 ^= 1; else lpar0 ^= 1;
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t id128 = umma_idesc_f16(128);
@@ -281,12 +307,19 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     umma_f16(tmem + 0, umma_desc_sw128(tX + ko), umma_desc_sw128(sbase + SM_W + kw), id128, kk > 0);
                 }
                 umma_commit(bar_m1);
+                if (ch + 1 < n_chunks) {                       // prefetch the next edge tile while this one is processed
+                    tma_wait_read0();                          // the edge' store that last used tN has drained
+                    const uint32_t bl = bar_ld0 + 8 * (cur ^ 1);
+                    mbar_expect_tx(bl, 32768u);
+                    tma_load_4d(tN, &emap, bl, 0, j0, i0 + 8, b);
+                    tma_load_4d(tN + 16384, &emap, bl, 64, j0, i0 + 8, b);
+                }
             }
             __syncthreads();                                   // B0: sT / sS / sQ visible
             mbar_wait(bar_m1, par, a.err, E_MMA1);
             tc_fence_after();
 
-            // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 A operand of G2 ----
+            // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 (hi, lo) A operand in TMEM ----
             float v[64];
             {
                 uint32_t r[32];
@@ -312,51 +345,53 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
                 sStat[(0 * 2 + half) * 128 + row] = make_float2(s1, s2);
             }
-            if (tid == 0) tma_wait_read0();                    // previous edge' store has left tY
             tc_fence_before();
-            __syncthreads();                                   // B1
+            __syncthreads();                                   // B1: statistics exchanged, every D1 read retired
+            tc_fence_after();
             {
                 const float2 o = sStat[(0 * 2 + (half ^ 1)) * 128 + row];
                 const float2 m = sStat[(0 * 2 + half) * 128 + row];
                 const float mean = (o.x + m.x) * (1.f / 128.f);
                 const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + kEps);
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    float y[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = (int)col0 + c8 * 8 + e;
-                        y[e] = fmaxf((v[c8 * 8 + e] - mean) * rstd * Pm[P_MEM_G * 128 + c] + Pm[P_MEM_B * 128 + c], 0.f);
-                    }
-                    uint4 u;
-                    u.x = pack_h2(y[0], y[1]); u.y = pack_h2(y[2], y[3]); u.z = pack_h2(y[4], y[5]); u.w = pack_h2(y[6], y[7]);
-                    st_shared_v4(tY + half * 16384 + sw128(row, c8), u);
+                for (int k2 = 0; k2 < 32; ++k2) {
+                    const int c = (int)col0 + k2 * 2;
+                    const float y0 = fmaxf((v[k2 * 2] - mean) * rstd * Pm[P_MEM_G * 128 + c] + Pm[P_MEM_B * 128 + c], 0.f);
+                    const float y1 = fmaxf((v[k2 * 2 + 1] - mean) * rstd * Pm[P_MEM_G * 128 + c + 1] + Pm[P_MEM_B * 128 + c + 1], 0.f);
+                    const __half2 h = __floats2half2_rn(y0, y1);
+                    const float2 hf = __half22float2(h);
+                    hi[k2] = *reinterpret_cast<const uint32_t*>(&h);
+                    lo[k2] = pack_h2(y0 - hf.x, y1 - hf.y);
                 }
+                // K elements [64*half, +64) -> cells [32*half, +32) of the hi block and of the lo block
+                TMEM_ST_X32(tmem + lane_base + half * 32, hi);
+                TMEM_ST_X32(tmem + lane_base + 64 + half * 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-            fence_proxy_async();
             tc_fence_before();
-            __syncthreads();                                   // B2: memory tile complete
+            __syncthreads();                                   // B2: A operand complete
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t id128 = umma_idesc_f16(128), id256 = umma_idesc_f16(256);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
                     const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-                    const uint64_t ad = umma_desc_sw128(tY + ko);
-                    if (a.has_edge) umma_f16(tmem + 128, ad, umma_desc_sw128(sbase + SM_W + kw + 128 * 128), id128, kk > 0);
-                    umma_f16(tmem + 256, ad, umma_desc_sw128(sbase + SM_W + kw + 256 * 128), id256, kk > 0);
+                    const uint32_t a_hi = tmem + kk * 8, a_lo = tmem + 64 + kk * 8;
+                    if (a.has_edge) {
+                        const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 128 * 128);
+                        umma_f16_ts(tmem + 128, a_hi, bd, id128, kk > 0);
+                        umma_f16_ts(tmem + 128, a_lo, bd, id128, 1);
+                    }
+                    const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 256 * 128);
+                    umma_f16_ts(tmem + 256, a_hi, bd, id256, kk > 0);
+                    umma_f16_ts(tmem + 256, a_lo, bd, id256, 1);
                 }
                 umma_commit(bar_m2);
             }
             mbar_wait(bar_m2, par, a.err, E_MMA2);
             tc_fence_after();
-            if (tid == 0 && ch + 1 < n_chunks) {               // prefetch next edge tile into tY (free now)
-                mbar_expect_tx(bar_load, 32768u);
-                tma_load_4d(tY, &emap, bar_load, 0, j0, i0 + 8, b);
-                tma_load_4d(tY + 16384, &emap, bar_load, 64, j0, i0 + 8, b);
-            }
 
             // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
             if (a.has_edge) {
@@ -451,18 +486,13 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
             }
 
-            if (a.has_edge) {
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();                               // B5: edge' tile complete
-                if (tid == 0) {
-                    tma_store_4d(&emap, tX, 0, j0, i0, b);
-                    tma_store_4d(&emap, tX + 16384, 64, j0, i0, b);
-                    tma_commit();
-                }
-            } else {
-                tc_fence_before();
-                __syncthreads();
+            if (a.has_edge) fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();                                   // B5: edge' tile complete, all TMEM reads retired
+            if (a.has_edge && tid == 0) {
+                tma_store_4d(&emap, tX, 0, j0, i0, b);
+                tma_store_4d(&emap, tX + 16384, 64, j0, i0, b);
+                tma_commit();
             }
             cur ^= 1;
             par ^= 1;
@@ -485,8 +515,10 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             }
             mrun[h] = mn;
         }
-        // scratch in tile buffer `cur` (free: no prefetch was issued for it): [3 src][2 half][16 j][76]
-        float* scr = reinterpret_cast<float*>(sgen + SM_TILE0 + cur * 32768);
+        // scratch in edge buffer `cur` (no prefetch was issued into it; drain the store that last used it)
+        if (tid == 0) tma_wait_read0();
+        __syncthreads();
+        float* scr = reinterpret_cast<float*>(sgen + SM_TILE0 + cur * 32768);   // [3 src][2 half][16 j][76]
         const int wq = warp & 3;
         if (wq != 0 && lane < 16) {
             float* d = scr + (((wq - 1) * 2 + half) * 16 + lane) * 76;
@@ -549,17 +581,18 @@ k_tc_selftest(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + 65536 + 64);
-    const uint32_t bar_l = sbase + 65536, bar_m = bar_l + 8;
+    const uint32_t bar_l = sbase + 65536, bar_m = bar_l + 8, bar_m2 = bar_l + 16;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(bar_l, 1); mbar_init(bar_m, 1); fence_barrier_init(); }
+    if (tid == 0) { mbar_init(bar_l, 1); mbar_init(bar_m, 1); mbar_init(bar_m2, 1); fence_barrier_init(); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + 65536 + 64), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + 65536 + 64), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sTmem;
+    const uint32_t tmem2 = tmem;
     if (tid == 0) {
         mbar_expect_tx(bar_l, 65536u);
         for (int kb = 0; kb < 2; ++kb) {
@@ -584,15 +617,45 @@ k_tc_selftest(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
         tmem_wait_ld();
         for (int k = 0; k < 32; ++k) out[row * 128 + p * 32 + k] = __uint_as_float(r[k]);
     }
+    uint32_t apk[64];     // this row of A as 64 packed fp16 pairs (K order)
     for (int c8 = 0; c8 < 16; ++c8) {
         const uint4 u = ld_shared_v4(sbase + (c8 >> 3) * 16384 + sw128(row, c8 & 7));
         const float2 e0 = unpack_h2(u.x), e1 = unpack_h2(u.y), e2 = unpack_h2(u.z), e3 = unpack_h2(u.w);
         float* o = out + 128 * 128 + row * 128 + c8 * 8;
         o[0] = e0.x; o[1] = e0.y; o[2] = e1.x; o[3] = e1.y; o[4] = e2.x; o[5] = e2.y; o[6] = e3.x; o[7] = e3.y;
+        apk[c8 * 4 + 0] = u.x; apk[c8 * 4 + 1] = u.y; apk[c8 * 4 + 2] = u.z; apk[c8 * 4 + 3] = u.w;
+    }
+    // second product with the A operand in tensor memory: D2 = A_tmem . W^T -> columns [64,192) after A in [0,64)
+    {
+        const uint32_t lb = (uint32_t)(warp * 32) << 16;
+        tc_fence_before();
+        __syncthreads();           // every thread has finished reading D (columns 0..127)
+        tc_fence_after();
+        TMEM_ST_X32(tmem2 + lb, apk);
+        TMEM_ST_X32(tmem2 + lb + 32, (apk + 32));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
+                umma_f16_ts(tmem2 + 64, tmem2 + kk * 8, umma_desc_sw128(sbase + 32768 + ko), umma_idesc_f16(128), kk > 0);
+            }
+            umma_commit(bar_m2);
+        }
+        mbar_wait(bar_m2, 0, err, E_MMA2);
+        tc_fence_after();
+        for (int p = 0; p < 4; ++p) {
+            uint32_t r[32];
+            TMEM_LD_X32(tmem2 + lb + 64 + p * 32, r);
+            tmem_wait_ld();
+            for (int k = 0; k < 32; ++k) out[2 * 128 * 128 + row * 128 + p * 32 + k] = __uint_as_float(r[k]);
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
 }  // namespace tc
@@ -753,12 +816,12 @@ const char* tc_selftest(const float* A_host, const float* W_host, float* D_host)
     std::vector<__half> hA(128 * 128), hW(128 * 128);
     for (int i = 0; i < 128 * 128; ++i) { hA[i] = __float2half_rn(A_host[i]); hW[i] = __float2half_rn(W_host[i]); }
     if (cudaMalloc(&dA, 32768) != cudaSuccess || cudaMalloc(&dW, 32768) != cudaSuccess ||
-        cudaMalloc(&dO, 2 * 65536) != cudaSuccess || cudaMalloc(&dErr, 4) != cudaSuccess)
+        cudaMalloc(&dO, 3 * 65536) != cudaSuccess || cudaMalloc(&dErr, 4) != cudaSuccess)
         return "selftest cudaMalloc failed";
     cudaMemcpy(dA, hA.data(), 32768, cudaMemcpyHostToDevice);
     cudaMemcpy(dW, hW.data(), 32768, cudaMemcpyHostToDevice);
     cudaMemset(dErr, 0, 4);
-    cudaMemset(dO, 0, 2 * 65536);
+    cudaMemset(dO, 0, 3 * 65536);
     alignas(64) CUtensorMap am, wm;
     if (const char* e = make_map_2d(&am, dA, 128)) return e;
     if (const char* e = make_map_2d(&wm, dW, 128)) return e;
@@ -774,7 +837,7 @@ const char* tc_selftest(const float* A_host, const float* W_host, float* D_host)
         cudaMemcpy(&code, dErr, 4, cudaMemcpyDeviceToHost);
         ret = tcfail(cudaGetErrorString(e), code);
     } else {
-        cudaMemcpy(D_host, dO, 2 * 65536, cudaMemcpyDeviceToHost);
+        cudaMemcpy(D_host, dO, 3 * 65536, cudaMemcpyDeviceToHost);
     }
     cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dErr);
     return ret;

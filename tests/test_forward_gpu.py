@@ -59,13 +59,15 @@ def test_tc_selftest(dev):
     g = torch.Generator().manual_seed(0)
     A = torch.randn(128, 128, generator=g)
     W = torch.randn(128, 128, generator=g)
-    D = torch.zeros(2, 128, 128)
+    D = torch.zeros(3, 128, 128)
     rc = L.mind_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(D.data_ptr()))
     assert rc == 0, L.mind_last_error()
     Ah, Wh = A.half().float(), W.half().float()
     assert torch.equal(D[1], Ah), "software swizzle does not match the TMA 128B swizzle"
     ref = Ah.double() @ Wh.double().t()
     assert (D[0].double() - ref).abs().max() < 1e-3 * ref.abs().max()
+    # same product with the A operand staged in tensor memory (tcgen05.st + A-from-TMEM MMA)
+    assert (D[2].double() - ref).abs().max() < 1e-3 * ref.abs().max(), "A-from-TMEM operand layout"
 
 
 @pytest.mark.parametrize("prec,tol", [("fp32", TOL_FP32), ("f16tc", TOL_TC)])
