@@ -64,6 +64,7 @@ struct MindCtx {
     bool finalized = false;
     int precision = MIND_PREC_FP32;
     int chunk_scenes = 32;
+    int actor_simt = 0;           // diagnostics: force the SIMT ActorNet in f16tc mode
     ActorNetWeights an{};
     FusionLayerW fl[6]{};
     TcWeights tc{};               // fp16 packed weights / per-layer params for the tensor-core path
@@ -120,6 +121,8 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
     if (!strcmp(name, "precision")) {
         if (value != MIND_PREC_FP32 && value != MIND_PREC_F16TC) return fail("precision must be 0 or 1");
         c->precision = (int)value;
+    } else if (!strcmp(name, "actor_simt")) {
+        c->actor_simt = value != 0;
     } else if (!strcmp(name, "profile")) {
         c->prof.on = value != 0;
     } else if (!strcmp(name, "chunk_scenes")) {
@@ -566,7 +569,7 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     Lin L{c, st};
     PROF_BEGIN();
     // ---- encoders -------------------------------------------------------------------------
-    if (c->precision == MIND_PREC_F16TC) {                                                  // network.py:586
+    if (c->precision == MIND_PREC_F16TC && !c->actor_simt) {                                // network.py:586
         if (const char* e = actor_tc_run(c->actor_tc, bt->actors, A, w.actor_ws, w.actor_feat, c->sm_count, st))
             return fail("actor_tc_run: %s", e);
     } else {

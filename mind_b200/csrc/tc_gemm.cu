@@ -306,6 +306,15 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
             p.out_hi[pidx] = __float2half(0.f);
             p.out_lo[pidx] = __float2half(0.f);
         }
+        // K-padded conv windows of the LAST actor read up to 4 rows past the logical end of this
+        // (possibly re-used, larger) buffer: keep them finite (they meet zero weights)
+        if (a == p.A - 1) {
+            const int64_t end = (int64_t)p.A * (p.L + 2) * p.C;
+            for (int c = threadIdx.x; c < 4 * p.C; c += blockDim.x) {
+                p.out_hi[end + c] = __float2half(0.f);
+                p.out_lo[end + c] = __float2half(0.f);
+            }
+        }
     }
 }
 
