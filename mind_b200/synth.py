@@ -101,3 +101,77 @@ def random_state_dict(seed: int = 0, like: Optional[dict] = None):
                 fan_in *= s
             sd[k] = torch.randn(shape, generator=g) / math.sqrt(fan_in)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------
+# S3: kinematic synthetic scene for the AIME tree.  Restates what
+# process_data (reference scenario_tree.py:136-206) builds, on hand-made inputs (no av2/shapely).
+# ---------------------------------------------------------------------------------------------
+def scene_s3(x0=(50, 60, 40, 80, 75, 65), y0=(0, 3.5, -3.5, 3.5, 0, -3.5), v=(6, 5, 7, 4, 6, 5),
+             tar_time_ahead: float = 5.0):
+    """Returns (collated one-scene dict, target_lane [301,2] float32, target_lane_info list of 6 arrays,
+    lane_graph dict).  Actor 0 is the ego ('AV')."""
+    import numpy as np
+    from . import plumbing as P
+    na = len(x0)
+    t = torch.arange(50, dtype=torch.float32) * 0.1
+    pos = torch.stack([torch.stack([x0[i] + v[i] * (t - 4.9), torch.full_like(t, float(y0[i]))], -1) for i in range(na)])
+    ang = torch.zeros(na, 50)
+    vel = torch.stack([torch.stack([torch.full_like(t, float(v[i])), torch.zeros_like(t)], -1) for i in range(na)])
+    ttype = torch.zeros(na, 50, 7, dtype=torch.int16)
+    ttype[..., 0] = 1
+    pad = torch.ones(na, 50, dtype=torch.int16)
+    # target lane: y = 0, x = 0..300 @ 1 m
+    lane = np.stack([np.arange(301, dtype=np.float32), np.zeros(301, dtype=np.float32)], -1)
+    one = lambda k: np.tile(np.eye(3, dtype=np.float32)[k], (301, 1))
+    info = [np.zeros(301, np.float32), one(0), one(0), one(1), np.ones(301, np.float32), np.zeros(301, np.float32)]
+    tl = torch.from_numpy(lane)
+    tli = P.pack_target_lane_info(info)
+
+    orig, rot, theta = P.origin_rotation(pos[0], ang[0])
+    # lane graph: 3 lanes x 20 segments of 15 m, 11 points each, scene frame then instance frame
+    node_ctrs, node_vecs, lane_ctrs, lane_vecs = [], [], [], []
+    for y in (-3.5, 0.0, 3.5):
+        for s in range(20):
+            xs = torch.linspace(15.0 * s, 15.0 * (s + 1), 11)
+            p = torch.stack([xs, torch.full_like(xs, y)], -1)
+            p = torch.matmul(p - orig, rot)
+            anch = p.mean(0)
+            d = (p[-1] - p[0]) / torch.norm(p[-1] - p[0])
+            r = torch.stack([torch.stack([d[0], -d[1]]), torch.stack([d[1], d[0]])])
+            q = torch.matmul(p - anch, r)
+            node_ctrs.append((q[:-1] + q[1:]) / 2.0)
+            node_vecs.append(q[1:] - q[:-1])
+            lane_ctrs.append(anch)
+            lane_vecs.append(d)
+    nl = 60
+    oh = lambda k: torch.tensor([1 if i == k else 0 for i in range(3)], dtype=torch.int16).repeat(nl, 10, 1)
+    graph = dict(node_ctrs=torch.stack(node_ctrs), node_vecs=torch.stack(node_vecs),
+                 intersect=torch.zeros(nl, 10, dtype=torch.int16), lane_type=oh(0), cross_left=oh(0), cross_right=oh(0),
+                 left=torch.ones(nl, 10, dtype=torch.int16), right=torch.ones(nl, 10, dtype=torch.int16),
+                 lane_ctrs=torch.stack(lane_ctrs), lane_vecs=torch.stack(lane_vecs), num_nodes=nl * 10, num_lanes=nl)
+
+    # scene-normalise, then per-actor normalise (scenario_tree.py:136-158)
+    spos = torch.matmul(pos - orig, rot)
+    sang = ang - theta
+    svel = torch.matmul(vel, rot)
+    pn, an, vn, ctrs, vecs = [], [], [], [], []
+    for i in range(na):
+        o, r, th = P.origin_rotation(spos[i], sang[i])
+        pn.append(torch.matmul(spos[i] - o, r))
+        an.append(sang[i] - th)
+        vn.append(torch.matmul(svel[i], r))
+        ctrs.append(o)
+        vecs.append(torch.stack([torch.cos(th), torch.sin(th)]))
+    an = torch.stack(an)
+    trajs = dict(TRAJS_POS_OBS=torch.stack(pn), TRAJS_ANG_OBS=torch.stack([torch.cos(an), torch.sin(an)], -1),
+                 TRAJS_VEL_OBS=torch.stack(vn), TRAJS_TYPE=ttype, PAD_OBS=pad, TRAJS_CTRS=torch.stack(ctrs),
+                 TRAJS_VECS=torch.stack(vecs), TRAJS_TID=["AV"] + [str(i) for i in range(1, na)],
+                 TRAJS_CAT=["av"] + ["exo"] * (na - 1))
+    tgt_pts, tgt_nodes, tgt_anch = P.high_level_command(tl, tli, orig, rot, float(v[0]), tar_time_ahead)
+    rpe = {"scene": P.pairwise_rpe(torch.cat([trajs["TRAJS_CTRS"], graph["lane_ctrs"]]),
+                                   torch.cat([trajs["TRAJS_VECS"], graph["lane_vecs"]])), "scene_mask": None}
+    tgt_rpe = P.pairwise_rpe(torch.stack([tgt_anch[0], trajs["TRAJS_CTRS"][0]]), torch.stack([tgt_anch[1], trajs["TRAJS_VECS"][0]]))
+    data = dict(ORIG=orig, ROT=rot, TRAJS=trajs, LANE_GRAPH=graph, TGT_PTS=tgt_pts, TGT_NODES=tgt_nodes, TGT_ANCH=tgt_anch,
+                RPE=rpe, TGT_RPE=tgt_rpe)
+    return P.collate_scenes([data]), lane, info, graph
