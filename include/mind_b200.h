@@ -111,6 +111,56 @@ int mind_forward(MindCtx* ctx, const MindBatch* batch, const MindOutputs* out, v
  * "cls_tok" [B,128].  Returns the number of floats written or <0. */
 int64_t mind_debug_tap(MindCtx* ctx, const char* name, float* dst, int64_t capacity, void* cuda_stream);
 
+/* ---- AIME scenario-tree step (reference planners/mind/scenario_tree.py) ---------------------
+ * One call per depth level, between two batched network calls.  All pointers are DEVICE pointers
+ * unless noted; F = frontier scenes of the level (they share n_actor: one tree = one root scene).
+ *
+ * mind_tree_level  replaces prune_merge (:281-412) + get_branch_time (:592-611) for the whole level:
+ *   in : network outputs cls [F,6], reg [F*Na,6,60,5], vel [F*Na,6,60,2]; per scene ORIG [F,2],
+ *        ROT [F,4] (row-major 2x2), actor anchors ctrs/vecs [F,Na,2]; parent histories (global
+ *        frame) hpos/hvel [F,Na,50,2], hang/hcov [F,Na,50]; parent probability pprob [F], cur_t [F];
+ *        target lane polyline tlane [n_tlane,2] (may be NULL), thresholds.
+ *   out: per (scene, rank k): order [F,6] (mode index of rank k, descending probability),
+ *        child histories cpos/cvel [F,6,Na,100,2], cang/ccov [F,6,Na,100], global predicted
+ *        positions gpos [F,6,Na,60,2], cprob [F,6] = p_mode * p_parent, keep [F,6] (survives
+ *        pruning + greedy topology merge), tb [F,6] (branch time; = pred_len when none).        */
+typedef struct {
+    int32_t n_frontier, n_actor, obs_len, pred_len, ego_idx, n_tlane;
+    float tar_dist_thres;
+    const float *cls, *reg, *vel;
+    const float *orig, *rot, *ctrs, *vecs;
+    const float *hpos, *hang, *hvel, *hcov;
+    const float* pprob;
+    const int32_t* cur_t;
+    const float* tlane;
+    float *cpos, *cang, *cvel, *ccov, *gpos;
+    int32_t* order;
+    float* cprob;
+    int32_t *keep, *tb;
+} MindTreeLevel;
+int mind_tree_level(const MindTreeLevel* a, void* cuda_stream);
+
+/* mind_tree_update  replaces update_obser (:467-567), get_new_lane_graph (utils.py:171-177),
+ * get_high_level_command (:613-652) and the actor half of collate_fn (utils.py:114-139) for the
+ * n_new children that branch: src [n_new,2] = (child row f*6+k, duration end_t-cur_t).
+ *   out: new observation windows npos/nvel [n_new,Na,50,2], nang/ncov [n_new,Na,50]; norig, nrot,
+ *        nctrs, nvecs; network inputs actors [n_new*Na,14,48], geometry geom_c/geom_v
+ *        [n_new,Na+Nl,2] (the network evaluates get_rpe from these), tgt_nodes [n_new,10,16],
+ *        tgt_rpe [n_new,20], tgt_pts [n_new,11,2].                                              */
+typedef struct {
+    int32_t n_new, n_actor, n_lane, n_tlane;
+    float tar_time_ahead;
+    const int32_t* src;
+    const float *cpos, *cang, *cvel, *ccov;
+    const float* ttype;                     /* [Na,7] actor type one-hot */
+    const float *lane_ctrs, *lane_vecs;     /* [Nl,2] anchors of the stored lane graph */
+    const float *tlane, *tinfo;             /* [n_tlane,2], [n_tlane,12] */
+    float *npos, *nang, *nvel, *ncov, *norig, *nrot, *nctrs, *nvecs;
+    float *actors, *geom_c, *geom_v, *tgt_nodes, *tgt_rpe, *tgt_pts;
+} MindTreeUpdate;
+int mind_tree_update(const MindTreeUpdate* u, void* cuda_stream);
+const char* mind_tree_last_error(void);
+
 /* bring-up self test of the TMA + tcgen05 + TMEM plumbing: D[0:128*128] = A . W^T (fp16 operands,
  * fp32 accumulate), D[128*128: 2*128*128] = the A tile read back through the software swizzle,
  * D[2*128*128: 3*128*128] = the same product with the A operand staged in tensor memory.

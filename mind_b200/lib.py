@@ -31,10 +31,26 @@ class MindOutputs(C.Structure):
                 ("cov_vel", C.c_void_p), ("param", C.c_void_p)]
 
 
+class MindTreeLevel(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("n_frontier", "n_actor", "obs_len", "pred_len", "ego_idx", "n_tlane")] +
+                [("tar_dist_thres", C.c_float)] +
+                [(n, C.c_void_p) for n in ("cls", "reg", "vel", "orig", "rot", "ctrs", "vecs", "hpos", "hang", "hvel", "hcov",
+                                           "pprob", "cur_t", "tlane", "cpos", "cang", "cvel", "ccov", "gpos", "order", "cprob",
+                                           "keep", "tb")])
+
+
+class MindTreeUpdate(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("n_new", "n_actor", "n_lane", "n_tlane")] + [("tar_time_ahead", C.c_float)] +
+                [(n, C.c_void_p) for n in ("src", "cpos", "cang", "cvel", "ccov", "ttype", "lane_ctrs", "lane_vecs", "tlane",
+                                           "tinfo", "npos", "nang", "nvel", "ncov", "norig", "nrot", "nctrs", "nvecs", "actors",
+                                           "geom_c", "geom_v", "tgt_nodes", "tgt_rpe", "tgt_pts")])
+
+
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
-           "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check", "mind_profile_read"]
+           "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check", "mind_profile_read",
+           "mind_tree_level", "mind_tree_update", "mind_tree_last_error"]
 
 _lib = None
 
@@ -76,6 +92,11 @@ def load(build_if_missing: bool = True):
     lib.mind_sync_check.restype = C.c_int
     lib.mind_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.mind_profile_read.restype = C.c_int
+    lib.mind_tree_level.argtypes = [C.POINTER(MindTreeLevel), C.c_void_p]
+    lib.mind_tree_level.restype = C.c_int
+    lib.mind_tree_update.argtypes = [C.POINTER(MindTreeUpdate), C.c_void_p]
+    lib.mind_tree_update.restype = C.c_int
+    lib.mind_tree_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

@@ -1,0 +1,407 @@
+"""AIME scenario-tree generator on the B200 path.
+
+Same constructor and methods as the reference's ScenarioTreeGenerator
+(planners/mind/scenario_tree.py:19-58: __init__(device, network, obs_len, pred_len, config),
+reset, set_target_lane, branch_aime, get_scenario_tree) and the same host control flow, including
+its quirks (depth counter in node ids :107/:321, re-examination of leaves :84-100).  Between two
+batched network calls everything numeric runs in libmind_b200.so: one mind_tree_level launch set
+per depth level (mode sort, frame transforms, pruning, topology merge, branch-time scan) and one
+mind_tree_update (observation re-normalisation, actor features, lane anchors, high-level command);
+the host only reads back four small [F,6] decision arrays per level and keeps the tree bookkeeping.
+The finished trees are handed out exactly as the reference does: a list of Tree objects whose
+node.data = [prob, trajs (Na,dur,2) f32, covs (Na,dur,1) f32, tgt_pts (11,2)] (numpy).
+"""
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import plumbing as P
+
+try:    # inside a MIND checkout: hand out the reference's own container types
+    from planners.basic.tree import Node, Tree          # type: ignore
+except Exception:                                       # stand-alone: structural mirror (planners/basic/tree.py)
+    class Node:
+        def __init__(self, key, parent_key, data):
+            self.key, self.parent_key, self.data = key, parent_key, data
+            self.children_keys, self.depth = [], 0
+
+        def __str__(self):
+            return "Node_%s: Parent: %s, Children: %s" % (self.key, self.parent_key, self.children_keys)
+
+    class Tree:
+        def __init__(self):
+            self.nodes, self.root, self.leaves = {}, None, []
+
+        def get_node(self, key):
+            return self.nodes[key]
+
+        def get_root(self):
+            return self.nodes[self.root]
+
+        def get_root_key(self):
+            return self.root
+
+        def has_children(self, key):
+            return len(self.nodes[key].children_keys) > 0
+
+        def get_children_keys(self, key):
+            return self.nodes[key].children_keys
+
+        def add_node(self, node):
+            if node.parent_key is None and not self.nodes:
+                self.nodes[node.key] = node
+                self.root = node.key
+                self.leaves.append(node.key)
+                return
+            if node.parent_key not in self.nodes:
+                raise KeyError("Parent does not exist.")
+            if node.key in self.nodes:
+                raise ValueError("Node key already exists.")
+            self.nodes[node.parent_key].children_keys.append(node.key)
+            if node.parent_key in self.leaves:
+                self.leaves.remove(node.parent_key)
+            node.depth = self.nodes[node.parent_key].depth + 1
+            self.nodes[node.key] = node
+            self.leaves.append(node.key)
+
+        def get_leaf_nodes(self):
+            return [self.nodes[k] for k in self.leaves]
+
+        def get_leaf_keys(self):
+            return self.leaves
+
+        def retrieve_nodes_to_root(self, key):
+            out, cur = [], self.nodes[key]
+            out.append(cur)
+            while cur.parent_key is not None:
+                cur = self.nodes[cur.parent_key]
+                out.append(cur)
+            return out
+
+        def size(self):
+            return len(self.nodes)
+
+
+class _Scen:
+    """scenario_tree.py:10-16 with device-side payload replaced by (level, row) handles."""
+    def __init__(self, rec, branch_flag=False, end_flag=False, terminate_flag=False):
+        self.rec = rec                  # dict: level, row, f, prob, cur_t, end_t, tb0, examined
+        self.obs_slot = None            # index of this node's scene in the next frontier
+        self.branch_flag, self.end_flag, self.terminate_flag = branch_flag, end_flag, terminate_flag
+
+
+class _Level:
+    """Device state of one frontier (F scenes): inputs of the batched network call + parents' histories."""
+    pass
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class ScenarioTreeGeneratorB200:
+    def __init__(self, device, network, obs_len=50, pred_len=60, config=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ScenarioTreeGeneratorB200 needs a CUDA device (no CPU fallback)")
+        if obs_len != 50:
+            raise ValueError("obs_len must be 50 (the network's history length)")
+        self.network, self.obs_len, self.pred_len = network, obs_len, pred_len
+        self.seq_len = obs_len + pred_len
+        self.config = config
+        self.tree = Tree()
+        self.lane_graph = None
+        self.target_lane = self.target_lane_info = None
+        self.ego_idx = 0
+        self.branch_depth = 0
+        self.net_batches: List[int] = []
+        self._lib = _lib.load()
+        self._levels: List[_Level] = []
+        self.front_end = None           # optional callable (lcl_smp, agent_obs) -> collated scene dict
+
+    # ---- reference surface ------------------------------------------------------------------
+    def reset(self):
+        self.branch_depth = 0
+        self.tree = Tree()
+        self._levels = []
+        self.net_batches = []
+
+    def set_target_lane(self, target_lane, target_lane_info):                     # :110-120
+        self.target_lane = torch.from_numpy(np.array(target_lane)).float().to(self.device).contiguous()
+        self.target_lane_info = P.pack_target_lane_info(target_lane_info).float().to(self.device).contiguous()
+
+    def branch_aime(self, lcl_smp, agent_obs):                                    # :38-58
+        data = self.process_data(lcl_smp, agent_obs)
+        return self.rollout(data)
+
+    def process_data(self, lcl_smp, agent_obs):
+        """:122-206 is the av2 / shapely front end (out of this path's scope); plug the
+        reference's own process_data (or any equivalent) in through `front_end`."""
+        if self.front_end is None:
+            raise NotImplementedError("process_data needs av2/shapely; set generator.front_end = callable returning the "
+                                      "collated scene dict, or call rollout(data)")
+        return self.front_end(lcl_smp, agent_obs)
+
+    def rollout(self, data):
+        """AIME iteration from a collated one-scene dict (what process_data returns)."""
+        self.init_scenario_tree(data)
+        nodes = self.get_branch_set()
+        guard = 0
+        while nodes:
+            level = self._levels[-1]
+            self.predict_scenes(level)
+            self.create_nodes(self.prune_merge(level, nodes))
+            self.decide_branch()
+            nodes = self.get_branch_set()
+            guard += 1
+            if guard > 64:
+                raise RuntimeError("scenario tree did not converge (re-expansion loop, reference quirk :84-100)")
+        assert len(self.get_end_set()) > 0, "No end node found in the scenario tree."
+        return self.get_scenario_tree()
+
+    # ---- level construction -----------------------------------------------------------------
+    def _root_level(self, data) -> _Level:
+        """prepare_root_data (:414-465): observations (actor-local) -> global-frame histories."""
+        dev = self.device
+        d = P.to_device(data, dev)
+        tj = d["TRAJS"][0]
+        orig, rot = d["ORIG"][0].float(), d["ROT"][0].float()
+        ctrs, vecs = tj["TRAJS_CTRS"].float(), tj["TRAJS_VECS"].float()
+        th_g = torch.atan2(rot[1, 0], rot[0, 0])
+        th = torch.atan2(vecs[:, 1], vecs[:, 0])
+        R = torch.stack([torch.cos(th), -torch.sin(th), torch.sin(th), torch.cos(th)], 1).view(-1, 2, 2)
+        pos = torch.matmul(tj["TRAJS_POS_OBS"].float(), R.transpose(-1, -2)) + ctrs[:, None]
+        vel = torch.matmul(tj["TRAJS_VEL_OBS"].float(), R.transpose(-1, -2))
+        ang = torch.atan2(tj["TRAJS_ANG_OBS"][..., 1], tj["TRAJS_ANG_OBS"][..., 0]).float()
+        L = _Level()
+        L.F, L.Na = 1, pos.shape[0]
+        L.hpos = (torch.matmul(pos, rot.T) + orig).contiguous().view(1, L.Na, 50, 2)
+        L.hvel = torch.matmul(vel, rot.T).contiguous().view(1, L.Na, 50, 2)
+        L.hang = (ang + th[:, None] + th_g).contiguous().view(1, L.Na, 50)
+        L.hcov = torch.full((1, L.Na, 50), 1e-5, device=dev)
+        L.orig, L.rot = orig.view(1, 2).contiguous(), rot.reshape(1, 4).contiguous()
+        L.ctrs, L.vecs = ctrs.view(1, L.Na, 2).contiguous(), vecs.view(1, L.Na, 2).contiguous()
+        L.pprob = torch.ones(1, device=dev)
+        L.cur_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.cur_t_host = [0]
+        L.tgt_pts = d["TGT_PTS"][0].float().view(1, 11, 2)
+        L.net_in = self.network.pre_process(data)
+        L.geom = None
+        L.parent_keys = ["root"]
+        # constants of the tree
+        self._ttype = tj["TRAJS_TYPE"][:, 0, :].float().contiguous()
+        g = P.to_device(self.lane_graph if self.lane_graph is not None else data["LANE_GRAPH"][0], dev)
+        self._lane_ctrs, self._lane_vecs = g["lane_ctrs"].float().contiguous(), g["lane_vecs"].float().contiguous()
+        self._lanes = d["LANES"].float().contiguous()
+        self._n_lane = self._lanes.shape[0]
+        return L
+
+    def init_scenario_tree(self, data):                                           # :60-67
+        root = self._root_level(data)
+        self._levels.append(root)
+        rn = Node("root", None, _Scen(None, branch_flag=True))
+        rn.data.obs_slot = 0
+        self.tree.add_node(rn)
+        self.predict_scenes(root)
+        self.create_nodes(self.prune_merge(root, [rn]))
+        self.decide_branch()
+
+    def predict_scenes(self, level: _Level):                                      # :69-71 (one batched call per level)
+        self.net_batches.append(level.F)
+        pk = self.network.forward_packed(level.net_in, geom=level.geom)
+        level.cls, level.reg, level.vel = pk[0], pk[1], pk[2]
+        return pk
+
+    # ---- prune & merge (:281-412) + branch-time scan (:592-611), whole level on the device -----
+    def prune_merge(self, level: _Level, nodes):
+        dev, F, Na = self.device, level.F, level.Na
+        f32 = dict(device=dev, dtype=torch.float32)
+        level.cpos = torch.empty(F, 6, Na, 100, 2, **f32)
+        level.cvel = torch.empty(F, 6, Na, 100, 2, **f32)
+        level.cang = torch.empty(F, 6, Na, 100, **f32)
+        level.ccov = torch.empty(F, 6, Na, 100, **f32)
+        level.gpos = torch.empty(F, 6, Na, 60, 2, **f32)
+        ibuf = torch.empty(3, F, 6, device=dev, dtype=torch.int32)      # order, keep, tb
+        cprob = torch.empty(F, 6, **f32)
+        a = _lib.MindTreeLevel()
+        a.n_frontier, a.n_actor, a.obs_len, a.pred_len = F, Na, self.obs_len, self.pred_len
+        a.ego_idx = self.ego_idx if self.ego_idx is not None else -1
+        a.n_tlane = 0 if self.target_lane is None else self.target_lane.shape[0]
+        a.tar_dist_thres = float(self.config.tar_dist_thres)
+        for name, t in (("cls", level.cls), ("reg", level.reg), ("vel", level.vel), ("orig", level.orig), ("rot", level.rot),
+                        ("ctrs", level.ctrs), ("vecs", level.vecs), ("hpos", level.hpos), ("hang", level.hang),
+                        ("hvel", level.hvel), ("hcov", level.hcov), ("pprob", level.pprob), ("cur_t", level.cur_t),
+                        ("tlane", self.target_lane), ("cpos", level.cpos), ("cang", level.cang), ("cvel", level.cvel),
+                        ("ccov", level.ccov), ("gpos", level.gpos), ("order", ibuf[0]), ("cprob", cprob), ("keep", ibuf[1]),
+                        ("tb", ibuf[2])):
+            setattr(a, name, t.data_ptr() if t is not None else None)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._lib.mind_tree_level(C.byref(a), C.c_void_p(stream)) != 0:
+            raise RuntimeError(self._lib.mind_tree_last_error().decode())
+        lv_index = next(i for i, L in enumerate(self._levels) if L is level)
+        ih = ibuf.cpu().numpy()                                           # the level's only D2H: decisions
+        ph = cprob.cpu().numpy()
+        out = []
+        for f in range(F):
+            for k in range(6):
+                if not ih[1, f, k]:
+                    continue
+                mode = int(ih[0, f, k])
+                out.append(dict(SCEN_ID="{}_{}_{}".format(self.branch_depth, f, mode), PARENT_ID=nodes[f].key,
+                                level=lv_index, row=f * 6 + k, f=f, prob=np.float32(ph[f, k]), cur_t=level.cur_t_host[f],
+                                end_t=self.pred_len, tb0=int(ih[2, f, k]), examined=False))
+        return out
+
+    def create_nodes(self, preds):                                                # :73-80
+        for p in preds:
+            self.tree.add_node(Node(p["SCEN_ID"], p["PARENT_ID"], _Scen(p)))
+
+    def get_branch_time(self, rec):                                               # :592-611
+        if not rec["examined"]:
+            rec["examined"] = True
+            if rec["tb0"] < rec["end_t"]:
+                rec["end_t"] = rec["tb0"]
+        return rec["end_t"]
+
+    def decide_branch(self):                                                      # :82-100
+        to_branch = []
+        for l in self.tree.get_leaf_nodes():
+            s = l.data
+            if s.branch_flag:
+                s.branch_flag = False
+                s.terminate_flag = True
+            elif not s.end_flag:
+                if l.depth >= self.config.max_depth:
+                    s.terminate_flag = True
+                else:
+                    t_b = self.get_branch_time(s.rec)
+                    if t_b < self.pred_len:
+                        to_branch.append(l)
+                        s.branch_flag = True
+                    else:
+                        s.end_flag = True
+        if to_branch:
+            self._levels.append(self.update_obser(to_branch))
+
+    def get_branch_set(self):                                                     # :102-108
+        out = [l for l in self.tree.get_leaf_nodes() if l.data.branch_flag]
+        self.branch_depth += 1
+        return out
+
+    def get_end_set(self):                                                        # :274-279
+        return [n for n in self.tree.get_leaf_nodes() if n.data.end_flag]
+
+    # ---- observation update for every branching child of the level (:467-567) ------------------
+    def update_obser(self, nodes) -> _Level:
+        dev, G = self.device, len(nodes)
+        Na, Nl = self._levels[0].Na, self._n_lane
+        f32 = dict(device=dev, dtype=torch.float32)
+        N = _Level()
+        N.F, N.Na = G, Na
+        N.hpos, N.hvel = torch.empty(G, Na, 50, 2, **f32), torch.empty(G, Na, 50, 2, **f32)
+        N.hang, N.hcov = torch.empty(G, Na, 50, **f32), torch.empty(G, Na, 50, **f32)
+        N.orig, N.rot = torch.empty(G, 2, **f32), torch.empty(G, 4, **f32)
+        N.ctrs, N.vecs = torch.empty(G, Na, 2, **f32), torch.empty(G, Na, 2, **f32)
+        actors = torch.empty(G * Na, 14, 48, **f32)
+        geom_c, geom_v = torch.empty(G, Na + Nl, 2, **f32), torch.empty(G, Na + Nl, 2, **f32)
+        tgt_nodes, tgt_rpe = torch.empty(G, 10, 16, **f32), torch.empty(G, 20, **f32)
+        N.tgt_pts = torch.empty(G, 11, 2, **f32)
+        N.pprob = torch.tensor([float(n.data.rec["prob"]) for n in nodes], **f32)
+        N.cur_t_host = [int(n.data.rec["end_t"]) for n in nodes]
+        N.cur_t = torch.tensor(N.cur_t_host, dtype=torch.int32, device=dev)
+        N.parent_keys = [n.key for n in nodes]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        by_level = {}
+        for g, n in enumerate(nodes):
+            by_level.setdefault(n.data.rec["level"], []).append(g)
+        for lv, gs in by_level.items():
+            if gs != list(range(gs[0], gs[0] + len(gs))):
+                raise RuntimeError("frontier nodes of one source level must be contiguous")
+            src_level = self._levels[lv]
+            src = torch.tensor([[nodes[g].data.rec["row"], nodes[g].data.rec["end_t"] - nodes[g].data.rec["cur_t"]] for g in gs],
+                               dtype=torch.int32, device=dev)
+            g0, n_new = gs[0], len(gs)
+            u = _lib.MindTreeUpdate()
+            u.n_new, u.n_actor, u.n_lane, u.n_tlane = n_new, Na, Nl, self.target_lane.shape[0]
+            u.tar_time_ahead = float(self.config.tar_time_ahead)
+            for name, t in (("src", src), ("cpos", src_level.cpos), ("cang", src_level.cang), ("cvel", src_level.cvel),
+                            ("ccov", src_level.ccov), ("ttype", self._ttype), ("lane_ctrs", self._lane_ctrs),
+                            ("lane_vecs", self._lane_vecs), ("tlane", self.target_lane), ("tinfo", self.target_lane_info),
+                            ("npos", N.hpos[g0:]), ("nang", N.hang[g0:]), ("nvel", N.hvel[g0:]), ("ncov", N.hcov[g0:]),
+                            ("norig", N.orig[g0:]), ("nrot", N.rot[g0:]), ("nctrs", N.ctrs[g0:]), ("nvecs", N.vecs[g0:]),
+                            ("actors", actors[g0 * Na:]), ("geom_c", geom_c[g0:]), ("geom_v", geom_v[g0:]),
+                            ("tgt_nodes", tgt_nodes[g0:]), ("tgt_rpe", tgt_rpe[g0:]), ("tgt_pts", N.tgt_pts[g0:])):
+                setattr(u, name, t.data_ptr())
+            if self._lib.mind_tree_update(C.byref(u), C.c_void_p(stream)) != 0:
+                raise RuntimeError(self._lib.mind_tree_last_error().decode())
+            self._keep = src
+        a_idcs = [torch.arange(g * Na, (g + 1) * Na) for g in range(G)]
+        l_idcs = [torch.arange(g * Nl, (g + 1) * Nl) for g in range(G)]
+        lanes = self._lanes.unsqueeze(0).expand(G, -1, -1, -1).reshape(G * Nl, 10, 16)
+        N.net_in = (actors, a_idcs, lanes, l_idcs, None, tgt_nodes, tgt_rpe)
+        N.geom = (geom_c.view(-1, 2), geom_v.view(-1, 2))
+        for g, n in enumerate(nodes):
+            n.data.obs_slot = g
+        return N
+
+    # ---- output packing (:208-272) -------------------------------------------------------------
+    def get_scenario_tree(self):
+        data_tree = Tree()
+        root = self.tree.get_root()
+        data_tree.add_node(Node(root.key, None, [1.0]))
+        for n in self.get_end_set():                                   # label the branches that finished
+            while n.parent_key is not None:
+                n.data.end_flag = True
+                n = self.tree.get_node(n.parent_key)
+        for key in root.children_keys:
+            n = self.tree.get_node(key)
+            if not n.data.end_flag:
+                continue
+            data_tree.add_node(Node(n.key, root.key, [1.0]))
+            queue = [n]
+            while queue:
+                c = queue.pop(0)
+                pp = data_tree.get_node(c.key).data[0]
+                kids = [self.tree.get_node(k) for k in c.children_keys if self.tree.get_node(k).data.end_flag]
+                total = 0.0
+                for k in kids:
+                    total += np.asarray(k.data.rec["prob"])
+                for k in kids:
+                    data_tree.add_node(Node(k.key, c.key, [np.asarray(k.data.rec["prob"]) / total * pp]))
+                    queue.append(k)
+        host = {}                                                     # one D2H per level that contributes nodes
+
+        def level_host(lv):
+            if lv not in host:
+                L = self._levels[lv]
+                host[lv] = (L.cpos.cpu().numpy(), L.ccov.cpu().numpy(), L.tgt_pts.cpu().numpy())
+            return host[lv]
+        for n in self.get_end_set():
+            while n.parent_key is not None:
+                rec = n.data.rec
+                dur = rec["end_t"] - rec["cur_t"]
+                dn = data_tree.get_node(n.key)
+                if len(dn.data) == 1:
+                    cpos, ccov, tgt = level_host(rec["level"])
+                    f, k = rec["row"] // 6, rec["row"] % 6
+                    dn.data += [np.ascontiguousarray(cpos[f, k, :, self.obs_len:self.obs_len + dur, :]),
+                                np.ascontiguousarray(ccov[f, k, :, self.obs_len:self.obs_len + dur, None]),
+                                tgt[f].copy()]
+                n = self.tree.get_node(n.parent_key)
+        trees = []
+        for key in data_tree.get_root().children_keys:
+            st = Tree()
+            n = data_tree.get_node(key)
+            st.add_node(Node(n.key, None, n.data))
+            queue = [n]
+            while queue:
+                c = queue.pop(0)
+                for ck in c.children_keys:
+                    cn = data_tree.get_node(ck)
+                    st.add_node(Node(cn.key, c.key, cn.data))
+                    queue.append(cn)
+            trees.append(st)
+        return trees

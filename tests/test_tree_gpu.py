@@ -1,0 +1,45 @@
+"""GPU: AIME scenario tree on the B200 path (CUDA tree-step kernels + CUDA predictor) vs the golden
+trees dumped from the unmodified reference: node ids / parents / per-level batch sizes exact
+(bit-exact mode and branch index selection), probabilities, trajectories, covariances within 1e-3."""
+import copy
+
+import pytest
+import torch
+
+from conftest import load_golden
+from test_tree_oracle import TreeCfg, compare_with_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def flatten(trees):
+    out = {}
+    for t in trees:
+        for k, n in t.nodes.items():
+            out[k] = (n.parent_key, float(n.data[0]), n.data[1], n.data[2], n.data[3])
+    return out
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16tc"])
+@pytest.mark.parametrize("v", [0, 1, 2])
+def test_tree_vs_golden(ckpt_sd, v, prec):
+    from mind_b200 import synth
+    from mind_b200.predictor import ScenePredNetB200
+    from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
+    from oracle.make_golden_tree import VARIANTS
+    dev = torch.device("cuda", 0)
+    net = ScenePredNetB200(None, dev)
+    net.load_state_dict(ckpt_sd)
+    net.set_precision(prec)
+    gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, TreeCfg())
+    data, lane, info, graph = synth.scene_s3(**VARIANTS[v])
+    gen.reset()
+    gen.set_target_lane(lane, info)
+    gen.lane_graph = copy.deepcopy(graph)
+    trees = gen.rollout(data)
+    flat = flatten(trees)
+    gold = load_golden("tree_s3.npz")
+    compare_with_golden(flat, gen.net_batches, gold, v)
+    for t in trees:
+        for n in t.nodes.values():
+            assert n.data[1].dtype.name == "float32" and n.data[1].ndim == 3 and n.data[2].shape[-1] == 1
