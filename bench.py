@@ -136,6 +136,38 @@ def cpu_port_rate(sd, seconds_target=10.0, chunk=2, seed0=5000):
     return n / el, cores, "%d S2 scenes (32 actors x 128 lanes) in %.1f s, batches of %d" % (n, el, chunk)
 
 
+class _TreeCfg:      # planners/mind/configs/planning/demo_1.py:3-10
+    max_depth = 5
+    tar_dist_thres = 10.0
+    tar_time_ahead = 5.0
+
+
+def bench_tree(net, dev, reps=5):
+    """tree-rollout ms/scene (BASELINE.json configs[2] stand-in): S3 kinematic scene (8 actors, 60 lane
+    polylines); (i) the natural AIME tree, (ii) forced-full depth 4 x branch 6 (level batches 1/6/36/216,
+    259 scene predictions, 1296 leaves).  Wall time from the collated root scene to the packed trees."""
+    import copy
+    from mind_b200 import synth
+    from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
+    args = dict(x0=(100, 108, 92, 120, 112, 96, 130, 85), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0), v=(5, 9, 3, 8, 2, 10, 6, 12))
+    out = {}
+    for name, ff in (("natural", None), ("forced_full", (10, 20, 30))):
+        gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
+        gen.force_full = ff
+        times = []
+        for r in range(reps + 2):
+            data, lane, info, graph = synth.scene_s3(**args)
+            gen.reset(); gen.set_target_lane(lane, info); gen.lane_graph = copy.deepcopy(graph)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            trees = gen.rollout(data)
+            torch.cuda.synchronize()
+            times.append((time.perf_counter() - t0) * 1e3)
+        out[name] = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches),
+                     "nodes": gen.tree.size(), "trees": len(trees)}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -296,6 +328,7 @@ def run_native(args):
                 "hbm_algorithmic_gbs": hb, "hbm_frac_of_measured": hb / pk["hbm"],
                 "flops_per_launch": flops, "bytes_per_launch": B * fusion_bytes_per_scene(True)}
     cpu_v, cores, sample = cpu_port_rate(sd)
+    tree = bench_tree(net, dev)
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -309,7 +342,8 @@ def run_native(args):
                     "ms_per_step": ms2 / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "stage_ms_per_step": stage_ms}
+            "stage_ms_per_step": stage_ms,
+            "tree_rollout": {"unit": "ms/scene", "scene": "S3 kinematic, 8 actors x 60 lane polylines", **tree}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -121,6 +121,8 @@ class ScenarioTreeGeneratorB200:
         self._lib = _lib.load()
         self._levels: List[_Level] = []
         self.front_end = None           # optional callable (lcl_smp, agent_obs) -> collated scene dict
+        # benchmark mode: keep all 6 modes of every scene, branch at fixed times
+        self.force_full = None          # e.g. (10, 20, 30): children of level d branch at force_full[d]
 
     # ---- reference surface ------------------------------------------------------------------
     def reset(self):
@@ -244,6 +246,9 @@ class ScenarioTreeGeneratorB200:
         lv_index = next(i for i, L in enumerate(self._levels) if L is level)
         ih = ibuf.cpu().numpy()                                           # the level's only D2H: decisions
         ph = cprob.cpu().numpy()
+        if self.force_full is not None:
+            ih[1] = 1
+            ih[2] = self.force_full[lv_index] if lv_index < len(self.force_full) else self.pred_len
         out = []
         for f in range(F):
             for k in range(6):
