@@ -235,7 +235,7 @@ def run_native(args):
             if gather_bufs is None:
                 gather_bufs = [torch.empty((world,) + tuple(t.shape), device=dev) for t in out[:3]]
             for g, t in zip(gather_bufs, out[:3]):   # cls, reg, vel : what prune_merge consumes
-                dist.all_gather_into_tensor(g, t)
+                dist.all_gather_into_tensor(g, t)        # equal shards: mind_b200.distributed fast path, preallocated
         return out
 
     for _ in range(args.warmup):
