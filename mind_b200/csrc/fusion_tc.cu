@@ -22,7 +22,7 @@ namespace mind {
 
 namespace tc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr float kEps = 1e-5f;
 
 // ---- shared memory map (bytes, relative to a 1024-aligned base) ----
@@ -33,8 +33,8 @@ constexpr uint32_t SM_S = SM_TILE1 + 32768;           // float [16][132]
 constexpr uint32_t SM_Q = SM_S + 16 * 132 * 4;        // float [16][132]
 constexpr uint32_t SM_T = SM_Q + 16 * 132 * 4;        // float [8][132]
 constexpr uint32_t SM_P = SM_T + 8 * 132 * 4;         // float [8][128] layer params
-constexpr uint32_t SM_STAT = SM_P + 8 * 128 * 4;      // float2 [2 buf][2 half][128]
-constexpr uint32_t SM_BAR = SM_STAT + 2 * 2 * 128 * 8;
+constexpr uint32_t SM_STAT = SM_P + 8 * 128 * 4;      // float2 [2 buf][4 quarter][128]
+constexpr uint32_t SM_BAR = SM_STAT + 2 * 4 * 128 * 8;
 constexpr uint32_t SM_TMEM = SM_BAR + 64;
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SM_TOTAL + 1024;      // slack for manual 1024 B alignment
@@ -157,6 +157,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
           "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),         \
           "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)          \
         : "memory")
+#define TMEM_ST_X16(taddr, r)                                                                                  \
+    asm volatile(                                                                                              \
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" \
+        ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),  \
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)       \
+        : "memory")
 // A operand from tensor memory (lane = row, two fp16 K elements per 32-bit cell), B from shared memory
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -209,6 +215,8 @@ struct LayerArgs {
 //   [  0,128)  D1 = edge.W_e^T ; after epilogue 1 the same columns hold the A operand of G2:
 //              memory as an fp16 (hi, lo) pair, two K elements per 32-bit cell: hi -> [0,64), lo -> [64,128)
 //   [128,256)  Dpe   [256,384)  Dk   [384,512)  Dv
+// Thread map: 512 threads = 16 warps; warp w owns TMEM lanes 32*(w&3).. (pair rows) and the
+// 32-channel column quarter q = w>>2, so every LayerNorm exchanges 4 partial sums through smem.
 __global__ void __launch_bounds__(kThreads, 1)
 k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -218,17 +226,18 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     float* sQ = reinterpret_cast<float*>(sgen + SM_Q);
     float* sT = reinterpret_cast<float*>(sgen + SM_T);
     float* sP = reinterpret_cast<float*>(sgen + SM_P);
-    float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);
+    float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);   // [2 buf][4 quarter][128 row]
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
-    const uint32_t bar_w = sbase + SM_BAR, bar_m1 = bar_w + 8, bar_m2 = bar_w + 16, bar_ld0 = bar_w + 24;   // bar_ld0, bar_ld0+8
+    const uint32_t bar_w = sbase + SM_BAR, bar_m1 = bar_w + 8, bar_m2a = bar_w + 16, bar_m2b = bar_w + 24, bar_ld0 = bar_w + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int half = warp >> 2;                  // column half: channels [64*half, 64*half+64)
+    const int q = warp >> 2;                     // column quarter: channels [32q, 32q+32)
     const int row = (warp & 3) * 32 + lane;      // TMEM lane = pair row inside the tile
     const int i_l = row >> 4, j_l = row & 15;
 
     if (tid == 0) {
-        mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1); mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
+        mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2a, 1); mbar_init(bar_m2b, 1);
+        mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -241,55 +250,67 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *sTmem;
 
-    // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
-    if (tid == 0) {
+    if (tid == 0) {   // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
         mbar_expect_tx(bar_w, 131072u);
         for (int kb = 0; kb < 2; ++kb)
             for (int m = 0; m < 4; ++m) tma_load_2d(sbase + SM_W + kb * 65536 + m * 16384, &wmap, bar_w, kb * 64, m * 128);
     }
     mbar_wait(bar_w, 0, a.err, E_LOAD_W);
 
-    uint32_t par = 0;             // parity of bar_m1 / bar_m2 (one completion per tile)
-    uint32_t lpar0 = 0, lpar1 = 0;   // parity of the two edge-load barriers (one completion per use of the buffer)
-    int cur = 0;                  // edge buffer of the current tile
+    uint32_t par = 0;                // parity of bar_m1 / bar_m2a / bar_m2b (one completion per tile)
+    uint32_t lpar0 = 0, lpar1 = 0;   // parity of the two edge-load barriers
+    int cur = 0;                     // edge buffer of the current tile
+    bool g1_ahead = false;           // (thread 0) G1 of the current tile was already issued behind the previous G2
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t col0 = (uint32_t)half * 64;
+    const int col0 = q * 32;
+    const uint32_t tile_off = (uint32_t)(q >> 1) * 16384u;      // k-block of this quarter inside an edge tile
+    const int chunk0 = (q & 1) * 4;                              // first 16-byte chunk of this quarter in its k-block
     const float* Pm = sP;
+
+    // G1 of one tile: D1 = edge(tX) . W_e^T
+    auto issue_g1 = [&](uint32_t tX) {
+        const uint32_t id128 = umma_idesc_f16(128);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
+            const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+            umma_f16(tmem + 0, umma_desc_sw128(tX + ko), umma_desc_sw128(sbase + SM_W + kw), id128, kk > 0);
+        }
+        umma_commit(bar_m1);
+    };
 
     for (int wi = blockIdx.x; wi < a.n_work; wi += gridDim.x) {
         const TcWork wk = a.work[wi];
         const int N = wk.n, j0 = wk.j0, b = wk.b;
         const int n_chunks = (N + 7) >> 3;
         const int64_t tok0 = (int64_t)b * a.Nmax;
-        if (tid == 0) {   // first edge tile of the work item -> buffer `cur` (free: see end of the loop body)
+        if (tid == 0) {   // first edge tile of the work item -> buffer `cur`
             const uint32_t bl = bar_ld0 + 8 * cur;
             mbar_expect_tx(bl, 32768u);
             tma_load_4d(sbase + SM_TILE0 + cur * 32768, &emap, bl, 0, j0, 0, b);
             tma_load_4d(sbase + SM_TILE0 + cur * 32768 + 16384, &emap, bl, 64, j0, 0, b);
         }
-        // S (src term, per query j) and q tiles
-        for (int idx = tid; idx < 16 * 32; idx += kThreads) {
-            const int jj = idx >> 5, c4 = idx & 31;
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        {   // S (src term, per query j) and q tiles: 16 x 32 float4 each, one per thread
+            const int jj = tid >> 5, c4 = tid & 31;
+            float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), qv = sv;
             if (j0 + jj < N) {
                 const float* p = a.stq + (tok0 + j0 + jj) * 384;
-                s = reinterpret_cast<const float4*>(p)[c4];
-                q = reinterpret_cast<const float4*>(p + 256)[c4];
+                sv = reinterpret_cast<const float4*>(p)[c4];
+                qv = reinterpret_cast<const float4*>(p + 256)[c4];
             }
-            *reinterpret_cast<float4*>(sS + jj * 132 + c4 * 4) = s;
-            *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = q;
+            *reinterpret_cast<float4*>(sS + jj * 132 + c4 * 4) = sv;
+            *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = qv;
         }
-        float acc[64], mrun[4], lrun[4];
+        float acc[32], mrun[2], lrun[2];
 #pragma unroll
-        for (int k = 0; k < 64; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { mrun[h] = -INFINITY; lrun[h] = 0.f; }
+        for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+        mrun[0] = mrun[1] = -INFINITY; lrun[0] = lrun[1] = 0.f;
 
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int i0 = ch * 8;
             const uint32_t tX = sbase + SM_TILE0 + cur * 32768;          // edge tile (in place -> edge')
             const uint32_t tN = sbase + SM_TILE0 + (cur ^ 1) * 32768;    // next edge tile (prefetch target)
-            {   // T (target term, per key i) tile
+            if (tid < 256) {   // T (target term, per key i) tile
                 const int ii = tid >> 5, c4 = tid & 31;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i0 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + ii) * 384 + 128)[c4];
@@ -298,16 +319,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             mbar_wait(bar_ld0 + 8 * cur, cur ? lpar1 : lpar0, a.err, E_LOAD_EDGE);   // every thread observes the TMA completion
             if (cur) lpar1 ^= 1; else lpar0 ^= 1;
             if (tid == 0) {
-                tc_fence_after();
-                const uint32_t id128 = umma_idesc_f16(128);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
-                    const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-                    umma_f16(tmem + 0, umma_desc_sw128(tX + ko), umma_desc_sw128(sbase + SM_W + kw), id128, kk > 0);
-                }
-                umma_commit(bar_m1);
-                if (ch + 1 < n_chunks) {                       // prefetch the next edge tile while this one is processed
+                if (!g1_ahead) { tc_fence_after(); issue_g1(tX); }
+                g1_ahead = false;
+                if (ch + 1 < n_chunks) {                       // prefetch the next edge tile
                     tma_wait_read0();                          // the edge' store that last used tN has drained
                     const uint32_t bl = bar_ld0 + 8 * (cur ^ 1);
                     mbar_expect_tx(bl, 32768u);
@@ -320,54 +334,55 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             tc_fence_after();
 
             // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 (hi, lo) A operand in TMEM ----
-            float v[64];
+            float v[32];
             {
                 uint32_t r[32];
+                TMEM_LD_X32(tmem + lane_base + col0, r);
+                tmem_wait_ld();
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    TMEM_LD_X32(tmem + lane_base + col0 + p * 32, r);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const int c = (int)col0 + p * 32 + k4 * 4;
-                        const float4 s = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
-                        const float4 t = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
-                        const float x0 = __uint_as_float(r[k4 * 4 + 0]) + s.x + t.x;
-                        const float x1 = __uint_as_float(r[k4 * 4 + 1]) + s.y + t.y;
-                        const float x2 = __uint_as_float(r[k4 * 4 + 2]) + s.z + t.z;
-                        const float x3 = __uint_as_float(r[k4 * 4 + 3]) + s.w + t.w;
-                        v[p * 32 + k4 * 4 + 0] = x0; v[p * 32 + k4 * 4 + 1] = x1;
-                        v[p * 32 + k4 * 4 + 2] = x2; v[p * 32 + k4 * 4 + 3] = x3;
-                        s1 += (x0 + x1) + (x2 + x3);
-                        s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
-                    }
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const int c = col0 + k4 * 4;
+                    const float4 s = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
+                    const float4 t = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
+                    const float x0 = __uint_as_float(r[k4 * 4 + 0]) + s.x + t.x;
+                    const float x1 = __uint_as_float(r[k4 * 4 + 1]) + s.y + t.y;
+                    const float x2 = __uint_as_float(r[k4 * 4 + 2]) + s.z + t.z;
+                    const float x3 = __uint_as_float(r[k4 * 4 + 3]) + s.w + t.w;
+                    v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
+                    s1 += (x0 + x1) + (x2 + x3);
+                    s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
                 }
-                sStat[(0 * 2 + half) * 128 + row] = make_float2(s1, s2);
+                sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
             }
             tc_fence_before();
             __syncthreads();                                   // B1: statistics exchanged, every D1 read retired
             tc_fence_after();
             {
-                const float2 o = sStat[(0 * 2 + (half ^ 1)) * 128 + row];
-                const float2 m = sStat[(0 * 2 + half) * 128 + row];
-                const float mean = (o.x + m.x) * (1.f / 128.f);
-                const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
+                const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
+                const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
+                const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
+                const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + kEps);
-                uint32_t hi[32], lo[32];
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int k2 = 0; k2 < 32; ++k2) {
-                    const int c = (int)col0 + k2 * 2;
-                    const float y0 = fmaxf((v[k2 * 2] - mean) * rstd * Pm[P_MEM_G * 128 + c] + Pm[P_MEM_B * 128 + c], 0.f);
-                    const float y1 = fmaxf((v[k2 * 2 + 1] - mean) * rstd * Pm[P_MEM_G * 128 + c + 1] + Pm[P_MEM_B * 128 + c + 1], 0.f);
-                    const __half2 h = __floats2half2_rn(y0, y1);
-                    const float2 hf = __half22float2(h);
-                    hi[k2] = *reinterpret_cast<const uint32_t*>(&h);
-                    lo[k2] = pack_h2(y0 - hf.x, y1 - hf.y);
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 g = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + col0 + k4 * 4);
+                    const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + col0 + k4 * 4);
+                    const float y0 = fmaxf((v[k4 * 4 + 0] - mean) * rstd * g.x + be.x, 0.f);
+                    const float y1 = fmaxf((v[k4 * 4 + 1] - mean) * rstd * g.y + be.y, 0.f);
+                    const float y2 = fmaxf((v[k4 * 4 + 2] - mean) * rstd * g.z + be.z, 0.f);
+                    const float y3 = fmaxf((v[k4 * 4 + 3] - mean) * rstd * g.w + be.w, 0.f);
+                    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    hi[k4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                    hi[k4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    lo[k4 * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
+                    lo[k4 * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
                 }
-                // K elements [64*half, +64) -> cells [32*half, +32) of the hi block and of the lo block
-                TMEM_ST_X32(tmem + lane_base + half * 32, hi);
-                TMEM_ST_X32(tmem + lane_base + 64 + half * 32, lo);
+                // K elements [32q, +32) -> cells [16q, +16) of the hi block and of the lo block
+                TMEM_ST_X16(tmem + lane_base + q * 16, hi);
+                TMEM_ST_X16(tmem + lane_base + 64 + q * 16, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             tc_fence_before();
@@ -375,58 +390,72 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t id128 = umma_idesc_f16(128), id256 = umma_idesc_f16(256);
+                if (a.has_edge) {                              // W_pe first: its epilogue overlaps the K|V MMAs
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+                        const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 128 * 128);
+                        umma_f16_ts(tmem + 128, tmem + kk * 8, bd, id128, kk > 0);
+                        umma_f16_ts(tmem + 128, tmem + 64 + kk * 8, bd, id128, 1);
+                    }
+                }
+                umma_commit(bar_m2a);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-                    const uint32_t a_hi = tmem + kk * 8, a_lo = tmem + 64 + kk * 8;
-                    if (a.has_edge) {
-                        const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 128 * 128);
-                        umma_f16_ts(tmem + 128, a_hi, bd, id128, kk > 0);
-                        umma_f16_ts(tmem + 128, a_lo, bd, id128, 1);
-                    }
                     const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 256 * 128);
-                    umma_f16_ts(tmem + 256, a_hi, bd, id256, kk > 0);
-                    umma_f16_ts(tmem + 256, a_lo, bd, id256, 1);
+                    umma_f16_ts(tmem + 256, tmem + kk * 8, bd, id256, kk > 0);
+                    umma_f16_ts(tmem + 256, tmem + 64 + kk * 8, bd, id256, 1);
                 }
-                umma_commit(bar_m2);
+                umma_commit(bar_m2b);
+                // G1 of the next tile runs behind G2 (MMAs execute in issue order; D1 is free once G2 has read A)
+                if (ch + 1 < n_chunks && mbar_try_wait(bar_ld0 + 8 * (cur ^ 1), (cur ^ 1) ? lpar1 : lpar0)) {
+                    tc_fence_after();
+                    issue_g1(tN);
+                    g1_ahead = true;
+                }
             }
-            mbar_wait(bar_m2, par, a.err, E_MMA2);
-            tc_fence_after();
 
             // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
             if (a.has_edge) {
+                mbar_wait(bar_m2a, par, a.err, E_MMA2);
+                tc_fence_after();
                 uint32_t r[32];
+                TMEM_LD_X32(tmem + lane_base + 128 + col0, r);
+                tmem_wait_ld();
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    TMEM_LD_X32(tmem + lane_base + 128 + col0 + p * 32, r);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const float x = __uint_as_float(r[k]) + Pm[P_BPE * 128 + (int)col0 + p * 32 + k];
-                        v[p * 32 + k] = x;
-                        s1 += x;
-                        s2 += x * x;
-                    }
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + col0 + k4 * 4);
+                    const float x0 = __uint_as_float(r[k4 * 4 + 0]) + bb.x, x1 = __uint_as_float(r[k4 * 4 + 1]) + bb.y;
+                    const float x2 = __uint_as_float(r[k4 * 4 + 2]) + bb.z, x3 = __uint_as_float(r[k4 * 4 + 3]) + bb.w;
+                    v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
+                    s1 += (x0 + x1) + (x2 + x3);
+                    s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
                 }
-                sStat[(1 * 2 + half) * 128 + row] = make_float2(s1, s2);
+                sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
                 __syncthreads();                               // B3
                 {
-                    const float2 o = sStat[(1 * 2 + (half ^ 1)) * 128 + row];
-                    const float2 m = sStat[(1 * 2 + half) * 128 + row];
-                    const float mean = (o.x + m.x) * (1.f / 128.f);
-                    const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
+                    const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
+                    const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
+                    const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
+                    const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
                     s1 = 0.f; s2 = 0.f;
 #pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8) {
-                        const uint4 eu = ld_shared_v4(tX + half * 16384 + sw128(row, c8));
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const uint4 eu = ld_shared_v4(tX + tile_off + sw128(row, chunk0 + c8));
                         const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
                         const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+                        const float4 ga = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8);
+                        const float4 gb = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8 + 4);
+                        const float4 ba = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8);
+                        const float4 bb = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8 + 4);
+                        const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const int c = (int)col0 + c8 * 8 + e;
-                            const float u = fmaxf((v[c8 * 8 + e] - mean) * rstd * Pm[P_PE_G * 128 + c] + Pm[P_PE_B * 128 + c], 0.f);
+                            const float u = fmaxf((v[c8 * 8 + e] - mean) * rstd * gv[e] + bv[e], 0.f);
                             const float x = ev[e] + u;
                             v[c8 * 8 + e] = x;
                             s1 += x;
@@ -434,34 +463,37 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         }
                     }
                 }
-                sStat[(0 * 2 + half) * 128 + row] = make_float2(s1, s2);
+                sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
                 __syncthreads();                               // B4
                 {
-                    const float2 o = sStat[(0 * 2 + (half ^ 1)) * 128 + row];
-                    const float2 m = sStat[(0 * 2 + half) * 128 + row];
-                    const float mean = (o.x + m.x) * (1.f / 128.f);
-                    const float var = fmaxf((o.y + m.y) * (1.f / 128.f) - mean * mean, 0.f);
+                    const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
+                    const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
+                    const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
+                    const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
 #pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8) {
-                        float y[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int c = (int)col0 + c8 * 8 + e;
-                            y[e] = (v[c8 * 8 + e] - mean) * rstd * Pm[P_NE_G * 128 + c] + Pm[P_NE_B * 128 + c];
-                        }
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const float4 ga = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8);
+                        const float4 gb = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8 + 4);
+                        const float4 ba = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8);
+                        const float4 bb = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8 + 4);
                         uint4 u;
-                        u.x = pack_h2(y[0], y[1]); u.y = pack_h2(y[2], y[3]); u.z = pack_h2(y[4], y[5]); u.w = pack_h2(y[6], y[7]);
-                        st_shared_v4(tX + half * 16384 + sw128(row, c8), u);
+                        u.x = pack_h2((v[c8 * 8 + 0] - mean) * rstd * ga.x + ba.x, (v[c8 * 8 + 1] - mean) * rstd * ga.y + ba.y);
+                        u.y = pack_h2((v[c8 * 8 + 2] - mean) * rstd * ga.z + ba.z, (v[c8 * 8 + 3] - mean) * rstd * ga.w + ba.w);
+                        u.z = pack_h2((v[c8 * 8 + 4] - mean) * rstd * gb.x + bb.x, (v[c8 * 8 + 5] - mean) * rstd * gb.y + bb.y);
+                        u.w = pack_h2((v[c8 * 8 + 6] - mean) * rstd * gb.z + bb.z, (v[c8 * 8 + 7] - mean) * rstd * gb.w + bb.w);
+                        st_shared_v4(tX + tile_off + sw128(row, chunk0 + c8), u);
                     }
                 }
             }
 
-            // ---- epilogue 2b: per-thread online softmax over this thread's key (i0 + i_l) ----
+            // ---- epilogue 2b: per-thread online softmax over this thread's key (i0 + i_l), 2 heads ----
+            mbar_wait(bar_m2b, par, a.err, E_MMA2);
+            tc_fence_after();
             {
                 const bool key_ok = (i0 + i_l < N);            // padded keys never enter the softmax
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
+                for (int h = 0; h < 2; ++h) {
                     uint32_t rk[16], rv[16];
                     TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
                     TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
@@ -470,11 +502,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     float s = 0.f;
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 q = *reinterpret_cast<const float4*>(sQ + j_l * 132 + (int)col0 + h * 16 + k4 * 4);
-                        s = fmaf(q.x, __uint_as_float(rk[k4 * 4 + 0]), s);
-                        s = fmaf(q.y, __uint_as_float(rk[k4 * 4 + 1]), s);
-                        s = fmaf(q.z, __uint_as_float(rk[k4 * 4 + 2]), s);
-                        s = fmaf(q.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                        const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
+                        s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
+                        s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
+                        s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
+                        s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
                     }
                     const float mnew = fmaxf(mrun[h], s);
                     const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
@@ -501,7 +533,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
         // lanes l and l^16 hold key slots 2w and 2w+1 of the same query
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < 2; ++h) {
             const float mo = __shfl_xor_sync(0xffffffffu, mrun[h], 16);
             const float lo = __shfl_xor_sync(0xffffffffu, lrun[h], 16);
             const float mn = fmaxf(mrun[h], mo);
@@ -518,23 +550,22 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         // scratch in edge buffer `cur` (no prefetch was issued into it; drain the store that last used it)
         if (tid == 0) tma_wait_read0();
         __syncthreads();
-        float* scr = reinterpret_cast<float*>(sgen + SM_TILE0 + cur * 32768);   // [3 src][2 half][16 j][76]
+        float* scr = reinterpret_cast<float*>(sgen + SM_TILE0 + cur * 32768);   // [3 src][4 quarter][16 j][40]
         const int wq = warp & 3;
         if (wq != 0 && lane < 16) {
-            float* d = scr + (((wq - 1) * 2 + half) * 16 + lane) * 76;
+            float* d = scr + (((wq - 1) * 4 + q) * 16 + lane) * 40;
 #pragma unroll
-            for (int k = 0; k < 64; ++k) d[k] = acc[k];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) { d[64 + h] = mrun[h]; d[68 + h] = lrun[h]; }
+            for (int k = 0; k < 32; ++k) d[k] = acc[k];
+            d[32] = mrun[0]; d[33] = mrun[1]; d[34] = lrun[0]; d[35] = lrun[1];
         }
         __syncthreads();
         if (wq == 0 && lane < 16 && j0 + lane < N) {
 #pragma unroll
             for (int src = 0; src < 3; ++src) {
-                const float* d = scr + ((src * 2 + half) * 16 + lane) * 76;
+                const float* d = scr + ((src * 4 + q) * 16 + lane) * 40;
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float mo = d[64 + h], lo = d[68 + h];
+                for (int h = 0; h < 2; ++h) {
+                    const float mo = d[32 + h], lo = d[34 + h];
                     const float mn = fmaxf(mrun[h], mo);
                     const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
                     const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
@@ -546,17 +577,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             }
             float* o = a.attn + (tok0 + j0 + lane) * 128 + col0;
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
+            for (int h = 0; h < 2; ++h) {
                 const float inv = 1.f / lrun[h];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const int c = h * 16 + k4 * 4;
-                    float4 r;
-                    r.x = acc[c + 0] * inv + Pm[P_BV * 128 + (int)col0 + c + 0];
-                    r.y = acc[c + 1] * inv + Pm[P_BV * 128 + (int)col0 + c + 1];
-                    r.z = acc[c + 2] * inv + Pm[P_BV * 128 + (int)col0 + c + 2];
-                    r.w = acc[c + 3] * inv + Pm[P_BV * 128 + (int)col0 + c + 3];
-                    *reinterpret_cast<float4*>(o + c) = r;
+                    const float4 bv = *reinterpret_cast<const float4*>(Pm + P_BV * 128 + col0 + c);
+                    *reinterpret_cast<float4*>(o + c) = make_float4(acc[c + 0] * inv + bv.x, acc[c + 1] * inv + bv.y,
+                                                                    acc[c + 2] * inv + bv.z, acc[c + 3] * inv + bv.w);
                 }
             }
         }

@@ -6,6 +6,7 @@
 // and layers.py (line numbers cited per kernel).
 #include "kernels.h"
 #include <math.h>
+#include <algorithm>
 
 namespace mind {
 
@@ -502,11 +503,91 @@ void launch_edge_init_f32(const SceneDesc* sd, const float* ctrs, const float* v
     k_edge_init<float><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sd, ctrs, vecs, W, b, g, be, edge, b0, nb, Nmax);
     ++g_launches;
 }
+// fp16 edge stream for the tensor-core path: a warp keeps its 4-channel weight slice in registers and
+// walks units of 8 consecutive queries j of one key row i; rpe values are loaded once per unit by the
+// first 40 "slots" of the warp and broadcast by shuffle.  Write-bound (256 B per pair row).
+__global__ void __launch_bounds__(256) k_edge_init_h8(const SceneDesc* __restrict__ sd, const float* __restrict__ ctrs,
+                                                      const float* __restrict__ vecs, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, __half* __restrict__ edge, int nb,
+                                                      int Nmax) {
+    const int lane = threadIdx.x & 31;
+    const int units_per_row = (Nmax + 7) >> 3;
+    const int64_t n_units = (int64_t)nb * Nmax * units_per_row;
+    float w[4][5], bi[4], gm[4], bt[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = lane * 4 + e;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[e][k] = __ldg(W + c * 5 + k);
+        bi[e] = __ldg(bias + c); gm[e] = __ldg(gamma + c); bt[e] = __ldg(beta + c);
+    }
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t u = warp0; u < n_units; u += nwarps) {
+        const int j8 = (int)(u % units_per_row);
+        const int64_t bi_ = u / units_per_row;
+        const int i = (int)(bi_ % Nmax), b = (int)(bi_ / Nmax);
+        const SceneDesc d = sd[b];
+        const int M = d.n_actor + d.n_lane;
+        const int j0 = j8 * 8;
+        // slot s = k*8 + jj (k < 4) in lanes 0..31, slots 32..39 (k = 4) in lanes 0..7
+        float va = 0.f, vb = 0.f;
+        if (i < M) {
+            const int jj = lane & 7, k = lane >> 3, j = j0 + jj;
+            if (j < M) {
+                if (d.rpe) {
+                    va = __ldg(d.rpe + ((int64_t)k * M + i) * M + j);
+                    if (lane < 8) vb = __ldg(d.rpe + ((int64_t)4 * M + i) * M + j);
+                } else {
+                    const float2 ci = reinterpret_cast<const float2*>(ctrs)[d.geom_off + i];
+                    const float2 cj = reinterpret_cast<const float2*>(ctrs)[d.geom_off + j];
+                    const float2 vi = reinterpret_cast<const float2*>(vecs)[d.geom_off + i];
+                    const float2 vj = reinterpret_cast<const float2*>(vecs)[d.geom_off + j];
+                    const float dx = cj.x - ci.x, dy = cj.y - ci.y;
+                    const float dist = sqrtf(dx * dx + dy * dy);
+                    const float nj = sqrtf(vj.x * vj.x + vj.y * vj.y), ni = sqrtf(vi.x * vi.x + vi.y * vi.y);
+                    const float den1 = nj * ni + 1e-10f, den2 = nj * dist + 1e-10f;
+                    va = k == 0 ? (vj.x * vi.x + vj.y * vi.y) / den1
+                       : k == 1 ? (vj.x * vi.y - vj.y * vi.x) / den1
+                       : k == 2 ? (vj.x * dx + vj.y * dy) / den2
+                                : (vj.x * dy - vj.y * dx) / den2;
+                    vb = dist * 2.f / 100.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = j0 + jj;
+            if (j >= Nmax) break;
+            const float r0 = __shfl_sync(0xffffffffu, va, jj), r1 = __shfl_sync(0xffffffffu, va, 8 + jj);
+            const float r2 = __shfl_sync(0xffffffffu, va, 16 + jj), r3 = __shfl_sync(0xffffffffu, va, 24 + jj);
+            const float r4 = __shfl_sync(0xffffffffu, vb, jj);
+            __half* dst = edge + (((int64_t)b * Nmax + i) * Nmax + j) * 128 + lane * 4;
+            if (i >= M || j >= M) { store4(dst, make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
+            float y[4], s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                y[e] = fmaf(w[e][4], r4, fmaf(w[e][3], r3, fmaf(w[e][2], r2, fmaf(w[e][1], r1, fmaf(w[e][0], r0, bi[e])))));
+                s += y[e];
+            }
+            const float mean = warp_sum(s) * (1.f / 128.f);
+            float q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float t = y[e] - mean; q += t * t; }
+            const float rstd = rsqrtf(warp_sum(q) * (1.f / 128.f) + LN_EPS);
+            store4(dst, make_float4(fmaxf((y[0] - mean) * rstd * gm[0] + bt[0], 0.f), fmaxf((y[1] - mean) * rstd * gm[1] + bt[1], 0.f),
+                                    fmaxf((y[2] - mean) * rstd * gm[2] + bt[2], 0.f), fmaxf((y[3] - mean) * rstd * gm[3] + bt[3], 0.f)));
+        }
+    }
+}
+
 void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
                           const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, cudaStream_t st) {
-    const int64_t rows = (int64_t)nb * Nmax * Nmax;
-    if (rows <= 0) return;
-    k_edge_init<__half><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sd, ctrs, vecs, W, b, g, be, edge, b0, nb, Nmax);
+    const int64_t units = (int64_t)nb * Nmax * ((Nmax + 7) / 8);
+    if (units <= 0) return;
+    const int64_t blocks = std::min<int64_t>((units + 7) / 8, 148 * 16);
+    k_edge_init_h8<<<(unsigned)blocks, 256, 0, st>>>(sd + b0, ctrs, vecs, W, b, g, be, edge, nb, Nmax);
     ++g_launches;
 }
 
