@@ -112,10 +112,96 @@ __global__ void __launch_bounds__(256) k_gemm_tn(GemmArgs g) {
     }
 }
 
+// large aligned case (K % 16 == 0, N % 128 == 0, 16-byte aligned rows): 128x128x16 tiles, 8x8 per
+// thread, register-staged double buffering of the global loads
+constexpr int HBM_ = 128, HBN_ = 128, HBK_ = 16;
+__global__ void __launch_bounds__(256) k_gemm_tn_big(GemmArgs g) {
+    __shared__ __align__(16) float As[2][HBK_][HBM_ + 4];
+    __shared__ __align__(16) float Ws[2][HBK_][HBN_ + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;             // 16 x 16 threads, 8 x 8 outputs each
+    const int64_t m0 = (int64_t)blockIdx.x * HBM_;
+    const int n0 = blockIdx.y * HBN_;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    // each thread stages 2 float4 of A and 2 of W per k-step: rows lrow and lrow+64, k offset lcol
+    const int lrow = tid >> 2, lcol = (tid & 3) * 4;
+    float4 ra[2], rw[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t m = m0 + lrow + h * 64;
+            ra[h] = (m < g.M) ? *reinterpret_cast<const float4*>(g.A + m * (int64_t)g.lda + k0 + lcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = n0 + lrow + h * 64;
+            rw[h] = *reinterpret_cast<const float4*>(g.W + (int64_t)n * g.ldw + k0 + lcol);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lrow + h * 64;
+            As[buf][lcol + 0][r] = ra[h].x; As[buf][lcol + 1][r] = ra[h].y; As[buf][lcol + 2][r] = ra[h].z; As[buf][lcol + 3][r] = ra[h].w;
+            Ws[buf][lcol + 0][r] = rw[h].x; Ws[buf][lcol + 1][r] = rw[h].y; Ws[buf][lcol + 2][r] = rw[h].z; Ws[buf][lcol + 3][r] = rw[h].w;
+        }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    const int nk = g.K / HBK_;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * HBK_);
+#pragma unroll
+        for (int kk = 0; kk < HBK_; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Ws[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) sstore(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int n = n0 + jh * 64 + tx * 4;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float x = acc[i][jh * 4 + e];
+                if (g.bias) x += g.bias[n + e];
+                if (g.gbias) x += g.gbias[(m / g.gsize) * (int64_t)g.ldg + n + e];
+                if (g.relu) x = fmaxf(x, 0.f);
+                v[e] = x;
+            }
+            *reinterpret_cast<float4*>(g.C + m * (int64_t)g.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 void launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return;
-    dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
-    k_gemm_tn<<<grid, 256, 0, st>>>(g);
+    const bool big = g.M >= 2048 && (g.N % HBN_) == 0 && (g.K % HBK_) == 0 && (g.lda & 3) == 0 && (g.ldw & 3) == 0 &&
+                     (g.ldc & 3) == 0 && ((((uintptr_t)g.A) | ((uintptr_t)g.W) | ((uintptr_t)g.C)) & 15) == 0;
+    if (big) {
+        dim3 grid((unsigned)((g.M + HBM_ - 1) / HBM_), (unsigned)(g.N / HBN_));
+        k_gemm_tn_big<<<grid, 256, 0, st>>>(g);
+    } else {
+        dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
+        k_gemm_tn<<<grid, 256, 0, st>>>(g);
+    }
     ++g_launches;
 }
 
