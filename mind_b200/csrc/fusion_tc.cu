@@ -174,6 +174,9 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// barrier among the 4 warps (128 threads) that share the same 32 pair rows (same TMEM lane quadrant)
+__device__ __forceinline__ void row_group_sync(int lg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory"); }
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows x 128 B] block that
 // uses the 128-byte swizzle (chunk index XOR row%8), block base 1024-aligned
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
@@ -310,7 +313,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             const int i0 = ch * 8;
             const uint32_t tX = sbase + SM_TILE0 + cur * 32768;          // edge tile (in place -> edge')
             const uint32_t tN = sbase + SM_TILE0 + (cur ^ 1) * 32768;    // next edge tile (prefetch target)
-            if (tid < 256) {   // T (target term, per key i) tile
+            if (ch == 0 && tid < 256) {   // T (target term, per key i) tile of the first chunk; later ones are staged before B5
                 const int ii = tid >> 5, c4 = tid & 31;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i0 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + ii) * 384 + 128)[c4];
@@ -329,7 +332,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     tma_load_4d(tN + 16384, &emap, bl, 64, j0, i0 + 8, b);
                 }
             }
-            __syncthreads();                                   // B0: sT / sS / sQ visible
+            if (ch == 0) __syncthreads();                      // B0 (first chunk only): sT / sS / sQ visible
             mbar_wait(bar_m1, par, a.err, E_MMA1);
             tc_fence_after();
 
@@ -356,7 +359,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
             }
             tc_fence_before();
-            __syncthreads();                                   // B1: statistics exchanged, every D1 read retired
+            row_group_sync(warp & 3);                          // B1 (row group): statistics exchanged, D1 reads of these lanes retired
             tc_fence_after();
             {
                 const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
@@ -434,7 +437,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
                 }
                 sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
-                __syncthreads();                               // B3
+                row_group_sync(warp & 3);                      // B3 (row group)
                 {
                     const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
                     const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
@@ -464,7 +467,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     }
                 }
                 sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
-                __syncthreads();                               // B4
+                row_group_sync(warp & 3);                      // B4 (row group)
                 {
                     const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
                     const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
@@ -518,9 +521,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
             }
 
+            if (ch + 1 < n_chunks && tid < 256) {              // stage the next chunk's T tile (sT is only read in epilogue 1)
+                const int ii = tid >> 5, c4 = tid & 31;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i0 + 8 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + 8 + ii) * 384 + 128)[c4];
+                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = t;
+            }
             if (a.has_edge) fence_proxy_async();
             tc_fence_before();
-            __syncthreads();                                   // B5: edge' tile complete, all TMEM reads retired
+            __syncthreads();                                   // B5: edge' tile complete, all TMEM reads retired, next sT visible
             if (a.has_edge && tid == 0) {
                 tma_store_4d(&emap, tX, 0, j0, i0, b);
                 tma_store_4d(&emap, tX + 16384, 64, j0, i0, b);
