@@ -22,7 +22,7 @@ namespace mind {
 
 namespace tc {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 544;   // 16 epilogue warps + 1 issuer warp
 constexpr float kEps = 1e-5f;
 
 // ---- shared memory map (bytes, relative to a 1024-aligned base) ----
@@ -35,7 +35,7 @@ constexpr uint32_t SM_T = SM_Q + 16 * 132 * 4;        // float [8][132]
 constexpr uint32_t SM_P = SM_T + 8 * 132 * 4;         // float [8][128] layer params
 constexpr uint32_t SM_STAT = SM_P + 8 * 128 * 4;      // float2 [2 buf][4 quarter][128]
 constexpr uint32_t SM_BAR = SM_STAT + 2 * 4 * 128 * 8;
-constexpr uint32_t SM_TMEM = SM_BAR + 64;
+constexpr uint32_t SM_TMEM = SM_BAR + 96;
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SM_TOTAL + 1024;      // slack for manual 1024 B alignment
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -54,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -218,8 +221,24 @@ struct LayerArgs {
 //   [  0,128)  D1 = edge.W_e^T ; after epilogue 1 the same columns hold the A operand of G2:
 //              memory as an fp16 (hi, lo) pair, two K elements per 32-bit cell: hi -> [0,64), lo -> [64,128)
 //   [128,256)  Dpe   [256,384)  Dk   [384,512)  Dv
-// Thread map: 512 threads = 16 warps; warp w owns TMEM lanes 32*(w&3).. (pair rows) and the
-// 32-channel column quarter q = w>>2, so every LayerNorm exchanges 4 partial sums through smem.
+// Roles: warps 0-15 = epilogue (warp w owns TMEM lanes 32*(w&3).. = pair rows, and the 32-channel
+// column quarter q = w>>2); warp 16 = issuer (TMA loads / stores, every tcgen05.mma, T-tile staging).
+// Steady state has no CTA-wide barrier: issuer and epilogue meet only through mbarriers, the four
+// warps that share rows through a named 128-thread barrier.
+struct TileIt {          // walks (work item, key chunk) in the CTA's static schedule
+    int wi, ch, n_chunks, b, j0, n;
+};
+__device__ __forceinline__ bool tile_valid(const TileIt& t, int n_work) { return t.wi < n_work; }
+__device__ __forceinline__ void tile_load_wi(TileIt& t, const TcWork* work, int n_work) {
+    if (t.wi < n_work) {
+        const TcWork w = work[t.wi];
+        t.b = w.b; t.j0 = w.j0; t.n = w.n; t.n_chunks = (w.n + 7) >> 3; t.ch = 0;
+    }
+}
+__device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_work, int stride) {
+    if (++t.ch >= t.n_chunks) { t.wi += stride; tile_load_wi(t, work, n_work); }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -231,19 +250,18 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     float* sP = reinterpret_cast<float*>(sgen + SM_P);
     float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);   // [2 buf][4 quarter][128 row]
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
-    const uint32_t bar_w = sbase + SM_BAR, bar_m1 = bar_w + 8, bar_m2a = bar_w + 16, bar_m2b = bar_w + 24, bar_ld0 = bar_w + 32;
+    const uint32_t bar_w = sbase + SM_BAR;
+    const uint32_t bar_m1 = bar_w + 8, bar_m2a = bar_w + 16, bar_m2b = bar_w + 24, bar_ld0 = bar_w + 32;   // +32, +40
+    const uint32_t bar_a = bar_w + 48, bar_e = bar_w + 56, bar_t = bar_w + 64;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp >> 2;                     // column quarter: channels [32q, 32q+32)
-    const int row = (warp & 3) * 32 + lane;      // TMEM lane = pair row inside the tile
-    const int i_l = row >> 4, j_l = row & 15;
-
     if (tid == 0) {
         mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2a, 1); mbar_init(bar_m2b, 1);
         mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
+        mbar_init(bar_a, 16); mbar_init(bar_e, 16); mbar_init(bar_t, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_TMEM), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -252,359 +270,391 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sTmem;
+    const int stride = gridDim.x;
 
-    if (tid == 0) {   // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
-        mbar_expect_tx(bar_w, 131072u);
-        for (int kb = 0; kb < 2; ++kb)
-            for (int m = 0; m < 4; ++m) tma_load_2d(sbase + SM_W + kb * 65536 + m * 16384, &wmap, bar_w, kb * 64, m * 128);
-    }
-    mbar_wait(bar_w, 0, a.err, E_LOAD_W);
-
-    uint32_t par = 0;                // parity of bar_m1 / bar_m2a / bar_m2b (one completion per tile)
-    uint32_t lpar0 = 0, lpar1 = 0;   // parity of the two edge-load barriers
-    int cur = 0;                     // edge buffer of the current tile
-    bool g1_ahead = false;           // (thread 0) G1 of the current tile was already issued behind the previous G2
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int col0 = q * 32;
-    const uint32_t tile_off = (uint32_t)(q >> 1) * 16384u;      // k-block of this quarter inside an edge tile
-    const int chunk0 = (q & 1) * 4;                              // first 16-byte chunk of this quarter in its k-block
-    const float* Pm = sP;
-
-    // G1 of one tile: D1 = edge(tX) . W_e^T
-    auto issue_g1 = [&](uint32_t tX) {
-        const uint32_t id128 = umma_idesc_f16(128);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
-            const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-            umma_f16(tmem + 0, umma_desc_sw128(tX + ko), umma_desc_sw128(sbase + SM_W + kw), id128, kk > 0);
+    if (warp == 16) {
+        // =============================== issuer warp ===============================
+        if (lane == 0) {   // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
+            mbar_expect_tx(bar_w, 131072u);
+            for (int kb = 0; kb < 2; ++kb)
+                for (int m = 0; m < 4; ++m) tma_load_2d(sbase + SM_W + kb * 65536 + m * 16384, &wmap, bar_w, kb * 64, m * 128);
+            mbar_wait(bar_w, 0, a.err, E_LOAD_W);
         }
-        umma_commit(bar_m1);
-    };
-
-    for (int wi = blockIdx.x; wi < a.n_work; wi += gridDim.x) {
-        const TcWork wk = a.work[wi];
-        const int N = wk.n, j0 = wk.j0, b = wk.b;
-        const int n_chunks = (N + 7) >> 3;
-        const int64_t tok0 = (int64_t)b * a.Nmax;
-        if (tid == 0) {   // first edge tile of the work item -> buffer `cur`
-            const uint32_t bl = bar_ld0 + 8 * cur;
+        __syncwarp();
+        auto load_tile = [&](const TileIt& t, int buf) {          // lane 0 only
+            const uint32_t bl = bar_ld0 + 8 * buf, dst = sbase + SM_TILE0 + buf * 32768;
             mbar_expect_tx(bl, 32768u);
-            tma_load_4d(sbase + SM_TILE0 + cur * 32768, &emap, bl, 0, j0, 0, b);
-            tma_load_4d(sbase + SM_TILE0 + cur * 32768 + 16384, &emap, bl, 64, j0, 0, b);
-        }
-        {   // S (src term, per query j) and q tiles: 16 x 32 float4 each, one per thread
-            const int jj = tid >> 5, c4 = tid & 31;
-            float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), qv = sv;
-            if (j0 + jj < N) {
-                const float* p = a.stq + (tok0 + j0 + jj) * 384;
-                sv = reinterpret_cast<const float4*>(p)[c4];
-                qv = reinterpret_cast<const float4*>(p + 256)[c4];
-            }
-            *reinterpret_cast<float4*>(sS + jj * 132 + c4 * 4) = sv;
-            *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = qv;
-        }
-        float acc[32], mrun[2], lrun[2];
+            tma_load_4d(dst, &emap, bl, 0, t.j0, t.ch * 8, t.b);
+            tma_load_4d(dst + 16384, &emap, bl, 64, t.j0, t.ch * 8, t.b);
+        };
+        auto stage_T = [&](const TileIt& t) {                     // whole warp: T (target term) rows of the tile's 8 keys
+            const int64_t tok0 = (int64_t)t.b * a.Nmax;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-        mrun[0] = mrun[1] = -INFINITY; lrun[0] = lrun[1] = 0.f;
-
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            const int i0 = ch * 8;
-            const uint32_t tX = sbase + SM_TILE0 + cur * 32768;          // edge tile (in place -> edge')
-            const uint32_t tN = sbase + SM_TILE0 + (cur ^ 1) * 32768;    // next edge tile (prefetch target)
-            if (ch == 0 && tid < 256) {   // T (target term, per key i) tile of the first chunk; later ones are staged before B5
-                const int ii = tid >> 5, c4 = tid & 31;
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i0 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + ii) * 384 + 128)[c4];
-                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = t;
+            for (int it = 0; it < 8; ++it) {
+                const int idx = it * 32 + lane, ii = idx >> 5, c4 = idx & 31;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t.ch * 8 + ii < t.n) v = reinterpret_cast<const float4*>(a.stq + (tok0 + t.ch * 8 + ii) * 384 + 128)[c4];
+                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = v;
             }
-            mbar_wait(bar_ld0 + 8 * cur, cur ? lpar1 : lpar0, a.err, E_LOAD_EDGE);   // every thread observes the TMA completion
-            if (cur) lpar1 ^= 1; else lpar0 ^= 1;
-            if (tid == 0) {
-                if (!g1_ahead) { tc_fence_after(); issue_g1(tX); }
-                g1_ahead = false;
-                if (ch + 1 < n_chunks) {                       // prefetch the next edge tile
-                    tma_wait_read0();                          // the edge' store that last used tN has drained
-                    const uint32_t bl = bar_ld0 + 8 * (cur ^ 1);
-                    mbar_expect_tx(bl, 32768u);
-                    tma_load_4d(tN, &emap, bl, 0, j0, i0 + 8, b);
-                    tma_load_4d(tN + 16384, &emap, bl, 64, j0, i0 + 8, b);
-                }
-            }
-            if (ch == 0) __syncthreads();                      // B0 (first chunk only): sT / sS / sQ visible
-            mbar_wait(bar_m1, par, a.err, E_MMA1);
-            tc_fence_after();
-
-            // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 (hi, lo) A operand in TMEM ----
-            float v[32];
-            {
-                uint32_t r[32];
-                TMEM_LD_X32(tmem + lane_base + col0, r);
-                tmem_wait_ld();
-                float s1 = 0.f, s2 = 0.f;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t);
+        };
+        auto issue_g1 = [&](int buf) {                            // lane 0 only
+            const uint32_t tX = sbase + SM_TILE0 + buf * 32768, id128 = umma_idesc_f16(128);
 #pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    const int c = col0 + k4 * 4;
-                    const float4 s = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
-                    const float4 t = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
-                    const float x0 = __uint_as_float(r[k4 * 4 + 0]) + s.x + t.x;
-                    const float x1 = __uint_as_float(r[k4 * 4 + 1]) + s.y + t.y;
-                    const float x2 = __uint_as_float(r[k4 * 4 + 2]) + s.z + t.z;
-                    const float x3 = __uint_as_float(r[k4 * 4 + 3]) + s.w + t.w;
-                    v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
-                    s1 += (x0 + x1) + (x2 + x3);
-                    s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
-                }
-                sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t ko = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
+                const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+                umma_f16(tmem + 0, umma_desc_sw128(tX + ko), umma_desc_sw128(sbase + SM_W + kw), id128, kk > 0);
             }
-            tc_fence_before();
-            row_group_sync(warp & 3);                          // B1 (row group): statistics exchanged, D1 reads of these lanes retired
-            tc_fence_after();
-            {
-                const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
-                const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
-                const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
-                const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + kEps);
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    const float4 g = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + col0 + k4 * 4);
-                    const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + col0 + k4 * 4);
-                    const float y0 = fmaxf((v[k4 * 4 + 0] - mean) * rstd * g.x + be.x, 0.f);
-                    const float y1 = fmaxf((v[k4 * 4 + 1] - mean) * rstd * g.y + be.y, 0.f);
-                    const float y2 = fmaxf((v[k4 * 4 + 2] - mean) * rstd * g.z + be.z, 0.f);
-                    const float y3 = fmaxf((v[k4 * 4 + 3] - mean) * rstd * g.w + be.w, 0.f);
-                    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    hi[k4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-                    hi[k4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                    lo[k4 * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
-                    lo[k4 * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
-                }
-                // K elements [32q, +32) -> cells [16q, +16) of the hi block and of the lo block
-                TMEM_ST_X16(tmem + lane_base + q * 16, hi);
-                TMEM_ST_X16(tmem + lane_base + 64 + q * 16, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            umma_commit(bar_m1);
+        };
+        TileIt cur_t{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        tile_load_wi(cur_t, a.work, a.n_work);
+        if (tile_valid(cur_t, a.n_work)) {
+            TileIt nxt = cur_t;
+            tile_next(nxt, a.work, a.n_work, stride);
+            uint32_t g = 0;                                       // tiles processed by this CTA
+            if (lane == 0) {
+                load_tile(cur_t, 0);
+                if (tile_valid(nxt, a.n_work)) load_tile(nxt, 1);
             }
-            tc_fence_before();
-            __syncthreads();                                   // B2: A operand complete
-            if (tid == 0) {
+            stage_T(cur_t);
+            if (lane == 0) {
+                mbar_wait(bar_ld0, 0, a.err, E_LOAD_EDGE);
                 tc_fence_after();
-                const uint32_t id128 = umma_idesc_f16(128), id256 = umma_idesc_f16(256);
-                if (a.has_edge) {                              // W_pe first: its epilogue overlaps the K|V MMAs
+                issue_g1(0);
+            }
+            while (true) {
+                const int buf = g & 1;
+                const uint32_t par = g & 1;
+                const bool has_next = tile_valid(nxt, a.n_work);
+                if (lane == 0) {
+                    // [A] A operand of this tile is in TMEM -> G2 (W_pe first: its epilogue overlaps the K|V MMAs)
+                    mbar_wait(bar_a, par, a.err, E_MMA2);
+                    tc_fence_after();
+                    const uint32_t id128 = umma_idesc_f16(128), id256 = umma_idesc_f16(256);
+                    if (a.has_edge) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+                            const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 128 * 128);
+                            umma_f16_ts(tmem + 128, tmem + kk * 8, bd, id128, kk > 0);
+                            umma_f16_ts(tmem + 128, tmem + 64 + kk * 8, bd, id128, 1);
+                        }
+                    }
+                    umma_commit(bar_m2a);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-                        const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 128 * 128);
-                        umma_f16_ts(tmem + 128, tmem + kk * 8, bd, id128, kk > 0);
-                        umma_f16_ts(tmem + 128, tmem + 64 + kk * 8, bd, id128, 1);
+                        const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 256 * 128);
+                        umma_f16_ts(tmem + 256, tmem + kk * 8, bd, id256, kk > 0);
+                        umma_f16_ts(tmem + 256, tmem + 64 + kk * 8, bd, id256, 1);
+                    }
+                    umma_commit(bar_m2b);
+                }
+                __syncwarp();
+                // [B] next tile: T rows (every epilogue warp is past epilogue 1 of this tile), then G1 behind G2
+                if (has_next) {
+                    stage_T(nxt);
+                    if (lane == 0) {
+                        mbar_wait(bar_ld0 + 8 * (buf ^ 1), ((g + 1) >> 1) & 1, a.err, E_LOAD_EDGE);
+                        tc_fence_after();
+                        issue_g1(buf ^ 1);
                     }
                 }
-                umma_commit(bar_m2a);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-                    const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 256 * 128);
-                    umma_f16_ts(tmem + 256, tmem + kk * 8, bd, id256, kk > 0);
-                    umma_f16_ts(tmem + 256, tmem + 64 + kk * 8, bd, id256, 1);
+                // [C] edge' tile complete -> TMA store ; [D] buffer free -> load the tile after next
+                TileIt nn = nxt;
+                if (has_next) tile_next(nn, a.work, a.n_work, stride);
+                if (lane == 0) {
+                    mbar_wait(bar_e, par, a.err, E_MMA2 + 1);
+                    if (a.has_edge) {
+                        const uint32_t tX = sbase + SM_TILE0 + buf * 32768;
+                        tma_store_4d(&emap, tX, 0, cur_t.j0, cur_t.ch * 8, cur_t.b);
+                        tma_store_4d(&emap, tX + 16384, 64, cur_t.j0, cur_t.ch * 8, cur_t.b);
+                        tma_commit();
+                    }
+                    if (has_next && tile_valid(nn, a.n_work)) {
+                        tma_wait_read0();
+                        load_tile(nn, buf);
+                    }
                 }
-                umma_commit(bar_m2b);
-                // G1 of the next tile runs behind G2 (MMAs execute in issue order; D1 is free once G2 has read A)
-                if (ch + 1 < n_chunks && mbar_try_wait(bar_ld0 + 8 * (cur ^ 1), (cur ^ 1) ? lpar1 : lpar0)) {
-                    tc_fence_after();
-                    issue_g1(tN);
-                    g1_ahead = true;
-                }
+                __syncwarp();
+                if (!has_next) break;
+                cur_t = nxt; nxt = nn; ++g;
             }
+            if (lane == 0) tma_wait_all0();
+        }
+    } else {
+        // =============================== epilogue warps ===============================
+        const int q = warp >> 2;                     // column quarter: channels [32q, 32q+32)
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;              // TMEM lane = pair row inside the tile
+        const int i_l = row >> 4, j_l = row & 15;
+        const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+        const int col0 = q * 32;
+        const uint32_t tile_off = (uint32_t)(q >> 1) * 16384u;      // k-block of this quarter inside an edge tile
+        const int chunk0 = (q & 1) * 4;                              // first 16-byte chunk of this quarter in its k-block
+        const float* Pm = sP;
+        uint32_t g = 0;                                              // tiles processed by this CTA
+        for (int wi = blockIdx.x; wi < a.n_work; wi += stride) {
+            const TcWork wk = a.work[wi];
+            const int N = wk.n, j0 = wk.j0, b = wk.b;
+            const int n_chunks = (N + 7) >> 3;
+            const int64_t tok0 = (int64_t)b * a.Nmax;
+            {   // S (src term, per query j) and q tiles: 16 x 32 float4 each, one per epilogue thread
+                const int jj = tid >> 5, c4 = tid & 31;
+                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), qv = sv;
+                if (j0 + jj < N) {
+                    const float* p = a.stq + (tok0 + j0 + jj) * 384;
+                    sv = reinterpret_cast<const float4*>(p)[c4];
+                    qv = reinterpret_cast<const float4*>(p + 256)[c4];
+                }
+                *reinterpret_cast<float4*>(sS + jj * 132 + c4 * 4) = sv;
+                *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = qv;
+            }
+            asm volatile("bar.sync 5, 512;" ::: "memory");         // epilogue warps only
+            float acc[32], mrun[2], lrun[2];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+            mrun[0] = mrun[1] = -INFINITY; lrun[0] = lrun[1] = 0.f;
 
-            // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
-            if (a.has_edge) {
-                mbar_wait(bar_m2a, par, a.err, E_MMA2);
+            for (int ch = 0; ch < n_chunks; ++ch, ++g) {
+                const int i0 = ch * 8;
+                const uint32_t par = g & 1;
+                const uint32_t tX = sbase + SM_TILE0 + (g & 1) * 32768;  // edge tile (in place -> edge')
+                mbar_wait(bar_t, par, a.err, E_LOAD_EDGE + 10);          // T rows staged by the issuer
+                mbar_wait(bar_m1, par, a.err, E_MMA1);
                 tc_fence_after();
-                uint32_t r[32];
-                TMEM_LD_X32(tmem + lane_base + 128 + col0, r);
-                tmem_wait_ld();
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + col0 + k4 * 4);
-                    const float x0 = __uint_as_float(r[k4 * 4 + 0]) + bb.x, x1 = __uint_as_float(r[k4 * 4 + 1]) + bb.y;
-                    const float x2 = __uint_as_float(r[k4 * 4 + 2]) + bb.z, x3 = __uint_as_float(r[k4 * 4 + 3]) + bb.w;
-                    v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
-                    s1 += (x0 + x1) + (x2 + x3);
-                    s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
-                }
-                sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
-                row_group_sync(warp & 3);                      // B3 (row group)
+
+                // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 (hi, lo) A operand in TMEM ----
+                float v[32];
                 {
-                    const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
-                    const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
-                    const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
-                    const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
-                    const float rstd = rsqrtf(var + kEps);
-                    s1 = 0.f; s2 = 0.f;
+                    uint32_t r[32];
+                    TMEM_LD_X32(tmem + lane_base + col0, r);
+                    tmem_wait_ld();
+                    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        const uint4 eu = ld_shared_v4(tX + tile_off + sw128(row, chunk0 + c8));
-                        const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
-                        const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
-                        const float4 ga = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8);
-                        const float4 gb = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8 + 4);
-                        const float4 ba = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8);
-                        const float4 bb = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8 + 4);
-                        const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float u = fmaxf((v[c8 * 8 + e] - mean) * rstd * gv[e] + bv[e], 0.f);
-                            const float x = ev[e] + u;
-                            v[c8 * 8 + e] = x;
-                            s1 += x;
-                            s2 += x * x;
-                        }
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const int c = col0 + k4 * 4;
+                        const float4 s = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
+                        const float4 t = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
+                        const float x0 = __uint_as_float(r[k4 * 4 + 0]) + s.x + t.x;
+                        const float x1 = __uint_as_float(r[k4 * 4 + 1]) + s.y + t.y;
+                        const float x2 = __uint_as_float(r[k4 * 4 + 2]) + s.z + t.z;
+                        const float x3 = __uint_as_float(r[k4 * 4 + 3]) + s.w + t.w;
+                        v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
+                        s1 += (x0 + x1) + (x2 + x3);
+                        s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
                     }
+                    sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
                 }
-                sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
-                row_group_sync(warp & 3);                      // B4 (row group)
+                tc_fence_before();
+                row_group_sync(lg);                                // statistics exchanged, D1 reads of these lanes retired
+                tc_fence_after();
                 {
                     const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
                     const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
                     const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        const float4 ga = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8);
-                        const float4 gb = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8 + 4);
-                        const float4 ba = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8);
-                        const float4 bb = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8 + 4);
-                        uint4 u;
-                        u.x = pack_h2((v[c8 * 8 + 0] - mean) * rstd * ga.x + ba.x, (v[c8 * 8 + 1] - mean) * rstd * ga.y + ba.y);
-                        u.y = pack_h2((v[c8 * 8 + 2] - mean) * rstd * ga.z + ba.z, (v[c8 * 8 + 3] - mean) * rstd * ga.w + ba.w);
-                        u.z = pack_h2((v[c8 * 8 + 4] - mean) * rstd * gb.x + bb.x, (v[c8 * 8 + 5] - mean) * rstd * gb.y + bb.y);
-                        u.w = pack_h2((v[c8 * 8 + 6] - mean) * rstd * gb.z + bb.z, (v[c8 * 8 + 7] - mean) * rstd * gb.w + bb.w);
-                        st_shared_v4(tX + tile_off + sw128(row, chunk0 + c8), u);
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 gg = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + col0 + k4 * 4);
+                        const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + col0 + k4 * 4);
+                        const float y0 = fmaxf((v[k4 * 4 + 0] - mean) * rstd * gg.x + be.x, 0.f);
+                        const float y1 = fmaxf((v[k4 * 4 + 1] - mean) * rstd * gg.y + be.y, 0.f);
+                        const float y2 = fmaxf((v[k4 * 4 + 2] - mean) * rstd * gg.z + be.z, 0.f);
+                        const float y3 = fmaxf((v[k4 * 4 + 3] - mean) * rstd * gg.w + be.w, 0.f);
+                        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        hi[k4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                        hi[k4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        lo[k4 * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
+                        lo[k4 * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
                     }
+                    // K elements [32q, +32) -> cells [16q, +16) of the hi block and of the lo block
+                    TMEM_ST_X16(tmem + lane_base + q * 16, hi);
+                    TMEM_ST_X16(tmem + lane_base + 64 + q * 16, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
-            }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a);                 // this warp's slice of the A operand is in TMEM
 
-            // ---- epilogue 2b: per-thread online softmax over this thread's key (i0 + i_l), 2 heads ----
-            mbar_wait(bar_m2b, par, a.err, E_MMA2);
-            tc_fence_after();
-            {
-                const bool key_ok = (i0 + i_l < N);            // padded keys never enter the softmax
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t rk[16], rv[16];
-                    TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
-                    TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
+                // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
+                if (a.has_edge) {
+                    mbar_wait(bar_m2a, par, a.err, E_MMA2);
+                    tc_fence_after();
+                    uint32_t r[32];
+                    TMEM_LD_X32(tmem + lane_base + 128 + col0, r);
                     tmem_wait_ld();
-                    if (!key_ok) continue;
-                    float s = 0.f;
+                    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
-                        s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
-                        s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
-                        s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
-                        s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + col0 + k4 * 4);
+                        const float x0 = __uint_as_float(r[k4 * 4 + 0]) + bb.x, x1 = __uint_as_float(r[k4 * 4 + 1]) + bb.y;
+                        const float x2 = __uint_as_float(r[k4 * 4 + 2]) + bb.z, x3 = __uint_as_float(r[k4 * 4 + 3]) + bb.w;
+                        v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
+                        s1 += (x0 + x1) + (x2 + x3);
+                        s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
                     }
-                    const float mnew = fmaxf(mrun[h], s);
-                    const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
-                    const float p = __expf(s - mnew);
-                    lrun[h] = lrun[h] * corr + p;
-                    mrun[h] = mnew;
+                    sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                    row_group_sync(lg);
+                    {
+                        const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
+                        const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
+                        const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
+                        const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
+                        const float rstd = rsqrtf(var + kEps);
+                        s1 = 0.f; s2 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) acc[h * 16 + k] = fmaf(p, __uint_as_float(rv[k]), acc[h * 16 + k] * corr);
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const uint4 eu = ld_shared_v4(tX + tile_off + sw128(row, chunk0 + c8));
+                            const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
+                            const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+                            const float4 ga = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8);
+                            const float4 gb = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8 + 4);
+                            const float4 ba = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8);
+                            const float4 bb = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8 + 4);
+                            const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float u = fmaxf((v[c8 * 8 + e] - mean) * rstd * gv[e] + bv[e], 0.f);
+                                const float x = ev[e] + u;
+                                v[c8 * 8 + e] = x;
+                                s1 += x;
+                                s2 += x * x;
+                            }
+                        }
+                    }
+                    sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                    row_group_sync(lg);
+                    {
+                        const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
+                        const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
+                        const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
+                        const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
+                        const float rstd = rsqrtf(var + kEps);
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const float4 ga = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8);
+                            const float4 gb = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8 + 4);
+                            const float4 ba = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8);
+                            const float4 bb = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8 + 4);
+                            uint4 u;
+                            u.x = pack_h2((v[c8 * 8 + 0] - mean) * rstd * ga.x + ba.x, (v[c8 * 8 + 1] - mean) * rstd * ga.y + ba.y);
+                            u.y = pack_h2((v[c8 * 8 + 2] - mean) * rstd * ga.z + ba.z, (v[c8 * 8 + 3] - mean) * rstd * ga.w + ba.w);
+                            u.z = pack_h2((v[c8 * 8 + 4] - mean) * rstd * gb.x + bb.x, (v[c8 * 8 + 5] - mean) * rstd * gb.y + bb.y);
+                            u.w = pack_h2((v[c8 * 8 + 6] - mean) * rstd * gb.z + bb.z, (v[c8 * 8 + 7] - mean) * rstd * gb.w + bb.w);
+                            st_shared_v4(tX + tile_off + sw128(row, chunk0 + c8), u);
+                        }
+                    }
                 }
+
+                // ---- epilogue 2b: per-thread online softmax over this thread's key (i0 + i_l), 2 heads ----
+                mbar_wait(bar_m2b, par, a.err, E_MMA2);
+                tc_fence_after();
+                {
+                    const bool key_ok = (i0 + i_l < N);            // padded keys never enter the softmax
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t rk[16], rv[16];
+                        TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
+                        TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
+                        tmem_wait_ld();
+                        if (!key_ok) continue;
+                        float s = 0.f;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
+                            s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
+                            s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
+                            s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
+                            s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                        }
+                        const float mnew = fmaxf(mrun[h], s);
+                        const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
+                        const float p = __expf(s - mnew);
+                        lrun[h] = lrun[h] * corr + p;
+                        mrun[h] = mnew;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) acc[h * 16 + k] = fmaf(p, __uint_as_float(rv[k]), acc[h * 16 + k] * corr);
+                    }
+                }
+                if (a.has_edge) fence_proxy_async();               // edge' (generic stores) -> visible to the TMA store
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_e);                 // tile done: edge' in smem, all TMEM reads retired
+                row_group_sync(lg);                                // statistics buffers can be reused by the next tile
             }
 
-            if (ch + 1 < n_chunks && tid < 256) {              // stage the next chunk's T tile (sT is only read in epilogue 1)
-                const int ii = tid >> 5, c4 = tid & 31;
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i0 + 8 + ii < N) t = reinterpret_cast<const float4*>(a.stq + (tok0 + i0 + 8 + ii) * 384 + 128)[c4];
-                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = t;
-            }
-            if (a.has_edge) fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();                                   // B5: edge' tile complete, all TMEM reads retired, next sT visible
-            if (a.has_edge && tid == 0) {
-                tma_store_4d(&emap, tX, 0, j0, i0, b);
-                tma_store_4d(&emap, tX + 16384, 64, j0, i0, b);
-                tma_commit();
-            }
-            cur ^= 1;
-            par ^= 1;
-        }
-
-        // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
-        // lanes l and l^16 hold key slots 2w and 2w+1 of the same query
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float mo = __shfl_xor_sync(0xffffffffu, mrun[h], 16);
-            const float lo = __shfl_xor_sync(0xffffffffu, lrun[h], 16);
-            const float mn = fmaxf(mrun[h], mo);
-            const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
-            const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-            lrun[h] = lrun[h] * ca + lo * cb;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float ao = __shfl_xor_sync(0xffffffffu, acc[h * 16 + k], 16);
-                acc[h * 16 + k] = acc[h * 16 + k] * ca + ao * cb;
-            }
-            mrun[h] = mn;
-        }
-        // scratch in edge buffer `cur` (no prefetch was issued into it; drain the store that last used it)
-        if (tid == 0) tma_wait_read0();
-        __syncthreads();
-        float* scr = reinterpret_cast<float*>(sgen + SM_TILE0 + cur * 32768);   // [3 src][4 quarter][16 j][40]
-        const int wq = warp & 3;
-        if (wq != 0 && lane < 16) {
-            float* d = scr + (((wq - 1) * 4 + q) * 16 + lane) * 40;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) d[k] = acc[k];
-            d[32] = mrun[0]; d[33] = mrun[1]; d[34] = lrun[0]; d[35] = lrun[1];
-        }
-        __syncthreads();
-        if (wq == 0 && lane < 16 && j0 + lane < N) {
-#pragma unroll
-            for (int src = 0; src < 3; ++src) {
-                const float* d = scr + ((src * 4 + q) * 16 + lane) * 40;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float mo = d[32 + h], lo = d[34 + h];
-                    const float mn = fmaxf(mrun[h], mo);
-                    const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
-                    const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-                    lrun[h] = lrun[h] * ca + lo * cb;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) acc[h * 16 + k] = acc[h * 16 + k] * ca + d[h * 16 + k] * cb;
-                    mrun[h] = mn;
-                }
-            }
-            float* o = a.attn + (tok0 + j0 + lane) * 128 + col0;
+            // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
+            // lanes l and l^16 hold key slots 2*lg and 2*lg+1 of the same query
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float inv = 1.f / lrun[h];
+                const float mo = __shfl_xor_sync(0xffffffffu, mrun[h], 16);
+                const float lo = __shfl_xor_sync(0xffffffffu, lrun[h], 16);
+                const float mn = fmaxf(mrun[h], mo);
+                const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
+                const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+                lrun[h] = lrun[h] * ca + lo * cb;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int c = h * 16 + k4 * 4;
-                    const float4 bv = *reinterpret_cast<const float4*>(Pm + P_BV * 128 + col0 + c);
-                    *reinterpret_cast<float4*>(o + c) = make_float4(acc[c + 0] * inv + bv.x, acc[c + 1] * inv + bv.y,
-                                                                    acc[c + 2] * inv + bv.z, acc[c + 3] * inv + bv.w);
+                for (int k = 0; k < 16; ++k) {
+                    const float ao = __shfl_xor_sync(0xffffffffu, acc[h * 16 + k], 16);
+                    acc[h * 16 + k] = acc[h * 16 + k] * ca + ao * cb;
+                }
+                mrun[h] = mn;
+            }
+            // three rounds through the (now dead) S|q tile area: row group r publishes, row group 0 accumulates
+            float* scr = sS;                                       // [4 quarter][16 j][40] floats = 10 KB <= S|q area
+            for (int r = 1; r < 4; ++r) {
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                if (lg == r && lane < 16) {
+                    float* d = scr + (q * 16 + lane) * 40;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) d[k] = acc[k];
+                    d[32] = mrun[0]; d[33] = mrun[1]; d[34] = lrun[0]; d[35] = lrun[1];
+                }
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                if (lg == 0 && lane < 16) {
+                    const float* d = scr + (q * 16 + lane) * 40;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float mo = d[32 + h], lo = d[34 + h];
+                        const float mn = fmaxf(mrun[h], mo);
+                        const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
+                        const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+                        lrun[h] = lrun[h] * ca + lo * cb;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) acc[h * 16 + k] = acc[h * 16 + k] * ca + d[h * 16 + k] * cb;
+                        mrun[h] = mn;
+                    }
                 }
             }
+            if (lg == 0 && lane < 16 && j0 + lane < N) {
+                float* o = a.attn + (tok0 + j0 + lane) * 128 + col0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float inv = 1.f / lrun[h];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const int c = h * 16 + k4 * 4;
+                        const float4 bv = *reinterpret_cast<const float4*>(Pm + P_BV * 128 + col0 + c);
+                        *reinterpret_cast<float4*>(o + c) = make_float4(acc[c + 0] * inv + bv.x, acc[c + 1] * inv + bv.y,
+                                                                        acc[c + 2] * inv + bv.z, acc[c + 3] * inv + bv.w);
+                    }
+                }
+            }
+            asm volatile("bar.sync 5, 512;" ::: "memory");         // scratch consumed before the next S|q tiles are written
         }
-        fence_proxy_async();
-        __syncthreads();   // scratch consumed before the next work item's first tile lands in it
     }
 
-    if (tid == 0) tma_wait_all0();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
