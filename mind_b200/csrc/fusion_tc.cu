@@ -166,6 +166,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),  \
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)       \
         : "memory")
+#define TMEM_ST_X8(taddr, r)                                                                       \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"           \
+                 ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr) \
+                 : "memory")
 // A operand from tensor memory (lane = row, two fp16 K elements per 32-bit cell), B from shared memory
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -239,7 +243,7 @@ __device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_w
     if (++t.ch >= t.n_chunks) { t.wi += stride; tile_load_wi(t, work, n_work); }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(120)      // 17 warps x 32 x 120 registers = 65,280 <= 64K
 k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -458,25 +462,29 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
-                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const float4 gg = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + col0 + k4 * 4);
-                        const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + col0 + k4 * 4);
-                        const float y0 = fmaxf((v[k4 * 4 + 0] - mean) * rstd * gg.x + be.x, 0.f);
-                        const float y1 = fmaxf((v[k4 * 4 + 1] - mean) * rstd * gg.y + be.y, 0.f);
-                        const float y2 = fmaxf((v[k4 * 4 + 2] - mean) * rstd * gg.z + be.z, 0.f);
-                        const float y3 = fmaxf((v[k4 * 4 + 3] - mean) * rstd * gg.w + be.w, 0.f);
-                        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        hi[k4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-                        hi[k4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                        lo[k4 * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
-                        lo[k4 * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
+                    for (int hf = 0; hf < 2; ++hf) {                 // two 16-column halves keep the live registers low
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int k4h = 0; k4h < 4; ++k4h) {
+                            const int k4 = hf * 4 + k4h;
+                            const float4 gg = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + col0 + k4 * 4);
+                            const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + col0 + k4 * 4);
+                            const float y0 = fmaxf((v[k4 * 4 + 0] - mean) * rstd * gg.x + be.x, 0.f);
+                            const float y1 = fmaxf((v[k4 * 4 + 1] - mean) * rstd * gg.y + be.y, 0.f);
+                            const float y2 = fmaxf((v[k4 * 4 + 2] - mean) * rstd * gg.z + be.z, 0.f);
+                            const float y3 = fmaxf((v[k4 * 4 + 3] - mean) * rstd * gg.w + be.w, 0.f);
+                            const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            hi[k4h * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                            hi[k4h * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                            lo[k4h * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
+                            lo[k4h * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
+                        }
+                        // K elements [32q + 16hf, +16) -> cells [16q + 8hf, +8) of the hi block and of the lo block
+                        TMEM_ST_X8(tmem + lane_base + q * 16 + hf * 8, hi);
+                        TMEM_ST_X8(tmem + lane_base + 64 + q * 16 + hf * 8, lo);
                     }
-                    // K elements [32q, +32) -> cells [16q, +16) of the hi block and of the lo block
-                    TMEM_ST_X16(tmem + lane_base + q * 16, hi);
-                    TMEM_ST_X16(tmem + lane_base + 64 + q * 16, lo);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 tc_fence_before();
