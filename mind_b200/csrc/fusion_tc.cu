@@ -243,7 +243,7 @@ __device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_w
     if (++t.ch >= t.n_chunks) { t.wi += stride; tile_load_wi(t, work, n_work); }
 }
 
-__global__ void __maxnreg__(120)      // 17 warps x 32 x 120 registers = 65,280 <= 64K
+__global__ void __maxnreg__(112)      // 17 warps, 512-register allocation units per warp: 17 x 3584 <= 64K
 k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
