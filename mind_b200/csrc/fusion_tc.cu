@@ -243,7 +243,7 @@ __device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_w
     if (++t.ch >= t.n_chunks) { t.wi += stride; tile_load_wi(t, work, n_work); }
 }
 
-__global__ void __maxnreg__(112)      // 17 warps, 512-register allocation units per warp: 17 x 3584 <= 64K
+__global__ void __launch_bounds__(kThreads, 1)      // 17 warps are granted registers as 5 warpgroups -> 96 / thread
 k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -432,26 +432,34 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 tc_fence_after();
 
                 // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 (hi, lo) A operand in TMEM ----
-                float v[32];
+                // streaming 16-column passes; x = D1 + S + T is parked in this thread's own Dpe cells
+                // (free until G2 of this tile is issued) so nothing has to live in registers across the barrier
+                const uint32_t scr_t = tmem + lane_base + 128 + col0;
                 {
-                    uint32_t r[32];
-                    TMEM_LD_X32(tmem + lane_base + col0, r);
-                    tmem_wait_ld();
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const int c = col0 + k4 * 4;
-                        const float4 s = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
-                        const float4 t = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
-                        const float x0 = __uint_as_float(r[k4 * 4 + 0]) + s.x + t.x;
-                        const float x1 = __uint_as_float(r[k4 * 4 + 1]) + s.y + t.y;
-                        const float x2 = __uint_as_float(r[k4 * 4 + 2]) + s.z + t.z;
-                        const float x3 = __uint_as_float(r[k4 * 4 + 3]) + s.w + t.w;
-                        v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
-                        s1 += (x0 + x1) + (x2 + x3);
-                        s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t r[16];
+                        TMEM_LD_X16(tmem + lane_base + col0 + hf * 16, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const int c = col0 + hf * 16 + k4 * 4;
+                            const float4 sv = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
+                            const float4 tv = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
+                            const float x0 = __uint_as_float(r[k4 * 4 + 0]) + sv.x + tv.x;
+                            const float x1 = __uint_as_float(r[k4 * 4 + 1]) + sv.y + tv.y;
+                            const float x2 = __uint_as_float(r[k4 * 4 + 2]) + sv.z + tv.z;
+                            const float x3 = __uint_as_float(r[k4 * 4 + 3]) + sv.w + tv.w;
+                            r[k4 * 4 + 0] = __float_as_uint(x0); r[k4 * 4 + 1] = __float_as_uint(x1);
+                            r[k4 * 4 + 2] = __float_as_uint(x2); r[k4 * 4 + 3] = __float_as_uint(x3);
+                            s1 += (x0 + x1) + (x2 + x3);
+                            s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                        }
+                        TMEM_ST_X16(scr_t + hf * 16, r);
                     }
                     sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 tc_fence_before();
                 row_group_sync(lg);                                // statistics exchanged, D1 reads of these lanes retired
@@ -463,23 +471,25 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {                 // two 16-column halves keep the live registers low
-                        uint32_t hi[8], lo[8];
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t r[16], hi[8], lo[8];
+                        TMEM_LD_X16(scr_t + hf * 16, r);
+                        tmem_wait_ld();
 #pragma unroll
-                        for (int k4h = 0; k4h < 4; ++k4h) {
-                            const int k4 = hf * 4 + k4h;
-                            const float4 gg = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + col0 + k4 * 4);
-                            const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + col0 + k4 * 4);
-                            const float y0 = fmaxf((v[k4 * 4 + 0] - mean) * rstd * gg.x + be.x, 0.f);
-                            const float y1 = fmaxf((v[k4 * 4 + 1] - mean) * rstd * gg.y + be.y, 0.f);
-                            const float y2 = fmaxf((v[k4 * 4 + 2] - mean) * rstd * gg.z + be.z, 0.f);
-                            const float y3 = fmaxf((v[k4 * 4 + 3] - mean) * rstd * gg.w + be.w, 0.f);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const int c = col0 + hf * 16 + k4 * 4;
+                            const float4 gg = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + c);
+                            const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + c);
+                            const float y0 = fmaxf((__uint_as_float(r[k4 * 4 + 0]) - mean) * rstd * gg.x + be.x, 0.f);
+                            const float y1 = fmaxf((__uint_as_float(r[k4 * 4 + 1]) - mean) * rstd * gg.y + be.y, 0.f);
+                            const float y2 = fmaxf((__uint_as_float(r[k4 * 4 + 2]) - mean) * rstd * gg.z + be.z, 0.f);
+                            const float y3 = fmaxf((__uint_as_float(r[k4 * 4 + 3]) - mean) * rstd * gg.w + be.w, 0.f);
                             const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
                             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            hi[k4h * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-                            hi[k4h * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                            lo[k4h * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
-                            lo[k4h * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
+                            hi[k4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                            hi[k4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                            lo[k4 * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
+                            lo[k4 * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
                         }
                         // K elements [32q + 16hf, +16) -> cells [16q + 8hf, +8) of the hi block and of the lo block
                         TMEM_ST_X8(tmem + lane_base + q * 16 + hf * 8, hi);
@@ -495,69 +505,92 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 if (a.has_edge) {
                     mbar_wait(bar_m2a, par, a.err, E_MMA2);
                     tc_fence_after();
-                    uint32_t r[32];
-                    TMEM_LD_X32(tmem + lane_base + 128 + col0, r);
-                    tmem_wait_ld();
-                    float s1 = 0.f, s2 = 0.f;
+                    {   // pass A: statistics of Dpe + b
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + col0 + k4 * 4);
-                        const float x0 = __uint_as_float(r[k4 * 4 + 0]) + bb.x, x1 = __uint_as_float(r[k4 * 4 + 1]) + bb.y;
-                        const float x2 = __uint_as_float(r[k4 * 4 + 2]) + bb.z, x3 = __uint_as_float(r[k4 * 4 + 3]) + bb.w;
-                        v[k4 * 4 + 0] = x0; v[k4 * 4 + 1] = x1; v[k4 * 4 + 2] = x2; v[k4 * 4 + 3] = x3;
-                        s1 += (x0 + x1) + (x2 + x3);
-                        s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t r[16];
+                            TMEM_LD_X16(scr_t + hf * 16, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + col0 + hf * 16 + k4 * 4);
+                                const float x0 = __uint_as_float(r[k4 * 4 + 0]) + bb.x, x1 = __uint_as_float(r[k4 * 4 + 1]) + bb.y;
+                                const float x2 = __uint_as_float(r[k4 * 4 + 2]) + bb.z, x3 = __uint_as_float(r[k4 * 4 + 3]) + bb.w;
+                                s1 += (x0 + x1) + (x2 + x3);
+                                s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                            }
+                        }
+                        sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
                     }
-                    sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
                     row_group_sync(lg);
-                    {
+                    {   // pass B: x = edge + ReLU(LN_p(Dpe + b)) written back to the same cells, statistics of x
                         const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
                         const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
                         const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
-                        s1 = 0.f; s2 = 0.f;
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
-                            const uint4 eu = ld_shared_v4(tX + tile_off + sw128(row, chunk0 + c8));
-                            const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
-                            const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
-                            const float4 ga = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8);
-                            const float4 gb = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + col0 + c8 * 8 + 4);
-                            const float4 ba = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8);
-                            const float4 bb = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + col0 + c8 * 8 + 4);
-                            const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t r[16];
+                            TMEM_LD_X16(scr_t + hf * 16, r);
+                            tmem_wait_ld();
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float u = fmaxf((v[c8 * 8 + e] - mean) * rstd * gv[e] + bv[e], 0.f);
-                                const float x = ev[e] + u;
-                                v[c8 * 8 + e] = x;
-                                s1 += x;
-                                s2 += x * x;
+                            for (int c8 = 0; c8 < 2; ++c8) {
+                                const int c = col0 + hf * 16 + c8 * 8;
+                                const uint4 eu = ld_shared_v4(tX + tile_off + sw128(row, chunk0 + hf * 2 + c8));
+                                const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
+                                const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+#pragma unroll
+                                for (int h4 = 0; h4 < 2; ++h4) {
+                                    const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + c + h4 * 4);
+                                    const float4 ga = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + c + h4 * 4);
+                                    const float4 ba = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + c + h4 * 4);
+                                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, gv[4] = {ga.x, ga.y, ga.z, ga.w}, av[4] = {ba.x, ba.y, ba.z, ba.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int k = c8 * 8 + h4 * 4 + e;
+                                        const float u = fmaxf((__uint_as_float(r[k]) + bv[e] - mean) * rstd * gv[e] + av[e], 0.f);
+                                        const float x = ev[h4 * 4 + e] + u;
+                                        r[k] = __float_as_uint(x);
+                                        s1 += x;
+                                        s2 += x * x;
+                                    }
+                                }
                             }
+                            TMEM_ST_X16(scr_t + hf * 16, r);
                         }
+                        sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
-                    sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
                     row_group_sync(lg);
-                    {
+                    {   // pass C: edge' = LN_e(x) -> fp16, in place in the smem tile
                         const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
                         const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
                         const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
-                            const float4 ga = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8);
-                            const float4 gb = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + col0 + c8 * 8 + 4);
-                            const float4 ba = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8);
-                            const float4 bb = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + col0 + c8 * 8 + 4);
-                            uint4 u;
-                            u.x = pack_h2((v[c8 * 8 + 0] - mean) * rstd * ga.x + ba.x, (v[c8 * 8 + 1] - mean) * rstd * ga.y + ba.y);
-                            u.y = pack_h2((v[c8 * 8 + 2] - mean) * rstd * ga.z + ba.z, (v[c8 * 8 + 3] - mean) * rstd * ga.w + ba.w);
-                            u.z = pack_h2((v[c8 * 8 + 4] - mean) * rstd * gb.x + bb.x, (v[c8 * 8 + 5] - mean) * rstd * gb.y + bb.y);
-                            u.w = pack_h2((v[c8 * 8 + 6] - mean) * rstd * gb.z + bb.z, (v[c8 * 8 + 7] - mean) * rstd * gb.w + bb.w);
-                            st_shared_v4(tX + tile_off + sw128(row, chunk0 + c8), u);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t r[16];
+                            TMEM_LD_X16(scr_t + hf * 16, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int c8 = 0; c8 < 2; ++c8) {
+                                const int c = col0 + hf * 16 + c8 * 8;
+                                const float4 ga = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + c);
+                                const float4 gb = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + c + 4);
+                                const float4 ba = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + c);
+                                const float4 bb = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + c + 4);
+                                const uint32_t* x = r + c8 * 8;
+                                uint4 u;
+                                u.x = pack_h2((__uint_as_float(x[0]) - mean) * rstd * ga.x + ba.x, (__uint_as_float(x[1]) - mean) * rstd * ga.y + ba.y);
+                                u.y = pack_h2((__uint_as_float(x[2]) - mean) * rstd * ga.z + ba.z, (__uint_as_float(x[3]) - mean) * rstd * ga.w + ba.w);
+                                u.z = pack_h2((__uint_as_float(x[4]) - mean) * rstd * gb.x + bb.x, (__uint_as_float(x[5]) - mean) * rstd * gb.y + bb.y);
+                                u.w = pack_h2((__uint_as_float(x[6]) - mean) * rstd * gb.z + bb.z, (__uint_as_float(x[7]) - mean) * rstd * gb.w + bb.w);
+                                st_shared_v4(tX + tile_off + sw128(row, chunk0 + hf * 2 + c8), u);
+                            }
                         }
                     }
                 }
@@ -569,20 +602,24 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const bool key_ok = (i0 + i_l < N);            // padded keys never enter the softmax
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        uint32_t rk[16], rv[16];
-                        TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
+                        uint32_t rv[16];
+                        float s = 0.f;
+                        {
+                            uint32_t rk[16];
+                            TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
+                                s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
+                                s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
+                                s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
+                                s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                            }
+                        }
                         TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
                         tmem_wait_ld();
                         if (!key_ok) continue;
-                        float s = 0.f;
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
-                            s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
-                            s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
-                            s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
-                            s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
-                        }
                         const float mnew = fmaxf(mrun[h], s);
                         const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
                         const float p = __expf(s - mnew);
