@@ -291,14 +291,21 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             tma_load_4d(dst, &emap, bl, 0, t.j0, t.ch * 8, t.b);
             tma_load_4d(dst + 16384, &emap, bl, 64, t.j0, t.ch * 8, t.b);
         };
-        auto stage_T = [&](const TileIt& t) {                     // whole warp: T (target term) rows of the tile's 8 keys
+        float4 tpre[8];                                            // T rows of the NEXT tile, prefetched into registers
+        auto fetch_T = [&](const TileIt& t) {                     // whole warp: issue the global loads only
             const int64_t tok0 = (int64_t)t.b * a.Nmax;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int idx = it * 32 + lane, ii = idx >> 5, c4 = idx & 31;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t.ch * 8 + ii < t.n) v = reinterpret_cast<const float4*>(a.stq + (tok0 + t.ch * 8 + ii) * 384 + 128)[c4];
-                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = v;
+                tpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t.ch * 8 + ii < t.n) tpre[it] = reinterpret_cast<const float4*>(a.stq + (tok0 + t.ch * 8 + ii) * 384 + 128)[c4];
+            }
+        };
+        auto publish_T = [&]() {                                  // whole warp: registers -> sT, then signal
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int idx = it * 32 + lane, ii = idx >> 5, c4 = idx & 31;
+                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = tpre[it];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_t);
@@ -323,7 +330,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 load_tile(cur_t, 0);
                 if (tile_valid(nxt, a.n_work)) load_tile(nxt, 1);
             }
-            stage_T(cur_t);
+            fetch_T(cur_t);
+            publish_T();
             if (lane == 0) {
                 mbar_wait(bar_ld0, 0, a.err, E_LOAD_EDGE);
                 tc_fence_after();
@@ -333,6 +341,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 const int buf = g & 1;
                 const uint32_t par = g & 1;
                 const bool has_next = tile_valid(nxt, a.n_work);
+                if (has_next) fetch_T(nxt);                       // global loads in flight while we wait for the A operand
                 if (lane == 0) {
                     // [A] A operand of this tile is in TMEM -> G2 (W_pe first: its epilogue overlaps the K|V MMAs)
                     mbar_wait(bar_a, par, a.err, E_MMA2);
@@ -360,12 +369,13 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 __syncwarp();
                 // [B] next tile: T rows (every epilogue warp is past epilogue 1 of this tile), then G1 behind G2
                 if (has_next) {
-                    stage_T(nxt);
                     if (lane == 0) {
                         mbar_wait(bar_ld0 + 8 * (buf ^ 1), ((g + 1) >> 1) & 1, a.err, E_LOAD_EDGE);
                         tc_fence_after();
                         issue_g1(buf ^ 1);
                     }
+                    __syncwarp();
+                    publish_T();                                   // every epilogue warp is past epilogue 1 of this tile (bar_a)
                 }
                 // [C] edge' tile complete -> TMA store ; [D] buffer free -> load the tile after next
                 TileIt nn = nxt;
