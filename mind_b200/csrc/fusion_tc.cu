@@ -35,7 +35,7 @@ constexpr uint32_t SM_T = SM_Q + 16 * 132 * 4;        // float [8][132]
 constexpr uint32_t SM_P = SM_T + 8 * 132 * 4;         // float [8][128] layer params
 constexpr uint32_t SM_STAT = SM_P + 8 * 128 * 4;      // float2 [2 buf][4 quarter][128]
 constexpr uint32_t SM_BAR = SM_STAT + 2 * 4 * 128 * 8;
-constexpr uint32_t SM_TMEM = SM_BAR + 96;
+constexpr uint32_t SM_TMEM = SM_BAR + 96;   // 10 mbarriers
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SM_TOTAL + 1024;      // slack for manual 1024 B alignment
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -256,13 +256,13 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
     const uint32_t bar_w = sbase + SM_BAR;
     const uint32_t bar_m1 = bar_w + 8, bar_m2a = bar_w + 16, bar_m2b = bar_w + 24, bar_ld0 = bar_w + 32;   // +32, +40
-    const uint32_t bar_a = bar_w + 48, bar_e = bar_w + 56, bar_t = bar_w + 64;
+    const uint32_t bar_a = bar_w + 48, bar_e = bar_w + 56, bar_t = bar_w + 64, bar_k = bar_w + 72;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2a, 1); mbar_init(bar_m2b, 1);
         mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
-        mbar_init(bar_a, 16); mbar_init(bar_e, 16); mbar_init(bar_t, 1);
+        mbar_init(bar_a, 16); mbar_init(bar_e, 16); mbar_init(bar_t, 1); mbar_init(bar_k, 16);
         fence_barrier_init();
     }
     if (warp == 16) {
@@ -357,6 +357,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         }
                     }
                     umma_commit(bar_m2a);
+                    mbar_wait(bar_k, par, a.err, E_MMA2 + 2);      // Dk/Dv of the previous tile have been consumed
+                    tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
@@ -432,6 +434,42 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 32; ++k) acc[k] = 0.f;
             mrun[0] = mrun[1] = -INFINITY; lrun[0] = lrun[1] = 0.f;
+
+            // ---- epilogue 2b: per-thread online softmax over this thread's key, 2 heads.  Runs one tile late
+            // (right after the A operand of the NEXT tile is handed over) so that it overlaps the W_pe MMAs.
+            auto attend = [&](uint32_t tile_par, bool key_ok) {
+                mbar_wait(bar_m2b, tile_par, a.err, E_MMA2);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t rv[16];
+                    float s = 0.f;
+                    {
+                        uint32_t rk[16];
+                        TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
+                            s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
+                            s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
+                            s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
+                            s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                        }
+                    }
+                    TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
+                    tmem_wait_ld();
+                    if (!key_ok) continue;
+                    const float mnew = fmaxf(mrun[h], s);
+                    const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
+                    const float p = __expf(s - mnew);
+                    lrun[h] = lrun[h] * corr + p;
+                    mrun[h] = mnew;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[h * 16 + k] = fmaf(p, __uint_as_float(rv[k]), acc[h * 16 + k] * corr);
+                }
+                tc_fence_before();
+            };
 
             for (int ch = 0; ch < n_chunks; ++ch, ++g) {
                 const int i0 = ch * 8;
@@ -510,6 +548,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_a);                 // this warp's slice of the A operand is in TMEM
+                if (ch > 0) attend(par ^ 1, (i0 - 8 + i_l) < N);   // attention epilogue of the previous tile, under the W_pe MMAs
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_k);                 // Dk/Dv free: the issuer may run the K|V MMAs of this tile
 
                 // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
                 if (a.has_edge) {
@@ -605,40 +646,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     }
                 }
 
-                // ---- epilogue 2b: per-thread online softmax over this thread's key (i0 + i_l), 2 heads ----
-                mbar_wait(bar_m2b, par, a.err, E_MMA2);
-                tc_fence_after();
-                {
-                    const bool key_ok = (i0 + i_l < N);            // padded keys never enter the softmax
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t rv[16];
-                        float s = 0.f;
-                        {
-                            uint32_t rk[16];
-                            TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
-                                s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
-                                s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
-                                s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
-                                s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
-                            }
-                        }
-                        TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
-                        tmem_wait_ld();
-                        if (!key_ok) continue;
-                        const float mnew = fmaxf(mrun[h], s);
-                        const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
-                        const float p = __expf(s - mnew);
-                        lrun[h] = lrun[h] * corr + p;
-                        mrun[h] = mnew;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) acc[h * 16 + k] = fmaf(p, __uint_as_float(rv[k]), acc[h * 16 + k] * corr);
-                    }
-                }
                 if (a.has_edge) fence_proxy_async();               // edge' (generic stores) -> visible to the TMA store
                 tc_fence_before();
                 __syncwarp();
@@ -646,6 +653,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 row_group_sync(lg);                                // statistics buffers can be reused by the next tile
             }
 
+            attend((g - 1) & 1, ((n_chunks - 1) * 8 + i_l) < N);   // attention epilogue of the work item's last tile
             // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
             // lanes l and l^16 hold key slots 2*lg and 2*lg+1 of the same query
 #pragma unroll
