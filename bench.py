@@ -164,7 +164,8 @@ def bench_tree(net, dev, reps=5):
             torch.cuda.synchronize()
             times.append((time.perf_counter() - t0) * 1e3)
         out[name] = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches),
-                     "nodes": gen.tree.size(), "trees": len(trees)}
+                     "nodes": gen.tree.size(), "trees": len(trees),
+                     "host_phase_ms_last": {k: round(v * 1e3, 3) for k, v in gen.timing.items()}}
     return out
 
 

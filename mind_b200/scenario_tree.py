@@ -32,8 +32,14 @@ except Exception:                                       # stand-alone: structura
             return "Node_%s: Parent: %s, Children: %s" % (self.key, self.parent_key, self.children_keys)
 
     class Tree:
+        """Same interface and leaf ordering as planners/basic/tree.py; leaves are kept in an insertion-ordered
+        dict so that attaching a child is O(1) (the reference's list.remove makes big trees quadratic)."""
         def __init__(self):
-            self.nodes, self.root, self.leaves = {}, None, []
+            self.nodes, self.root, self._leaves = {}, None, {}
+
+        @property
+        def leaves(self):
+            return list(self._leaves)
 
         def get_node(self, key):
             return self.nodes[key]
@@ -54,24 +60,23 @@ except Exception:                                       # stand-alone: structura
             if node.parent_key is None and not self.nodes:
                 self.nodes[node.key] = node
                 self.root = node.key
-                self.leaves.append(node.key)
+                self._leaves[node.key] = None
                 return
             if node.parent_key not in self.nodes:
                 raise KeyError("Parent does not exist.")
             if node.key in self.nodes:
                 raise ValueError("Node key already exists.")
             self.nodes[node.parent_key].children_keys.append(node.key)
-            if node.parent_key in self.leaves:
-                self.leaves.remove(node.parent_key)
+            self._leaves.pop(node.parent_key, None)
             node.depth = self.nodes[node.parent_key].depth + 1
             self.nodes[node.key] = node
-            self.leaves.append(node.key)
+            self._leaves[node.key] = None
 
         def get_leaf_nodes(self):
-            return [self.nodes[k] for k in self.leaves]
+            return [self.nodes[k] for k in self._leaves]
 
         def get_leaf_keys(self):
-            return self.leaves
+            return list(self._leaves)
 
         def retrieve_nodes_to_root(self, key):
             out, cur = [], self.nodes[key]
@@ -120,6 +125,7 @@ class ScenarioTreeGeneratorB200:
         self.net_batches: List[int] = []
         self._lib = _lib.load()
         self._levels: List[_Level] = []
+        self.timing = {}                # seconds per phase of the last rollout (host wall clock)
         self.front_end = None           # optional callable (lcl_smp, agent_obs) -> collated scene dict
         # benchmark mode: keep all 6 modes of every scene, branch at fixed times
         self.force_full = None          # e.g. (10, 20, 30): children of level d branch at force_full[d]
@@ -147,22 +153,38 @@ class ScenarioTreeGeneratorB200:
                                       "collated scene dict, or call rollout(data)")
         return self.front_end(lcl_smp, agent_obs)
 
+    def _tick(self, name, t0):
+        import time
+        self.timing[name] = self.timing.get(name, 0.0) + (time.perf_counter() - t0)
+        return time.perf_counter()
+
     def rollout(self, data):
         """AIME iteration from a collated one-scene dict (what process_data returns)."""
+        import time
+        self.timing = {}
+        t = time.perf_counter()
         self.init_scenario_tree(data)
+        t = self._tick("root_level", t)
         nodes = self.get_branch_set()
         guard = 0
         while nodes:
             level = self._levels[-1]
             self.predict_scenes(level)
-            self.create_nodes(self.prune_merge(level, nodes))
+            t = self._tick("predict", t)
+            pm = self.prune_merge(level, nodes)
+            t = self._tick("tree_level+d2h", t)
+            self.create_nodes(pm)
+            t = self._tick("create_nodes", t)
             self.decide_branch()
+            t = self._tick("decide+update", t)
             nodes = self.get_branch_set()
             guard += 1
             if guard > 64:
                 raise RuntimeError("scenario tree did not converge (re-expansion loop, reference quirk :84-100)")
         assert len(self.get_end_set()) > 0, "No end node found in the scenario tree."
-        return self.get_scenario_tree()
+        out = self.get_scenario_tree()
+        self._tick("pack_output", t)
+        return out
 
     # ---- level construction -----------------------------------------------------------------
     def _root_level(self, data) -> _Level:
@@ -392,9 +414,9 @@ class ScenarioTreeGeneratorB200:
                 if len(dn.data) == 1:
                     cpos, ccov, tgt = level_host(rec["level"])
                     f, k = rec["row"] // 6, rec["row"] % 6
-                    dn.data += [np.ascontiguousarray(cpos[f, k, :, self.obs_len:self.obs_len + dur, :]),
-                                np.ascontiguousarray(ccov[f, k, :, self.obs_len:self.obs_len + dur, None]),
-                                tgt[f].copy()]
+                    dn.data += [cpos[f, k, :, self.obs_len:self.obs_len + dur, :],
+                                ccov[f, k, :, self.obs_len:self.obs_len + dur, None],
+                                tgt[f]]
                 n = self.tree.get_node(n.parent_key)
         trees = []
         for key in data_tree.get_root().children_keys:
