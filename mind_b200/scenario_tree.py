@@ -248,8 +248,8 @@ class ScenarioTreeGeneratorB200:
         level.cang = torch.empty(F, 6, Na, 100, **f32)
         level.ccov = torch.empty(F, 6, Na, 100, **f32)
         level.gpos = torch.empty(F, 6, Na, 60, 2, **f32)
-        ibuf = torch.empty(3, F, 6, device=dev, dtype=torch.int32)      # order, keep, tb
-        cprob = torch.empty(F, 6, **f32)
+        ibuf = torch.empty(4, F, 6, device=dev, dtype=torch.int32)      # order, keep, tb | cprob (fp32 bits): one D2H
+        cprob = ibuf[3].view(torch.float32)
         a = _lib.MindTreeLevel()
         a.n_frontier, a.n_actor, a.obs_len, a.pred_len = F, Na, self.obs_len, self.pred_len
         a.ego_idx = self.ego_idx if self.ego_idx is not None else -1
@@ -267,7 +267,7 @@ class ScenarioTreeGeneratorB200:
             raise RuntimeError(self._lib.mind_tree_last_error().decode())
         lv_index = next(i for i, L in enumerate(self._levels) if L is level)
         ih = ibuf.cpu().numpy()                                           # the level's only D2H: decisions
-        ph = cprob.cpu().numpy()
+        ph = ih[3].view(np.float32)
         if self.force_full is not None:
             ih[1] = 1
             ih[2] = self.force_full[lv_index] if lv_index < len(self.force_full) else self.pred_len
@@ -380,7 +380,8 @@ class ScenarioTreeGeneratorB200:
         root = self.tree.get_root()
         data_tree.add_node(Node(root.key, None, [1.0]))
         for n in self.get_end_set():                                   # label the branches that finished
-            while n.parent_key is not None:
+            n = self.tree.get_node(n.parent_key) if n.parent_key is not None else n
+            while n.parent_key is not None and not n.data.end_flag:   # ancestors already labelled: stop early
                 n.data.end_flag = True
                 n = self.tree.get_node(n.parent_key)
         for key in root.children_keys:
@@ -406,18 +407,16 @@ class ScenarioTreeGeneratorB200:
                 L = self._levels[lv]
                 host[lv] = (L.cpos.cpu().numpy(), L.ccov.cpu().numpy(), L.tgt_pts.cpu().numpy())
             return host[lv]
-        for n in self.get_end_set():
-            while n.parent_key is not None:
-                rec = n.data.rec
-                dur = rec["end_t"] - rec["cur_t"]
-                dn = data_tree.get_node(n.key)
-                if len(dn.data) == 1:
-                    cpos, ccov, tgt = level_host(rec["level"])
-                    f, k = rec["row"] // 6, rec["row"] % 6
-                    dn.data += [cpos[f, k, :, self.obs_len:self.obs_len + dur, :],
-                                ccov[f, k, :, self.obs_len:self.obs_len + dur, None],
-                                tgt[f]]
-                n = self.tree.get_node(n.parent_key)
+        for key, dn in data_tree.nodes.items():                        # every labelled node gets its payload once
+            if key == root.key or len(dn.data) != 1:
+                continue
+            rec = self.tree.get_node(key).data.rec
+            dur = rec["end_t"] - rec["cur_t"]
+            cpos, ccov, tgt = level_host(rec["level"])
+            f, k = rec["row"] // 6, rec["row"] % 6
+            dn.data += [cpos[f, k, :, self.obs_len:self.obs_len + dur, :],
+                        ccov[f, k, :, self.obs_len:self.obs_len + dur, None],
+                        tgt[f]]
         trees = []
         for key in data_tree.get_root().children_keys:
             st = Tree()
