@@ -24,6 +24,10 @@ void launch_gemm(const GemmArgs& g, cudaStream_t st);
 void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta,
                       float* out, int64_t rows, int D, int relu, cudaStream_t st);
 
+// D = 128 LayerNorm that also writes the fp16 (hi, lo) operand split for the tensor-core GEMM engine
+void launch_layernorm_hl(const float* x, const float* res, const float* gamma, const float* beta, float* out32, __half* hi,
+                         __half* lo, int64_t rows, int relu, cudaStream_t st);
+
 // max over groups of `g` consecutive rows: in [G*g, D] -> out [G, D]
 void launch_group_max(const float* in, float* out, int64_t G, int g, int D, cudaStream_t st);
 

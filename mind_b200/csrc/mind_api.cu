@@ -69,6 +69,9 @@ struct MindCtx {
     FusionLayerW fl[6]{};
     TcWeights tc{};               // fp16 packed weights / per-layer params for the tensor-core path
     ActorTc actor_tc{};           // ActorNet on the tensor-core GEMM engine
+    struct LaneW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; const float* bias = nullptr; };
+    LaneW lane_tc[2][4];          // per aggregate block: fc1.0, fc1.3, fc2.0[:, :128], fc2.3 as [128][hi 128 | lo 128] fp16
+    int* lane_err = nullptr;
     // descriptor tables
     SceneDesc* d_sd = nullptr; int sd_cap = 0;
     int32_t* d_actor_scene = nullptr; int as_cap = 0;
@@ -106,6 +109,8 @@ extern "C" void mind_destroy(MindCtx* c) {
     if (c->d_actor_scene) cudaFree(c->d_actor_scene);
     tc_free(c->tc);
     actor_tc_free(c->actor_tc);
+    for (auto& blk : c->lane_tc) for (auto& lw : blk) if (lw.W) cudaFree(lw.W);
+    if (c->lane_err) cudaFree(c->lane_err);
     delete c;
 }
 
@@ -311,6 +316,29 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
         if (err) return fail("tc_pack_weights: %s", err);
         err = actor_tc_pack(c->actor_tc, c->host_w, c->dev_w);
         if (err) return fail("actor_tc_pack: %s", err);
+        // LaneNet linears as [N=128][hi K=128 | lo K=128] fp16 operands of the GEMM engine
+        const char* lnames[4] = {"fc1.0", "fc1.3", "fc2.0", "fc2.3"};
+        for (int blk = 0; blk < 2; ++blk)
+            for (int j = 0; j < 4; ++j) {
+                const std::string P = "lane_net.aggre" + std::to_string(blk + 1) + "." + lnames[j];
+                const std::vector<float>* Wv = find(c, P + ".weight");
+                if (!Wv) return fail("missing %s", P.c_str());
+                const int ldw = (j == 2) ? 256 : 128;
+                std::vector<__half> Wp((size_t)128 * 256);
+                for (int o = 0; o < 128; ++o)
+                    for (int k = 0; k < 128; ++k) {
+                        const float wv = (*Wv)[(size_t)o * ldw + k];
+                        const __half hh = __float2half_rn(wv);
+                        Wp[(size_t)o * 256 + k] = hh;
+                        Wp[(size_t)o * 256 + 128 + k] = __float2half_rn(wv - __half2float(hh));
+                    }
+                MindCtx::LaneW& lw = c->lane_tc[blk][j];
+                if (!lw.W) CUDA_OK(cudaMalloc(&lw.W, Wp.size() * sizeof(__half)));
+                CUDA_OK(cudaMemcpy(lw.W, Wp.data(), Wp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                if (const char* e2 = tcg_encode_w(lw.wmap, lw.W, 256, 128, 128)) return fail("lane wmap: %s", e2);
+                lw.bias = (j == 2) ? nullptr : c->dev_w.at(P + ".bias");
+            }
+        if (!c->lane_err) { CUDA_OK(cudaMalloc(&c->lane_err, sizeof(int))); CUDA_OK(cudaMemset(c->lane_err, 0, sizeof(int))); }
     }
     c->finalized = true;
     return 0;
@@ -344,6 +372,8 @@ struct Ws {
     // tensor-core path
     __half* edge16;
     char* actor_ws;
+    __half *lh[3], *ll[3];     // lane-net fp16 hi/lo operand buffers [R,128]
+    float* lt32;
     // decoder
     float *actors_f, *cls_tok, *tr, *tg1, *tgt, *c1, *ce, *qkv, *att, *co, *f1, *f2, *a1, *ae, *embed, *h1, *h2, *param;
     float *k1, *k2, *logit;
@@ -378,10 +408,14 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w
         w.kv = cv.take<float>(C * pairs * 256);
         w.edge16 = nullptr;
         w.actor_ws = nullptr;
+        for (int i = 0; i < 3; ++i) w.lh[i] = w.ll[i] = nullptr;
+        w.lt32 = nullptr;
     } else {
         w.edge = w.tmp = w.memory = w.kv = nullptr;
         w.edge16 = cv.take<__half>((int64_t)B * pairs * 128);
         w.actor_ws = cv.take<char>(actor_tc_ws_bytes(A));
+        for (int i = 0; i < 3; ++i) { w.lh[i] = cv.take<__half>(R * 128 + 512); w.ll[i] = cv.take<__half>(R * 128 + 512); }
+        w.lt32 = cv.take<float>(R * 128);
     }
     w.actors_f = cv.take<float>((int64_t)A * 128);
     w.cls_tok = cv.take<float>((int64_t)B * 128);
@@ -460,6 +494,49 @@ static void run_lane_net(MindCtx* c, const Ws& w, int64_t Lp, cudaStream_t st) {
             launch_group_max(w.la, w.lane_feat, Lp, 10, 128, st);
         }
     }
+}
+
+// LaneNet with its eight [R,128]x[128,128] linears on the tcgen05 GEMM engine (3-term fp16 split, fp32-equivalent);
+// LayerNorm kernels emit the (hi, lo) operands.  Same dataflow as run_lane_net (network.py:64-121).
+static const char* run_lane_net_tc(MindCtx* c, const Ws& w, int64_t Lp, cudaStream_t st) {
+    Lin L{c, st};
+    const int64_t R = Lp * 10;
+    const char* err = nullptr;
+    auto tc = [&](const __half* ah, const __half* al, const MindCtx::LaneW& lw, float* C, const float* gbias) {
+        if (err) return;
+        alignas(64) unsigned char mh[128], ml[128];
+        if ((err = tcg_encode_a(mh, ah, 128, R, 1, 128, R * 128, 128, 1))) return;
+        if ((err = tcg_encode_a(ml, al, 128, R, 1, 128, R * 128, 128, 1))) return;
+        TcGemm g;
+        g.amap_hi = mh; g.amap_lo = ml; g.wmap = lw.wmap; g.split = 1; g.k_blocks = 2;
+        g.r_in = 128; g.r_out = 1; g.L_inner = (int)R; g.n_outer = 1; g.N = 128; g.n_tile = 128;
+        g.C = C; g.ldc = 128; g.bias = lw.bias; g.gbias = gbias; g.gsize = 10; g.ldg = 128; g.err = c->lane_err;
+        err = tcg_launch(g, c->sm_count, st);
+    };
+    // proj (K = 16: SIMT), x -> fp32 + hi/lo
+    L.gemm(w.lane_in, 16, L.W("lane_net.proj.0.weight"), 16, L.W("lane_net.proj.0.bias"), w.lt32, 128, R, 128, 16);
+    launch_layernorm_hl(w.lt32, nullptr, L.W("lane_net.proj.1.weight"), L.W("lane_net.proj.1.bias"), w.lx, w.lh[0], w.ll[0], R, 1, st);
+    for (int blk = 0; blk < 2 && !err; ++blk) {
+        const std::string P = "lane_net.aggre" + std::to_string(blk + 1) + ".";
+        tc(w.lh[0], w.ll[0], c->lane_tc[blk][0], w.lt32, nullptr);
+        launch_layernorm_hl(w.lt32, nullptr, L.W(P + "fc1.1.weight"), L.W(P + "fc1.1.bias"), nullptr, w.lh[1], w.ll[1], R, 1, st);
+        tc(w.lh[1], w.ll[1], c->lane_tc[blk][1], w.lt32, nullptr);
+        launch_layernorm_hl(w.lt32, nullptr, L.W(P + "fc1.4.weight"), L.W(P + "fc1.4.bias"), w.ly, w.lh[2], w.ll[2], R, 1, st);
+        launch_group_max(w.ly, w.lm, Lp, 10, 128, st);
+        const float* W20 = L.W(P + "fc2.0.weight");
+        L.gemm(w.lm, 128, W20 + 128, 256, L.W(P + "fc2.0.bias"), w.lgb, 128, Lp, 128, 128);
+        tc(w.lh[2], w.ll[2], c->lane_tc[blk][2], w.lt32, w.lgb);
+        launch_layernorm_hl(w.lt32, nullptr, L.W(P + "fc2.1.weight"), L.W(P + "fc2.1.bias"), nullptr, w.lh[1], w.ll[1], R, 1, st);
+        tc(w.lh[1], w.ll[1], c->lane_tc[blk][3], w.lt32, nullptr);
+        launch_layernorm(w.lt32, nullptr, L.W(P + "fc2.4.weight"), L.W(P + "fc2.4.bias"), w.ly, R, 128, 1, st);
+        if (blk == 0) {
+            launch_layernorm_hl(w.lx, w.ly, L.W(P + "norm.weight"), L.W(P + "norm.bias"), w.lx, w.lh[0], w.ll[0], R, 0, st);
+        } else {
+            launch_layernorm(w.lx, w.ly, L.W(P + "norm.weight"), L.W(P + "norm.bias"), w.la, R, 128, 0, st);
+            launch_group_max(w.la, w.lane_feat, Lp, 10, 128, st);
+        }
+    }
+    return err;
 }
 
 // node-side tail of a rela-fusion layer on token rows [r0, r0+rows): out-proj, LN2, FFN, LN3
@@ -581,7 +658,11 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         CUDA_OK(cudaMemcpyAsync(w.lane_in, bt->lanes, sizeof(float) * (size_t)Ltot * 160, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemcpyAsync(w.lane_in + (int64_t)Ltot * 160, bt->tgt_nodes, sizeof(float) * (size_t)B * 160,
                             cudaMemcpyDeviceToDevice, st));
-    run_lane_net(c, w, Lp, st);                                                             // :587,589
+    if (c->precision == MIND_PREC_F16TC && !c->actor_simt) {                                // :587,589
+        if (const char* e = run_lane_net_tc(c, w, Lp, st)) return fail("run_lane_net_tc: %s", e);
+    } else {
+        run_lane_net(c, w, Lp, st);
+    }
     PROF_NEXT("lane_net");
     const float* tgt_feat = w.lane_feat + (int64_t)Ltot * 128;
     // ---- fusion ---------------------------------------------------------------------------

@@ -269,6 +269,45 @@ void launch_layernorm(const float* x, const float* res, const float* gamma, cons
     ++g_launches;
 }
 
+// LayerNorm over D = 128 that also emits the fp16 (hi, lo) split consumed by the tensor-core GEMM engine
+__global__ void __launch_bounds__(256) k_layernorm_hl(const float* __restrict__ x, const float* __restrict__ res,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ out32, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                      int64_t rows, int relu) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float4 t = reinterpret_cast<const float4*>(x + row * 128)[lane];
+    if (res) {
+        const float4 r = reinterpret_cast<const float4*>(res + row * 128)[lane];
+        t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+    }
+    const float mean = warp_sum((t.x + t.y) + (t.z + t.w)) * (1.f / 128.f);
+    const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+    const float rstd = rsqrtf(warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f) + LN_EPS);
+    const float4 gm = reinterpret_cast<const float4*>(gamma)[lane];
+    const float4 bt = reinterpret_cast<const float4*>(beta)[lane];
+    float y[4] = {a * rstd * gm.x + bt.x, b * rstd * gm.y + bt.y, c * rstd * gm.z + bt.z, d * rstd * gm.w + bt.w};
+    if (relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
+    if (out32) reinterpret_cast<float4*>(out32 + row * 128)[lane] = make_float4(y[0], y[1], y[2], y[3]);
+    if (hi) {
+        const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), l23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
+        uint2 uh, ul;
+        uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+        ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+        reinterpret_cast<uint2*>(hi + row * 128)[lane] = uh;
+        reinterpret_cast<uint2*>(lo + row * 128)[lane] = ul;
+    }
+}
+void launch_layernorm_hl(const float* x, const float* res, const float* gamma, const float* beta, float* out32, __half* hi,
+                         __half* lo, int64_t rows, int relu, cudaStream_t st) {
+    if (rows <= 0) return;
+    k_layernorm_hl<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, res, gamma, beta, out32, hi, lo, rows, relu);
+    ++g_launches;
+}
+
 __global__ void k_group_max(const float* __restrict__ in, float* __restrict__ out, int64_t G, int g, int D) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= G * D) return;

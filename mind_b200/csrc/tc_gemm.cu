@@ -105,6 +105,7 @@ struct Args {
     int N, n_tile;
     float* C; int ldc;
     const float* bias; int relu;
+    const float* gbias; int gsize, ldg;     // per row-group bias [(row / gsize), N]
     float* stats;
     int* err;
 };
@@ -185,7 +186,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
             const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
             const int outer = o * g.r_out + row / g.r_in, inner = c * g.r_in + row % g.r_in;
             const bool valid = outer < g.n_outer && inner < g.L_inner;
-            float* crow = g.C + ((int64_t)outer * g.L_inner + inner) * g.ldc;
+            const int64_t orow = (int64_t)outer * g.L_inner + inner;
+            float* crow = g.C + orow * g.ldc;
+            const float* grow = (g.gbias && valid) ? g.gbias + (orow / g.gsize) * g.ldg : nullptr;
             mbar_wait(bars + 64 + 8 * acc, acc_phase, g.err, 14);
             tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
@@ -203,6 +206,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                         float x = __uint_as_float(r[k4 * 4 + e]);
                         if (n < g.N) {
                             if (g.bias) x += __ldg(g.bias + n);
+                            if (grow) x += __ldg(grow + n);
                             if (g.relu) x = fmaxf(x, 0.f);
                             s1 += x; s2 += x * x;
                         }
@@ -290,15 +294,37 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
     __syncthreads();
     const float mean = sm[0], rstd = sm[1];
     const int n = p.L * p.C;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i4 = threadIdx.x; i4 < (n >> 2); i4 += blockDim.x) {      // C % 4 == 0: 4 channels per iteration
+        const int i = i4 << 2;
         const int t = i / p.C, c = i - t * p.C;
-        float y = (p.raw[(int64_t)a * n + i] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
+        const float4 x = *reinterpret_cast<const float4*>(p.raw + (int64_t)a * n + i);
+        const float4 gm = *reinterpret_cast<const float4*>(p.gamma + c), bt = *reinterpret_cast<const float4*>(p.beta + c);
+        float y[4] = {(x.x - mean) * rstd * gm.x + bt.x, (x.y - mean) * rstd * gm.y + bt.y,
+                      (x.z - mean) * rstd * gm.z + bt.z, (x.w - mean) * rstd * gm.w + bt.w};
         const int64_t pidx = ((int64_t)a * (p.L + 2) + t + 1) * p.C + c;
-        if (p.res_raw) y += (p.res_raw[(int64_t)a * n + i] - sm[2]) * sm[3] * __ldg(p.res_gamma + c) + __ldg(p.res_beta + c);
-        else if (p.res_hi) y += __half2float(p.res_hi[pidx]) + __half2float(p.res_lo[pidx]);
-        if (p.relu) y = fmaxf(y, 0.f);
-        if (p.out_hi) split_store(p.out_hi, p.out_lo, pidx, y);
-        if (p.out_f32) p.out_f32[(int64_t)a * n + i] = y;
+        if (p.res_raw) {
+            const float4 r = *reinterpret_cast<const float4*>(p.res_raw + (int64_t)a * n + i);
+            const float4 g2 = *reinterpret_cast<const float4*>(p.res_gamma + c), b2 = *reinterpret_cast<const float4*>(p.res_beta + c);
+            y[0] += (r.x - sm[2]) * sm[3] * g2.x + b2.x; y[1] += (r.y - sm[2]) * sm[3] * g2.y + b2.y;
+            y[2] += (r.z - sm[2]) * sm[3] * g2.z + b2.z; y[3] += (r.w - sm[2]) * sm[3] * g2.w + b2.w;
+        } else if (p.res_hi) {
+            const uint2 h = *reinterpret_cast<const uint2*>(p.res_hi + pidx), l = *reinterpret_cast<const uint2*>(p.res_lo + pidx);
+            const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+            y[0] += h0.x + l0.x; y[1] += h0.y + l0.y; y[2] += h1.x + l1.x; y[3] += h1.y + l1.y;
+        }
+        if (p.relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
+        if (p.out_hi) {
+            const __half2 a01 = __floats2half2_rn(y[0], y[1]), a23 = __floats2half2_rn(y[2], y[3]);
+            const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
+            const __half2 b01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), b23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
+            uint2 uh, ul;
+            uh.x = *reinterpret_cast<const uint32_t*>(&a01); uh.y = *reinterpret_cast<const uint32_t*>(&a23);
+            ul.x = *reinterpret_cast<const uint32_t*>(&b01); ul.y = *reinterpret_cast<const uint32_t*>(&b23);
+            *reinterpret_cast<uint2*>(p.out_hi + pidx) = uh;
+            *reinterpret_cast<uint2*>(p.out_lo + pidx) = ul;
+        }
+        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)a * n + i) = make_float4(y[0], y[1], y[2], y[3]);
     }
     if (p.out_hi) {   // zero pad rows t = 0 and t = L+1
         for (int c = threadIdx.x; c < 2 * p.C; c += blockDim.x) {
@@ -416,6 +442,7 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.tiles_outer = (p.n_outer + p.r_out - 1) / p.r_out;
     g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
     g.C = p.C; g.ldc = p.ldc; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
+    g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
     const int total = g.tiles_inner * g.tiles_outer * g.tiles_n;
     if (total <= 0) return nullptr;
     CUtensorMap a0, a1, w;

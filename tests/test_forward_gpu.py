@@ -150,9 +150,13 @@ def test_actor_net_tensor_core_stage(ckpt_sd, rand_sd, dev):
     net = make_net(ckpt_sd, dev, "f16tc")
     net(to_dev(synth.batch_from_scenes([synth.scene_s1(1234)]), dev))
     af = net.debug_tap("actor_feat", 32 * 128).view(32, 128)
+    lf = net.debug_tap("lane_feat", 129 * 128).view(129, 128)
     torch.cuda.synchronize()
     e = rel_err(af, gold["actor_feat"])
     print("actor_feat (tc, ckpt) rel err %.3e" % e)
+    assert e < 2e-5
+    e = max(rel_err(lf[:128], gold["lane_feat"]), rel_err(lf[128:], gold["tgt_feat"]))
+    print("lane_feat (tc, ckpt) rel err %.3e" % e)
     assert e < 2e-5
     gold = load_golden("ragged_rand.npz")
     net = make_net(rand_sd, dev, "f16tc")
