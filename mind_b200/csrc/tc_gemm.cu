@@ -348,24 +348,38 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
 // optionally also emitted as padded hi/lo (input of the output Res1d) ; last_only extracts t = L-1
 __global__ void __launch_bounds__(256) k_fpn_up_add(const float* __restrict__ prev, const float* __restrict__ lat,
                                                     float* __restrict__ out, __half* hi, __half* lo, int A, int L, int C) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)A * L * C) return;
-    const int c = (int)(idx % C);
-    const int t = (int)((idx / C) % L);
-    const int a = (int)(idx / ((int64_t)C * L));
+    // 4 channels per thread (C % 4 == 0)
+    const int64_t idx4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C4 = C >> 2;
+    if (idx4 >= (int64_t)A * L * C4) return;
+    const int c = (int)(idx4 % C4) * 4;
+    const int t = (int)((idx4 / C4) % L);
+    const int a = (int)(idx4 / ((int64_t)C4 * L));
     const int Lp = L >> 1;
     float src = fmaxf(((float)t + 0.5f) * 0.5f - 0.5f, 0.f);
     const int i0 = (int)floorf(src);
     const int i1 = min(i0 + 1, Lp - 1);
     const float lam = src - (float)i0;
     const float* pp = prev + (int64_t)a * Lp * C;
-    const float y = pp[i0 * C + c] * (1.f - lam) + pp[i1 * C + c] * lam + lat[idx];
-    out[idx] = y;
+    const float4 p0 = *reinterpret_cast<const float4*>(pp + i0 * C + c), p1 = *reinterpret_cast<const float4*>(pp + i1 * C + c);
+    const int64_t idx = ((int64_t)a * L + t) * C + c;
+    const float4 lt = *reinterpret_cast<const float4*>(lat + idx);
+    float y[4] = {p0.x * (1.f - lam) + p1.x * lam + lt.x, p0.y * (1.f - lam) + p1.y * lam + lt.y,
+                  p0.z * (1.f - lam) + p1.z * lam + lt.z, p0.w * (1.f - lam) + p1.w * lam + lt.w};
+    *reinterpret_cast<float4*>(out + idx) = make_float4(y[0], y[1], y[2], y[3]);
     if (hi) {
         const int64_t pidx = ((int64_t)a * (L + 2) + t + 1) * C + c;
-        split_store(hi, lo, pidx, y);
-        if (t == 0) { const int64_t z = ((int64_t)a * (L + 2)) * C + c; hi[z] = __float2half(0.f); lo[z] = __float2half(0.f); }
-        if (t == L - 1) { const int64_t z = ((int64_t)a * (L + 2) + L + 1) * C + c; hi[z] = __float2half(0.f); lo[z] = __float2half(0.f); }
+        const __half2 a01 = __floats2half2_rn(y[0], y[1]), a23 = __floats2half2_rn(y[2], y[3]);
+        const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
+        const __half2 b01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), b23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
+        uint2 uh, ul;
+        uh.x = *reinterpret_cast<const uint32_t*>(&a01); uh.y = *reinterpret_cast<const uint32_t*>(&a23);
+        ul.x = *reinterpret_cast<const uint32_t*>(&b01); ul.y = *reinterpret_cast<const uint32_t*>(&b23);
+        *reinterpret_cast<uint2*>(hi + pidx) = uh;
+        *reinterpret_cast<uint2*>(lo + pidx) = ul;
+        const uint2 z = make_uint2(0u, 0u);
+        if (t == 0) { const int64_t zi = ((int64_t)a * (L + 2)) * C + c; *reinterpret_cast<uint2*>(hi + zi) = z; *reinterpret_cast<uint2*>(lo + zi) = z; }
+        if (t == L - 1) { const int64_t zi = ((int64_t)a * (L + 2) + L + 1) * C + c; *reinterpret_cast<uint2*>(hi + zi) = z; *reinterpret_cast<uint2*>(lo + zi) = z; }
     }
 }
 
@@ -471,7 +485,7 @@ void tcg_gn_apply(const TcApply& q, cudaStream_t st) {
     ++g_launches;
 }
 void tcg_fpn_up_add(const float* prev, const float* lat, float* out, __half* hi, __half* lo, int A, int L, int C, cudaStream_t st) {
-    const int64_t n = (int64_t)A * L * C;
+    const int64_t n = (int64_t)A * L * (C / 4);
     if (n <= 0) return;
     tcg::k_fpn_up_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prev, lat, out, hi, lo, A, L, C);
     ++g_launches;
