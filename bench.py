@@ -358,8 +358,12 @@ def run_native(args):
         flops = B * fusion_flops_per_scene(True)
         ach = flops / per_launch_s / 1e12
         hb = B * fusion_bytes_per_scene(True) / per_launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "fusion_tc_traffic.json")
+        if os.path.exists(tp) and B == 256:                     # dram bytes per launch from the committed ncu --set full capture
+            traffic = json.load(open(tp))["dram_bytes_per_launch"]
         roof = {"kernel": "k_rela_fusion_tc (layers 0-4)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
-                "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + ", sustained bf16/fp16 dense",
+                "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": traffic, "peak_source": pk["src"] + ", sustained bf16/fp16 dense",
                 "ms_per_launch": f_ms / f_n, "launches_timed": f_n,
                 "hbm_algorithmic_gbs": hb, "hbm_frac_of_measured": hb / pk["hbm"],
                 "flops_per_launch": flops, "bytes_per_launch": B * fusion_bytes_per_scene(True)}
