@@ -19,8 +19,11 @@ namespace tcg {
 constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr uint32_t STAGE_A = 16384, STAGE_W = 32768, STAGE = STAGE_A + STAGE_W;
+constexpr uint32_t RES_W_MAX = 98304;          // resident-W mode: W region (96 KB) + 6 A stages of 16 KB
+constexpr int RES_STAGES = 6;
+static_assert(RES_W_MAX + RES_STAGES * STAGE_A <= kStages * STAGE, "resident layout must fit the ring region");
 constexpr uint32_t SM_BAR = kStages * STAGE;
-constexpr uint32_t SM_TMEM = SM_BAR + 128;
+constexpr uint32_t SM_TMEM = SM_BAR + 192;
 constexpr uint32_t SMEM_BYTES = SM_TMEM + 16 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,6 +111,7 @@ struct Args {
     const float* gbias; int gsize, ldg;     // per row-group bias [(row / gsize), N]
     float* stats;
     int* err;
+    int w_resident;            // all W k-blocks fit in smem: loaded once per CTA, A ring of 16 KB stages
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -118,11 +122,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
     const uint32_t bars = sbase + SM_BAR;
-    // full[s] = bars + 8 s ; empty[s] = bars + 32 + 8 s ; tmem_full[a] = bars + 64 + 8 a ; tmem_empty[a] = bars + 80 + 8 a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 32 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bars + 64 + 8 * a, 1); mbar_init(bars + 80 + 8 * a, 4); }
+        // full[s] = bars + 8 s, empty[s] = bars + 64 + 8 s (s < 8), tmem_full[a] = bars + 128 + 8 a,
+        // tmem_empty[a] = bars + 144 + 8 a, W-resident = bars + 160
+        for (int s = 0; s < 8; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 64 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bars + 128 + 8 * a, 1); mbar_init(bars + 144 + 8 * a, 4); }
+        mbar_init(bars + 160, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -136,21 +142,42 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
     const int total_tiles = g.tiles_outer * g.tiles_inner * g.tiles_n;
     const int nq = g.n_terms * g.k_blocks;
 
+    // resident mode: smem = [W: all k-blocks, <= RES_W_MAX][A ring: RES_STAGES x 16 KB]; bar_wres = bars + 96
+    const uint32_t bar_wres = bars + 160;
+    const int nkb_w = g.n_terms == 3 ? 2 * g.k_blocks : g.k_blocks;          // W k-blocks (hi | lo)
+    const uint32_t wblk = (uint32_t)g.n_tile * 128u;                          // bytes of one W k-block
+    const uint32_t res_a0 = sbase + RES_W_MAX;                                // A ring base in resident mode
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % g.tiles_n; const int rest = tile / g.tiles_n;
-                const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
-                for (int q = 0; q < nq; ++q) {
-                    const int term = q / g.k_blocks, kb = q - term * g.k_blocks;
-                    mbar_wait(bars + 32 + 8 * stage, phase ^ 1, g.err, 11);
-                    const uint32_t full = bars + 8 * stage;
-                    mbar_expect_tx(full, STAGE_A + (uint32_t)g.n_tile * 128u);
-                    const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
-                    tma_load_3d(sA, g.a_sel[term] ? &amap1 : &amap0, full, kb * 64, c * g.r_in, o * g.r_out);
-                    tma_load_2d(sW, &wmap, full, g.w_k_off[term] + kb * 64, nt * g.n_tile);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (g.w_resident) {
+                mbar_expect_tx(bar_wres, (uint32_t)nkb_w * wblk);
+                for (int kb = 0; kb < nkb_w; ++kb) tma_load_2d(sbase + kb * wblk, &wmap, bar_wres, kb * 64, 0);
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int c = tile % g.tiles_inner, o = tile / g.tiles_inner;
+                    for (int kb = 0; kb < g.k_blocks; ++kb)
+                        for (int part = 0; part < (g.n_terms == 3 ? 2 : 1); ++part) {     // A_hi[kb], then A_lo[kb]
+                            mbar_wait(bars + 64 + 8 * stage, phase ^ 1, g.err, 11);
+                            const uint32_t full = bars + 8 * stage;
+                            mbar_expect_tx(full, STAGE_A);
+                            tma_load_3d(res_a0 + stage * STAGE_A, part ? &amap1 : &amap0, full, kb * 64, c * g.r_in, o * g.r_out);
+                            if (++stage == RES_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                }
+            } else {
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int nt = tile % g.tiles_n; const int rest = tile / g.tiles_n;
+                    const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
+                    for (int q = 0; q < nq; ++q) {
+                        const int term = q / g.k_blocks, kb = q - term * g.k_blocks;
+                        mbar_wait(bars + 64 + 8 * stage, phase ^ 1, g.err, 11);
+                        const uint32_t full = bars + 8 * stage;
+                        mbar_expect_tx(full, STAGE_A + (uint32_t)g.n_tile * 128u);
+                        const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+                        tma_load_3d(sA, g.a_sel[term] ? &amap1 : &amap0, full, kb * 64, c * g.r_in, o * g.r_out);
+                        tma_load_2d(sW, &wmap, full, g.w_k_off[term] + kb * 64, nt * g.n_tile);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -158,22 +185,52 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             const uint32_t idesc = umma_idesc_f16(g.n_tile);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(bars + 80 + 8 * acc, acc_phase ^ 1, g.err, 12);
-                tc_fence_after();
-                for (int q = 0; q < nq; ++q) {
-                    mbar_wait(bars + 8 * stage, phase, g.err, 13);
+            if (g.w_resident) {
+                mbar_wait(bar_wres, 0, g.err, 15);
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    mbar_wait(bars + 144 + 8 * acc, acc_phase ^ 1, g.err, 12);
                     tc_fence_after();
-                    const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+                    uint32_t first = 1;
+                    for (int kb = 0; kb < g.k_blocks; ++kb)
+                        for (int part = 0; part < (g.n_terms == 3 ? 2 : 1); ++part) {
+                            mbar_wait(bars + 8 * stage, phase, g.err, 13);
+                            tc_fence_after();
+                            const uint32_t sA = res_a0 + stage * STAGE_A;
+                            const uint32_t sWhi = sbase + kb * wblk, sWlo = sbase + (g.k_blocks + kb) * wblk;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sW + kk * 32), idesc,
-                                 (q | kk) != 0);
-                    umma_commit(bars + 32 + 8 * stage);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            for (int kk = 0; kk < 4; ++kk) {       // A_hi: x W_hi and x W_lo ; A_lo: x W_hi
+                                umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sWhi + kk * 32), idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            if (part == 0 && g.n_terms == 3) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sWlo + kk * 32), idesc, 1u);
+                            }
+                            umma_commit(bars + 64 + 8 * stage);
+                            if (++stage == RES_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    umma_commit(bars + 128 + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(bars + 64 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            } else {
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    mbar_wait(bars + 144 + 8 * acc, acc_phase ^ 1, g.err, 12);
+                    tc_fence_after();
+                    for (int q = 0; q < nq; ++q) {
+                        mbar_wait(bars + 8 * stage, phase, g.err, 13);
+                        tc_fence_after();
+                        const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sW + kk * 32), idesc,
+                                     (q | kk) != 0);
+                        umma_commit(bars + 64 + 8 * stage);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bars + 128 + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
             }
         }
     } else {
@@ -189,7 +246,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
             const int64_t orow = (int64_t)outer * g.L_inner + inner;
             float* crow = g.C + orow * g.ldc;
             const float* grow = (g.gbias && valid) ? g.gbias + (orow / g.gsize) * g.ldg : nullptr;
-            mbar_wait(bars + 64 + 8 * acc, acc_phase, g.err, 14);
+            mbar_wait(bars + 128 + 8 * acc, acc_phase, g.err, 14);
             tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
             for (int n0 = 0; n0 < g.n_tile; n0 += 32) {
@@ -225,7 +282,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 80 + 8 * acc);
+            if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
             if (g.stats) {   // per-(outer, inner tile) partial sums; r_in is a power of two <= 32
                 if (!valid) { s1 = 0.f; s2 = 0.f; }
                 for (int off = g.r_in >> 1; off > 0; off >>= 1) {
@@ -457,6 +514,8 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
     g.C = p.C; g.ldc = p.ldc; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
     g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
+    const int nkb_w = (p.split ? 2 : 1) * p.k_blocks;
+    g.w_resident = (g.tiles_n == 1 && (int64_t)nkb_w * p.n_tile * 128 <= (int64_t)tcg::RES_W_MAX) ? 1 : 0;
     const int total = g.tiles_inner * g.tiles_outer * g.tiles_n;
     if (total <= 0) return nullptr;
     CUtensorMap a0, a1, w;
