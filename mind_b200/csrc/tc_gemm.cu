@@ -252,21 +252,37 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
             for (int n0 = 0; n0 < g.n_tile; n0 += 32) {
                 uint32_t r[32];
                 TCG_LD_X32(tmem + lane_base + acc * 256 + n0, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int nb = nt * g.n_tile + n0;
+                // bias / group-bias for the whole 32-column chunk first (vector loads, independent of the TMEM data)
+                float4 bz[8];
 #pragma unroll
                 for (int k4 = 0; k4 < 8; ++k4) {
+                    const int n = nb + k4 * 4;
+                    bz[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (n + 3 < g.N) {
+                        if (g.bias) bz[k4] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                        if (grow) {
+                            const float4 gz = __ldg(reinterpret_cast<const float4*>(grow + n));
+                            bz[k4].x += gz.x; bz[k4].y += gz.y; bz[k4].z += gz.z; bz[k4].w += gz.w;
+                        }
+                    } else {
+                        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < g.N) t4[e] = (g.bias ? __ldg(g.bias + n + e) : 0.f) + (grow ? __ldg(grow + n + e) : 0.f);
+                        bz[k4] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float bb[4] = {bz[k4].x, bz[k4].y, bz[k4].z, bz[k4].w};
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int n = nb + k4 * 4 + e;
-                        float x = __uint_as_float(r[k4 * 4 + e]);
-                        if (n < g.N) {
-                            if (g.bias) x += __ldg(g.bias + n);
-                            if (grow) x += __ldg(grow + n);
-                            if (g.relu) x = fmaxf(x, 0.f);
-                            s1 += x; s2 += x * x;
-                        }
+                        float x = __uint_as_float(r[k4 * 4 + e]) + bb[e];
+                        if (g.relu) x = fmaxf(x, 0.f);
+                        if (n < g.N) { s1 += x; s2 += x * x; }
                         v[e] = x;
                     }
                     if (valid) {
