@@ -40,7 +40,7 @@ int64_t carve(void* ws, int A, Bufs& b) {
     b.o[0] = hl(50 * 32); b.o[1] = hl(26 * 64); b.o[2] = hl(14 * 128); b.o[3] = hl(8 * 256);
     b.p = hl(50 * 128);
     b.raw1 = c.take<float>((int64_t)A * 6144); b.raw2 = c.take<float>((int64_t)A * 6144); b.raw3 = c.take<float>((int64_t)A * 6144);
-    b.st1 = c.take<float>((int64_t)A * 6); b.st2 = c.take<float>((int64_t)A * 6); b.st3 = c.take<float>((int64_t)A * 6);
+    b.st1 = c.take<float>((int64_t)A * 12); b.st2 = c.take<float>((int64_t)A * 12); b.st3 = c.take<float>((int64_t)A * 12);
     b.pyr0 = c.take<float>((int64_t)A * 6144); b.pyr1 = c.take<float>((int64_t)A * 6144);
     b.lat = c.take<float>((int64_t)A * 6144); b.outf = c.take<float>((int64_t)A * 6144);
     return (c.off + 255) & ~int64_t(255);

@@ -17,7 +17,7 @@ namespace mind {
 namespace tcg {
 
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 constexpr uint32_t STAGE_A = 16384, STAGE_W = 32768, STAGE = STAGE_A + STAGE_W;
 constexpr uint32_t RES_W_MAX = 98304;          // resident-W mode: W region (96 KB) + 6 A stages of 16 KB
 constexpr int RES_STAGES = 6;
@@ -127,7 +127,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
         // full[s] = bars + 8 s, empty[s] = bars + 64 + 8 s (s < 8), tmem_full[a] = bars + 128 + 8 a,
         // tmem_empty[a] = bars + 144 + 8 a, W-resident = bars + 160
         for (int s = 0; s < 8; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 64 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bars + 128 + 8 * a, 1); mbar_init(bars + 144 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bars + 128 + 8 * a, 1); mbar_init(bars + 144 + 8 * a, g.n_tile >= 64 ? 8 : 4); }
         mbar_init(bars + 160, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -235,10 +235,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
         }
     } else {
         int acc = 0; uint32_t acc_phase = 0;
-        const int lg = warp & 3;
+        const int lg = warp & 3;                       // TMEM lane quadrant (warp id mod 4)
+        const int chalf = (warp - 2) >> 2;             // warps 2-5: first column half, 6-9: second half
+        const bool split_cols = g.n_tile >= 64;
+        const int col_lo = split_cols ? chalf * (g.n_tile >> 1) : 0;
+        const int col_hi = split_cols ? col_lo + (g.n_tile >> 1) : g.n_tile;
         const int row = lg * 32 + lane;
         const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < total_tiles && (split_cols || chalf == 0); tile += gridDim.x) {
             const int nt = tile % g.tiles_n; const int rest = tile / g.tiles_n;
             const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
             const int outer = o * g.r_out + row / g.r_in, inner = c * g.r_in + row % g.r_in;
@@ -249,7 +253,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
             mbar_wait(bars + 128 + 8 * acc, acc_phase, g.err, 14);
             tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
-            for (int n0 = 0; n0 < g.n_tile; n0 += 32) {
+            for (int n0 = col_lo; n0 < col_hi; n0 += 32) {
                 uint32_t r[32];
                 TCG_LD_X32(tmem + lane_base + acc * 256 + n0, r);
                 const int nb = nt * g.n_tile + n0;
@@ -305,9 +309,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                     s1 += __shfl_xor_sync(0xffffffffu, s1, off);
                     s2 += __shfl_xor_sync(0xffffffffu, s2, off);
                 }
-                if ((row % g.r_in) == 0 && outer < g.n_outer) {
-                    float* sp = g.stats + ((int64_t)outer * g.tiles_inner + c) * 2;
+                if ((row % g.r_in) == 0 && outer < g.n_outer) {   // [outer][inner tile][column half][2]
+                    float* sp = g.stats + (((int64_t)outer * g.tiles_inner + c) * 2 + chalf) * 2;
                     sp[0] = s1; sp[1] = s2;
+                    if (!split_cols) { sp[2] = 0.f; sp[3] = 0.f; }
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -340,7 +345,7 @@ __global__ void k_actor_prep(const float* __restrict__ actors, __half* __restric
 }
 
 // y = GN(raw) (+ GN(res_raw) | + (res_hi+res_lo))  (ReLU)  -> hi/lo padded [A][L+2][C] and / or fp32 [A][L][C]
-// stats: [A][3][2] partial (sum, sum^2) over the actor's C*L outputs (3 inner tiles per actor)
+// stats: [A][3 inner tiles][2 column halves][2] partial (sum, sum^2) over the actor's C*L outputs
 struct ApplyArgs {
     const float* raw; const float* stats; const float* gamma; const float* beta;
     const float* res_raw; const float* res_stats; const float* res_gamma; const float* res_beta;
@@ -353,14 +358,14 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
     __shared__ float sm[4];
     if (threadIdx.x == 0) {
         const float n = (float)(p.L * p.C);
-        const float* s = p.stats + (int64_t)a * 6;
-        const float mean = ((s[0] + s[2]) + s[4]) / n;
-        const float var = fmaxf(((s[1] + s[3]) + s[5]) / n - mean * mean, 0.f);
+        const float* s = p.stats + (int64_t)a * 12;     // 3 inner tiles x 2 column halves x (sum, sum^2), fixed order
+        const float mean = (((s[0] + s[2]) + (s[4] + s[6])) + (s[8] + s[10])) / n;
+        const float var = fmaxf((((s[1] + s[3]) + (s[5] + s[7])) + (s[9] + s[11])) / n - mean * mean, 0.f);
         sm[0] = mean; sm[1] = rsqrtf(var + 1e-5f);
         if (p.res_raw) {
-            const float* r = p.res_stats + (int64_t)a * 6;
-            const float m2 = ((r[0] + r[2]) + r[4]) / n;
-            const float v2 = fmaxf(((r[1] + r[3]) + r[5]) / n - m2 * m2, 0.f);
+            const float* r = p.res_stats + (int64_t)a * 12;
+            const float m2 = (((r[0] + r[2]) + (r[4] + r[6])) + (r[8] + r[10])) / n;
+            const float v2 = fmaxf((((r[1] + r[3]) + (r[5] + r[7])) + (r[9] + r[11])) / n - m2 * m2, 0.f);
             sm[2] = m2; sm[3] = rsqrtf(v2 + 1e-5f);
         }
     }

@@ -19,7 +19,7 @@ struct TcGemm {
     float* C = nullptr; int ldc = 0;
     const float* bias = nullptr; int relu = 0;
     const float* gbias = nullptr; int gsize = 1, ldg = 0;   // per row-group bias [(row / gsize), N]
-    float* stats = nullptr;          // [n_outer][ceil(L_inner / r_in)][2] partial (sum, sum^2) or null
+    float* stats = nullptr;          // [n_outer][ceil(L_inner / r_in)][2 column halves][2] partial (sum, sum^2) or null
     int* err = nullptr;
 };
 
