@@ -103,10 +103,6 @@ class _Level:
     pass
 
 
-def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-
-
 class ScenarioTreeGeneratorB200:
     def __init__(self, device, network, obs_len=50, pred_len=60, config=None):
         self.device = torch.device(device)
@@ -200,6 +196,10 @@ class ScenarioTreeGeneratorB200:
         pos = torch.matmul(tj["TRAJS_POS_OBS"].float(), R.transpose(-1, -2)) + ctrs[:, None]
         vel = torch.matmul(tj["TRAJS_VEL_OBS"].float(), R.transpose(-1, -2))
         ang = torch.atan2(tj["TRAJS_ANG_OBS"][..., 1], tj["TRAJS_ANG_OBS"][..., 0]).float()
+        if pos.shape[0] > 256:
+            raise ValueError("the tree-step kernels support at most 256 actors per scene (got %d)" % pos.shape[0])
+        if pos.shape[1] != self.obs_len:
+            raise ValueError("observation length %d != obs_len %d" % (pos.shape[1], self.obs_len))
         L = _Level()
         L.F, L.Na = 1, pos.shape[0]
         L.hpos = (torch.matmul(pos, rot.T) + orig).contiguous().view(1, L.Na, 50, 2)
