@@ -215,7 +215,8 @@ struct LayerArgs {
     int n_work;
     const float* stq;     // [B*Nmax, 384]
     const float* params;  // [8][128]
-    float* attn;          // [B*Nmax, 128]
+    __half* attn_hi;      // [B*Nmax, 128] attention output as an fp16 (hi, lo) pair: A operand of the out-proj GEMM
+    __half* attn_lo;
     int Nmax;
     int has_edge;
     int* err;
@@ -698,7 +699,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
             }
             if (lg == 0 && lane < 16 && j0 + lane < N) {
-                float* o = a.attn + (tok0 + j0 + lane) * 128 + col0;
+                const int64_t orow = (tok0 + j0 + lane) * 128 + col0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float inv = 1.f / lrun[h];
@@ -706,8 +707,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const int c = h * 16 + k4 * 4;
                         const float4 bv = *reinterpret_cast<const float4*>(Pm + P_BV * 128 + col0 + c);
-                        *reinterpret_cast<float4*>(o + c) = make_float4(acc[c + 0] * inv + bv.x, acc[c + 1] * inv + bv.y,
-                                                                        acc[c + 2] * inv + bv.z, acc[c + 3] * inv + bv.w);
+                        const float y0 = acc[c + 0] * inv + bv.x, y1 = acc[c + 1] * inv + bv.y;
+                        const float y2 = acc[c + 2] * inv + bv.z, y3 = acc[c + 3] * inv + bv.w;
+                        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        uint2 uh, ul;
+                        uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        ul.x = pack_h2(y0 - f01.x, y1 - f01.y); ul.y = pack_h2(y2 - f23.x, y3 - f23.y);
+                        *reinterpret_cast<uint2*>(a.attn_hi + orow + c) = uh;
+                        *reinterpret_cast<uint2*>(a.attn_lo + orow + c) = ul;
                     }
                 }
             }
@@ -938,7 +946,7 @@ const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, in
     return nullptr;
 }
 
-const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, float* attn, int sm_count, cudaStream_t st) {
+const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* attn_hi, __half* attn_lo, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(tc::k_rela_fusion_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
@@ -946,7 +954,7 @@ const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, float* at
         attr = true;
     }
     tc::LayerArgs a;
-    a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn = attn;
+    a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn_hi = attn_hi; a.attn_lo = attn_lo;
     a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err;
     const int grid = std::max(1, std::min(w.n_work, sm_count));
     CUtensorMap em, wm;

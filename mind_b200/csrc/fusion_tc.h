@@ -39,8 +39,8 @@ void tc_free(TcWeights& w);
 // per forward: work list + tensor map over edge16 [B,Nmax,Nmax,128] fp16
 const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, cudaStream_t st);
 // One fused layer over the whole batch: updates edge16 in place (layers 0-4), reads STQ
-// [B*Nmax,384] (S | T | q/4), writes attn [B*Nmax,128] (attention output before out-proj).
-const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, float* attn, int sm_count, cudaStream_t st);
+// [B*Nmax,384] (S | T | q/4), writes the attention output (before out-proj) as an fp16 (hi, lo) pair [B*Nmax,128].
+const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* attn_hi, __half* attn_lo, int sm_count, cudaStream_t st);
 // bring-up self test: D[128,128] = A[128,128] . W[128,128]^T through TMA + tcgen05 + TMEM
 const char* tc_selftest(const float* A_host, const float* W_host, float* D_host);
 

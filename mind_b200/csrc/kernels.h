@@ -28,6 +28,9 @@ void launch_layernorm(const float* x, const float* res, const float* gamma, cons
 void launch_layernorm_hl(const float* x, const float* res, const float* gamma, const float* beta, float* out32, __half* hi,
                          __half* lo, int64_t rows, int relu, cudaStream_t st);
 
+// fp32 -> fp16 (hi, lo) split of n floats (n % 4 == 0)
+void launch_split_hl(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
+
 // max over groups of `g` consecutive rows: in [G*g, D] -> out [G, D]
 void launch_group_max(const float* in, float* out, int64_t G, int g, int D, cudaStream_t st);
 

@@ -72,6 +72,8 @@ struct MindCtx {
     struct LaneW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; const float* bias = nullptr; };
     LaneW lane_tc[2][4];          // per aggregate block: fc1.0, fc1.3, fc2.0[:, :128], fc2.3 as [128][hi 128 | lo 128] fp16
     int* lane_err = nullptr;
+    struct NodeW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; int N = 0, K = 0, n_tile = 128; };
+    NodeW node_tc[6][4];          // per fusion layer: [S|T|q] (384x128), out-proj (128x128), linear1 (256x128), linear2 (128x256)
     // descriptor tables
     SceneDesc* d_sd = nullptr; int sd_cap = 0;
     int32_t* d_actor_scene = nullptr; int as_cap = 0;
@@ -111,6 +113,7 @@ extern "C" void mind_destroy(MindCtx* c) {
     actor_tc_free(c->actor_tc);
     for (auto& blk : c->lane_tc) for (auto& lw : blk) if (lw.W) cudaFree(lw.W);
     if (c->lane_err) cudaFree(c->lane_err);
+    for (auto& lay : c->node_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
     delete c;
 }
 
@@ -339,6 +342,42 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
                 lw.bias = (j == 2) ? nullptr : c->dev_w.at(P + ".bias");
             }
         if (!c->lane_err) { CUDA_OK(cudaMalloc(&c->lane_err, sizeof(int))); CUDA_OK(cudaMemset(c->lane_err, 0, sizeof(int))); }
+        // node-side projections of every fusion layer as [N][hi K | lo K] fp16 operands of the GEMM engine
+        for (int l = 0; l < 6; ++l) {
+            char pfx[96];
+            snprintf(pfx, sizeof pfx, "fusion_net.fuse_scene.fusion.%d.", l);
+            const std::string P(pfx);
+            struct Spec { const std::vector<float>* W; int N, K; float scale_from_row, scale; };
+            auto pack = [&](MindCtx::NodeW& nw, const std::vector<float>& Wsrc, int N, int K, int n_tile) -> const char* {
+                std::vector<__half> Wp((size_t)N * 2 * K);
+                for (int o = 0; o < N; ++o)
+                    for (int k = 0; k < K; ++k) {
+                        const float wv = Wsrc[(size_t)o * K + k];
+                        const __half hh = __float2half_rn(wv);
+                        Wp[(size_t)o * 2 * K + k] = hh;
+                        Wp[(size_t)o * 2 * K + K + k] = __float2half_rn(wv - __half2float(hh));
+                    }
+                if (!nw.W && cudaMalloc(&nw.W, Wp.size() * sizeof(__half)) != cudaSuccess) return "cudaMalloc(node W) failed";
+                if (cudaMemcpy(nw.W, Wp.data(), Wp.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return "copy node W failed";
+                nw.N = N; nw.K = K; nw.n_tile = n_tile;
+                return tcg_encode_w(nw.wmap, nw.W, 2 * K, N, n_tile);
+            };
+            // fused [S | T | q/4] projection: same rows as the fp32 #Wstq pack
+            const std::vector<float>* Wm = find(c, P + "proj_memory.0.weight");
+            const std::vector<float>* Win = find(c, P + "multihead_attn.in_proj_weight");
+            std::vector<float> Wstq((size_t)384 * 128);
+            for (int o = 0; o < 128; ++o)
+                for (int k = 0; k < 128; ++k) {
+                    Wstq[(size_t)o * 128 + k] = (*Wm)[(size_t)o * 384 + 128 + k];
+                    Wstq[(size_t)(128 + o) * 128 + k] = (*Wm)[(size_t)o * 384 + 256 + k];
+                    Wstq[(size_t)(256 + o) * 128 + k] = 0.25f * (*Win)[(size_t)o * 128 + k];
+                }
+            const char* e3;
+            if ((e3 = pack(c->node_tc[l][0], Wstq, 384, 128, 128))) return fail("node pack: %s", e3);
+            if ((e3 = pack(c->node_tc[l][1], *find(c, P + "multihead_attn.out_proj.weight"), 128, 128, 128))) return fail("node pack: %s", e3);
+            if ((e3 = pack(c->node_tc[l][2], *find(c, P + "linear1.weight"), 256, 128, 256))) return fail("node pack: %s", e3);
+            if ((e3 = pack(c->node_tc[l][3], *find(c, P + "linear2.weight"), 128, 256, 128))) return fail("node pack: %s", e3);
+        }
     }
     c->finalized = true;
     return 0;
@@ -374,6 +413,7 @@ struct Ws {
     char* actor_ws;
     __half *lh[3], *ll[3];     // lane-net fp16 hi/lo operand buffers [R,128]
     float* lt32;
+    __half *xh, *xl, *ah, *al, *fh, *fl;   // token state / attention output / FFN hidden as fp16 hi/lo operands
     // decoder
     float *actors_f, *cls_tok, *tr, *tg1, *tgt, *c1, *ce, *qkv, *att, *co, *f1, *f2, *a1, *ae, *embed, *h1, *h2, *param;
     float *k1, *k2, *logit;
@@ -410,12 +450,16 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w
         w.actor_ws = nullptr;
         for (int i = 0; i < 3; ++i) w.lh[i] = w.ll[i] = nullptr;
         w.lt32 = nullptr;
+        w.xh = w.xl = w.ah = w.al = w.fh = w.fl = nullptr;
     } else {
         w.edge = w.tmp = w.memory = w.kv = nullptr;
         w.edge16 = cv.take<__half>((int64_t)B * pairs * 128);
         w.actor_ws = cv.take<char>(actor_tc_ws_bytes(A));
         for (int i = 0; i < 3; ++i) { w.lh[i] = cv.take<__half>(R * 128 + 512); w.ll[i] = cv.take<__half>(R * 128 + 512); }
         w.lt32 = cv.take<float>(R * 128);
+        w.xh = cv.take<__half>(TOK * 128 + 512); w.xl = cv.take<__half>(TOK * 128 + 512);
+        w.ah = cv.take<__half>(TOK * 128 + 512); w.al = cv.take<__half>(TOK * 128 + 512);
+        w.fh = cv.take<__half>(TOK * 256 + 512); w.fl = cv.take<__half>(TOK * 256 + 512);
     }
     w.actors_f = cv.take<float>((int64_t)A * 128);
     w.cls_tok = cv.take<float>((int64_t)B * 128);
@@ -537,6 +581,36 @@ static const char* run_lane_net_tc(MindCtx* c, const Ws& w, int64_t Lp, cudaStre
         }
     }
     return err;
+}
+
+// node-side projections on the tcgen05 GEMM engine (3-term fp16 split): x (fp32 + hi/lo) is the running token state
+static const char* node_tc_gemm(MindCtx* c, const MindCtx::NodeW& nw, const __half* ah, const __half* al, int64_t rows,
+                                const float* bias, int relu, float* C, int ldc, __half* chi, __half* clo, int ldh, cudaStream_t st) {
+    alignas(64) unsigned char mh[128], ml[128];
+    const char* err;
+    if ((err = tcg_encode_a(mh, ah, nw.K, rows, 1, nw.K, rows * nw.K, 128, 1))) return err;
+    if ((err = tcg_encode_a(ml, al, nw.K, rows, 1, nw.K, rows * nw.K, 128, 1))) return err;
+    TcGemm g;
+    g.amap_hi = mh; g.amap_lo = ml; g.wmap = nw.wmap; g.split = 1; g.k_blocks = nw.K / 64;
+    g.r_in = 128; g.r_out = 1; g.L_inner = (int)rows; g.n_outer = 1; g.N = nw.N; g.n_tile = nw.n_tile;
+    g.C = C; g.ldc = ldc; g.Chi = chi; g.Clo = clo; g.ldh = ldh; g.bias = bias; g.relu = relu; g.err = c->lane_err;
+    return tcg_launch(g, c->sm_count, st);
+}
+
+static const char* run_node_pre_tc(MindCtx* c, int l, const Ws& w, int64_t rows, cudaStream_t st) {
+    return node_tc_gemm(c, c->node_tc[l][0], w.xh, w.xl, rows, c->fl[l].bstq, 0, w.stq, 384, nullptr, nullptr, 0, st);
+}
+
+// out-proj, LN2, FFN, LN3 (network.py:178-179,222-232); x fp32 and its hi/lo copy are updated in place
+static const char* run_node_post_tc(MindCtx* c, int l, const Ws& w, int64_t rows, cudaStream_t st) {
+    const FusionLayerW& f = c->fl[l];
+    const char* err;
+    if ((err = node_tc_gemm(c, c->node_tc[l][1], w.ah, w.al, rows, f.bo, 0, w.xo, 128, nullptr, nullptr, 0, st))) return err;
+    launch_layernorm_hl(w.x, w.xo, f.n2_g, f.n2_b, w.x, w.xh, w.xl, rows, 0, st);
+    if ((err = node_tc_gemm(c, c->node_tc[l][2], w.xh, w.xl, rows, f.b1, 1, nullptr, 0, w.fh, w.fl, 256, st))) return err;
+    if ((err = node_tc_gemm(c, c->node_tc[l][3], w.fh, w.fl, rows, f.b2, 0, w.xo, 128, nullptr, nullptr, 0, st))) return err;
+    launch_layernorm_hl(w.x, w.xo, f.n3_g, f.n3_b, w.x, w.xh, w.xl, rows, 0, st);
+    return nullptr;
 }
 
 // node-side tail of a rela-fusion layer on token rows [r0, r0+rows): out-proj, LN2, FFN, LN3
@@ -698,15 +772,18 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     } else {
         launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, st);
         if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, w.edge16, st)) return fail("tc_prepare: %s", perr);
+        const int64_t TOKR = (int64_t)B * Nmax;
+        launch_split_hl(w.x, w.xh, w.xl, TOKR * 128, st);                      // token state as fp16 hi/lo operand
+        CUDA_OK(cudaMemsetAsync(w.ah, 0, sizeof(__half) * (size_t)TOKR * 128, st));   // padded token rows are never written by the fused kernel
+        CUDA_OK(cudaMemsetAsync(w.al, 0, sizeof(__half) * (size_t)TOKR * 128, st));
         PROF_NEXT("edge_init");
         for (int l = 0; l < 6; ++l) {
-            const FusionLayerW& f = c->fl[l];
-            L.gemm(w.x, 128, f.Wstq, 128, f.bstq, w.stq, 384, (int64_t)B * Nmax, 384, 128);
+            if (const char* e = run_node_pre_tc(c, l, w, TOKR, st)) return fail("node_pre_tc(%d): %s", l, e);
             PROF_NEXT("node_pre");
-            const char* err = tc_fusion_layer(c->tc, l, w.stq, w.attn, c->sm_count, st);
+            const char* err = tc_fusion_layer(c->tc, l, w.stq, w.ah, w.al, c->sm_count, st);
             if (err) return fail("tc_fusion_layer(%d): %s", l, err);
             PROF_NEXT(l < 5 ? "fusion_tc" : "fusion_tc_last");
-            run_node_post(c, f, w, 0, (int64_t)B * Nmax, st);
+            if (const char* e = run_node_post_tc(c, l, w, TOKR, st)) return fail("node_post_tc(%d): %s", l, e);
             PROF_NEXT("node_post");
         }
     }

@@ -308,6 +308,27 @@ void launch_layernorm_hl(const float* x, const float* res, const float* gamma, c
     ++g_launches;
 }
 
+// fp32 -> fp16 (hi, lo) operand split
+__global__ void k_split_hl(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+    ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+    reinterpret_cast<uint2*>(hi)[i] = uh;
+    reinterpret_cast<uint2*>(lo)[i] = ul;
+}
+void launch_split_hl(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    const int64_t n4 = n / 4;
+    k_split_hl<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, hi, lo, n4);
+    ++g_launches;
+}
+
 __global__ void k_group_max(const float* __restrict__ in, float* __restrict__ out, int64_t G, int g, int D) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= G * D) return;

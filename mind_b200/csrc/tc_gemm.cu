@@ -107,6 +107,7 @@ struct Args {
     int L_inner, n_outer;
     int N, n_tile;
     float* C; int ldc;
+    __half* Chi; __half* Clo; int ldh;      // optional fp16 (hi, lo) copy of the output (operand of a following GEMM)
     const float* bias; int relu;
     const float* gbias; int gsize, ldg;     // per row-group bias [(row / gsize), N]
     float* stats;
@@ -291,11 +292,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                     }
                     if (valid) {
                         const int n = nb + k4 * 4;
-                        if (n + 3 < g.N && ((g.ldc & 3) == 0)) {
-                            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-                        } else {
+                        if (g.C) {
+                            if (n + 3 < g.N && ((g.ldc & 3) == 0)) {
+                                *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) if (n + e < g.N) crow[n + e] = v[e];
+                                for (int e = 0; e < 4; ++e) if (n + e < g.N) crow[n + e] = v[e];
+                            }
+                        }
+                        if (g.Chi && n + 3 < g.N) {
+                            const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+                            uint2 uh, ul;
+                            uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+                            *reinterpret_cast<uint2*>(g.Chi + orow * g.ldh + n) = uh;
+                            *reinterpret_cast<uint2*>(g.Clo + orow * g.ldh + n) = ul;
                         }
                     }
                 }
@@ -533,7 +546,7 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.tiles_inner = (p.L_inner + p.r_in - 1) / p.r_in;
     g.tiles_outer = (p.n_outer + p.r_out - 1) / p.r_out;
     g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
-    g.C = p.C; g.ldc = p.ldc; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
+    g.C = p.C; g.ldc = p.ldc; g.Chi = p.Chi; g.Clo = p.Clo; g.ldh = p.ldh; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
     g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
     const int nkb_w = (p.split ? 2 : 1) * p.k_blocks;
     g.w_resident = (g.tiles_n == 1 && (int64_t)nkb_w * p.n_tile * 128 <= (int64_t)tcg::RES_W_MAX) ? 1 : 0;

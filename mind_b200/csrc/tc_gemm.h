@@ -17,6 +17,7 @@ struct TcGemm {
     int L_inner = 0, n_outer = 1;    // logical extents; output row = outer * L_inner + inner
     int N = 0, n_tile = 128;
     float* C = nullptr; int ldc = 0;
+    __half* Chi = nullptr; __half* Clo = nullptr; int ldh = 0;   // optional fp16 (hi, lo) copy of the output
     const float* bias = nullptr; int relu = 0;
     const float* gbias = nullptr; int gsize = 1, ldg = 0;   // per row-group bias [(row / gsize), N]
     float* stats = nullptr;          // [n_outer][ceil(L_inner / r_in)][2 column halves][2] partial (sum, sum^2) or null
