@@ -43,3 +43,33 @@ def test_tree_vs_golden(ckpt_sd, v, prec):
     for t in trees:
         for n in t.nodes.values():
             assert n.data[1].dtype.name == "float32" and n.data[1].ndim == 3 and n.data[2].shape[-1] == 1
+
+
+def test_tree_vs_oracle_tree_new_scene(ckpt_sd):
+    """a 10-actor scene that is not among the goldens: CUDA tree (exact fp32 predictor) vs the CPU oracle tree."""
+    from mind_b200 import synth
+    from mind_b200.predictor import ScenePredNetB200
+    from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
+    from oracle.tree_oracle import TreeOracle, flatten_trees
+    from test_tree_oracle import OracleNet
+    import numpy as np
+    scene = dict(x0=(70, 78, 62, 90, 84, 66, 100, 55, 110, 48), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0, 3.5, -3.5),
+                 v=(7, 3, 11, 5, 9, 2, 6, 12, 4, 8))
+    dev = torch.device("cuda", 0)
+    net = ScenePredNetB200(None, dev)
+    net.load_state_dict(ckpt_sd)
+    net.set_precision("fp32")
+    gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, TreeCfg())
+    data, lane, info, graph = synth.scene_s3(**scene)
+    gen.reset(); gen.set_target_lane(lane, info); gen.lane_graph = copy.deepcopy(graph)
+    got = flatten(gen.rollout(data))
+    orc = TreeOracle(OracleNet(ckpt_sd), 50, 50, TreeCfg())
+    data, lane, info, graph = synth.scene_s3(**scene)
+    orc.reset(); orc.set_target_lane(lane, info); orc.lane_graph = copy.deepcopy(graph)
+    want = flatten_trees(orc.rollout(data))
+    assert gen.net_batches == orc.net_batches
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert got[k][0] == want[k][0] and abs(got[k][1] - want[k][1]) < 1e-4
+        assert got[k][2].shape == want[k][2].shape and np.abs(got[k][2] - want[k][2]).max() < 1e-3
+        assert np.abs(got[k][3] - want[k][3]).max() < 1e-3 * max(1.0, np.abs(want[k][3]).max())
