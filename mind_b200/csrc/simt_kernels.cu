@@ -702,46 +702,28 @@ __global__ void __launch_bounds__(256) k_edge_init_h8(const SceneDesc* __restric
                 }
             }
         }
-        // all 8 rows of the unit at once: 8 independent reduction chains keep the shuffle pipe busy
-        float y[8][4], sm[8], sq[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const float r0 = __shfl_sync(0xffffffffu, va, jj), r1 = __shfl_sync(0xffffffffu, va, 8 + jj);
-            const float r2 = __shfl_sync(0xffffffffu, va, 16 + jj), r3 = __shfl_sync(0xffffffffu, va, 24 + jj);
-            const float r4 = __shfl_sync(0xffffffffu, vb, jj);
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                y[jj][e] = fmaf(w[e][4], r4, fmaf(w[e][3], r3, fmaf(w[e][2], r2, fmaf(w[e][1], r1, fmaf(w[e][0], r0, bi[e])))));
-                s += y[jj][e];
-            }
-            sm[jj] = s;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) sm[jj] += __shfl_xor_sync(0xffffffffu, sm[jj], o);
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            sm[jj] *= (1.f / 128.f);
-            float q = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { const float t = y[jj][e] - sm[jj]; q += t * t; }
-            sq[jj] = q;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) sq[jj] += __shfl_xor_sync(0xffffffffu, sq[jj], o);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const int j = j0 + jj;
             if (j >= Nmax) break;
+            const float r0 = __shfl_sync(0xffffffffu, va, jj), r1 = __shfl_sync(0xffffffffu, va, 8 + jj);
+            const float r2 = __shfl_sync(0xffffffffu, va, 16 + jj), r3 = __shfl_sync(0xffffffffu, va, 24 + jj);
+            const float r4 = __shfl_sync(0xffffffffu, vb, jj);
             __half* dst = edge + (((int64_t)b * Nmax + i) * Nmax + j) * 128 + lane * 4;
             if (i >= M || j >= M) { store4(dst, make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
-            const float mean = sm[jj], rstd = rsqrtf(sq[jj] * (1.f / 128.f) + LN_EPS);
-            store4(dst, make_float4(fmaxf((y[jj][0] - mean) * rstd * gm[0] + bt[0], 0.f), fmaxf((y[jj][1] - mean) * rstd * gm[1] + bt[1], 0.f),
-                                    fmaxf((y[jj][2] - mean) * rstd * gm[2] + bt[2], 0.f), fmaxf((y[jj][3] - mean) * rstd * gm[3] + bt[3], 0.f)));
+            float y[4], s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                y[e] = fmaf(w[e][4], r4, fmaf(w[e][3], r3, fmaf(w[e][2], r2, fmaf(w[e][1], r1, fmaf(w[e][0], r0, bi[e])))));
+                s += y[e];
+            }
+            const float mean = warp_sum(s) * (1.f / 128.f);
+            float q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float t = y[e] - mean; q += t * t; }
+            const float rstd = rsqrtf(warp_sum(q) * (1.f / 128.f) + LN_EPS);
+            store4(dst, make_float4(fmaxf((y[0] - mean) * rstd * gm[0] + bt[0], 0.f), fmaxf((y[1] - mean) * rstd * gm[1] + bt[1], 0.f),
+                                    fmaxf((y[2] - mean) * rstd * gm[2] + bt[2], 0.f), fmaxf((y[3] - mean) * rstd * gm[3] + bt[3], 0.f)));
         }
     }
 }
