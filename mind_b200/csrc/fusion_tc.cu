@@ -220,6 +220,7 @@ struct LayerArgs {
     int Nmax;
     int has_edge;
     int* err;
+    float* part;          // partial softmax states of key-split items: [slot][16 j][144]
 };
 
 // TMEM column map (512 columns x 128 lanes, fp32 cells)
@@ -231,17 +232,17 @@ struct LayerArgs {
 // Steady state has no CTA-wide barrier: issuer and epilogue meet only through mbarriers, the four
 // warps that share rows through a named 128-thread barrier.
 struct TileIt {          // walks (work item, key chunk) in the CTA's static schedule
-    int wi, ch, n_chunks, b, j0, n;
+    int wi, ch, ch1, b, j0, n;
 };
 __device__ __forceinline__ bool tile_valid(const TileIt& t, int n_work) { return t.wi < n_work; }
 __device__ __forceinline__ void tile_load_wi(TileIt& t, const TcWork* work, int n_work) {
     if (t.wi < n_work) {
         const TcWork w = work[t.wi];
-        t.b = w.b; t.j0 = w.j0; t.n = w.n; t.n_chunks = (w.n + 7) >> 3; t.ch = 0;
+        t.b = w.b; t.j0 = w.j0; t.n = w.n; t.ch = w.ch0; t.ch1 = w.ch1;
     }
 }
 __device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_work, int stride) {
-    if (++t.ch >= t.n_chunks) { t.wi += stride; tile_load_wi(t, work, n_work); }
+    if (++t.ch >= t.ch1) { t.wi += stride; tile_load_wi(t, work, n_work); }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)      // 17 warps are granted registers as 5 warpgroups -> 96 / thread
@@ -417,7 +418,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         for (int wi = blockIdx.x; wi < a.n_work; wi += stride) {
             const TcWork wk = a.work[wi];
             const int N = wk.n, j0 = wk.j0, b = wk.b;
-            const int n_chunks = (N + 7) >> 3;
+            const int ch0 = wk.ch0, ch1 = wk.ch1;
             const int64_t tok0 = (int64_t)b * a.Nmax;
             {   // S (src term, per query j) and q tiles: 16 x 32 float4 each, one per epilogue thread
                 const int jj = tid >> 5, c4 = tid & 31;
@@ -472,7 +473,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 tc_fence_before();
             };
 
-            for (int ch = 0; ch < n_chunks; ++ch, ++g) {
+            for (int ch = ch0; ch < ch1; ++ch, ++g) {
                 const int i0 = ch * 8;
                 const uint32_t par = g & 1;
                 const uint32_t tX = sbase + SM_TILE0 + (g & 1) * 32768;  // edge tile (in place -> edge')
@@ -549,7 +550,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_a);                 // this warp's slice of the A operand is in TMEM
-                if (ch > 0) attend(par ^ 1, (i0 - 8 + i_l) < N);   // attention epilogue of the previous tile, under the W_pe MMAs
+                if (ch > ch0) attend(par ^ 1, (i0 - 8 + i_l) < N); // attention epilogue of the previous tile, under the W_pe MMAs
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_k);                 // Dk/Dv free: the issuer may run the K|V MMAs of this tile
 
@@ -654,7 +655,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 row_group_sync(lg);                                // statistics buffers can be reused by the next tile
             }
 
-            attend((g - 1) & 1, ((n_chunks - 1) * 8 + i_l) < N);   // attention epilogue of the work item's last tile
+            attend((g - 1) & 1, ((ch1 - 1) * 8 + i_l) < N);        // attention epilogue of the work item's last tile
             // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
             // lanes l and l^16 hold key slots 2*lg and 2*lg+1 of the same query
 #pragma unroll
@@ -698,7 +699,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     }
                 }
             }
-            if (lg == 0 && lane < 16 && j0 + lane < N) {
+            if (wk.slot >= 0) {
+                if (lg == 0 && lane < 16) {                        // key-split item: park the un-normalised state for k_merge_parts
+                    float* d = a.part + ((int64_t)wk.slot * 16 + lane) * 144;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) d[col0 + k] = acc[k];
+                    d[128 + q * 2] = mrun[0]; d[128 + q * 2 + 1] = mrun[1];
+                    d[136 + q * 2] = lrun[0]; d[136 + q * 2 + 1] = lrun[1];
+                }
+            } else if (lg == 0 && lane < 16 && j0 + lane < N) {
                 const int64_t orow = (tok0 + j0 + lane) * 128 + col0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -728,6 +737,32 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge of key-split work items: one CTA (128 threads = channels) per (split item, query)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_merge_parts(const TcMerge* __restrict__ jobs, const float* __restrict__ part,
+                                                     const float* __restrict__ params, __half* __restrict__ attn_hi,
+                                                     __half* __restrict__ attn_lo, int Nmax) {
+    const TcMerge jb = jobs[blockIdx.x >> 4];
+    const int jl = blockIdx.x & 15, c = threadIdx.x, hd = c >> 4;
+    if (jb.j0 + jl >= jb.n) return;
+    float m = -INFINITY;
+    for (int p = 0; p < jb.nparts; ++p) m = fmaxf(m, part[((int64_t)(jb.slot0 + p) * 16 + jl) * 144 + 128 + hd]);
+    float l = 0.f, acc = 0.f;
+    for (int p = 0; p < jb.nparts; ++p) {
+        const float* d = part + ((int64_t)(jb.slot0 + p) * 16 + jl) * 144;
+        const float mp = d[128 + hd];
+        const float w = (mp == -INFINITY) ? 0.f : __expf(mp - m);
+        l += d[136 + hd] * w;
+        acc += d[c] * w;
+    }
+    const float y = acc / l + params[P_BV * 128 + c];
+    const __half hh = __float2half_rn(y);
+    const int64_t o = ((int64_t)jb.b * Nmax + jb.j0 + jl) * 128 + c;
+    attn_hi[o] = hh;
+    attn_lo[o] = __float2half_rn(y - __half2float(hh));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -877,6 +912,9 @@ void tc_free(TcWeights& w) {
         l.Wcat = nullptr; l.params = nullptr;
     }
     if (w.d_work) cudaFree(w.d_work);
+    if (w.d_merge) cudaFree(w.d_merge);
+    if (w.d_part) cudaFree(w.d_part);
+    w.d_merge = nullptr; w.d_part = nullptr; w.merge_cap = w.part_cap = 0;
     if (w.d_err) cudaFree(w.d_err);
     w.d_work = nullptr; w.d_err = nullptr; w.work_cap = 0; w.packed = false;
 }
@@ -926,10 +964,34 @@ const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, in
     std::vector<TcWork> work;
     for (int b = 0; b < B; ++b) {
         const int n = sd[b].n_actor + sd[b].n_lane + 1;
-        for (int j0 = 0; j0 < n; j0 += 16) work.push_back(TcWork{b, j0, n, 0});
+        for (int j0 = 0; j0 < n; j0 += 16) work.push_back(TcWork{b, j0, n, 0, (n + 7) >> 3, -1, 0, 0});
     }
     // longest work items first (static round-robin over persistent CTAs)
     std::stable_sort(work.begin(), work.end(), [](const TcWork& x, const TcWork& y) { return x.n > y.n; });
+    // tail: the items of the last, partially filled round are split along the key axis into parts that keep
+    // every CTA busy; their partial softmax states are merged by k_merge_parts
+    std::vector<TcMerge> merges;
+    int n_slots = 0;
+    const int grid = std::max(1, std::min((int)work.size(), w.sm_count));
+    const int rem = (int)(work.size() % (size_t)grid);
+    if ((int)work.size() > grid && rem > 0 && rem * 2 <= grid) {
+        std::vector<TcWork> tail(work.end() - rem, work.end());
+        work.resize(work.size() - rem);
+        const int per = grid / rem;                                  // parts per leftover item
+        for (const TcWork& t : tail) {
+            const int nch = t.ch1 - t.ch0;
+            const int parts = std::max(1, std::min(per, nch));
+            if (parts == 1) { work.push_back(t); continue; }
+            merges.push_back(TcMerge{t.b, t.j0, t.n, n_slots, parts, 0, 0, 0});
+            for (int p = 0; p < parts; ++p) {
+                TcWork x = t;
+                x.ch0 = t.ch0 + (int)((int64_t)nch * p / parts);
+                x.ch1 = t.ch0 + (int)((int64_t)nch * (p + 1) / parts);
+                x.slot = n_slots++;
+                work.push_back(x);
+            }
+        }
+    }
     if ((int)work.size() > w.work_cap) {
         if (w.d_work) cudaFree(w.d_work);
         if (cudaMalloc(&w.d_work, work.size() * sizeof(TcWork)) != cudaSuccess) return "cudaMalloc(work) failed";
@@ -938,6 +1000,21 @@ const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, in
     if (cudaMemcpyAsync(w.d_work, work.data(), work.size() * sizeof(TcWork), cudaMemcpyHostToDevice, st) != cudaSuccess)
         return "copy work list failed";
     w.n_work = (int)work.size();
+    w.n_merge = (int)merges.size();
+    if (w.n_merge > 0) {
+        if (w.n_merge > w.merge_cap) {
+            if (w.d_merge) cudaFree(w.d_merge);
+            if (cudaMalloc(&w.d_merge, merges.size() * sizeof(TcMerge)) != cudaSuccess) return "cudaMalloc(merge) failed";
+            w.merge_cap = w.n_merge;
+        }
+        if (n_slots > w.part_cap) {
+            if (w.d_part) cudaFree(w.d_part);
+            if (cudaMalloc(&w.d_part, (size_t)n_slots * 16 * 144 * sizeof(float)) != cudaSuccess) return "cudaMalloc(part) failed";
+            w.part_cap = n_slots;
+        }
+        if (cudaMemcpyAsync(w.d_merge, merges.data(), merges.size() * sizeof(TcMerge), cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return "copy merge list failed";
+    }
     if (w.emap_ptr != edge16 || w.emap_B != B || w.emap_N != Nmax) {
         if (const char* e = make_map_edge(w.emap, edge16, B, Nmax)) return e;
         w.emap_ptr = edge16; w.emap_B = B; w.emap_N = Nmax;
@@ -955,13 +1032,17 @@ const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* a
     }
     tc::LayerArgs a;
     a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn_hi = attn_hi; a.attn_lo = attn_lo;
-    a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err;
+    a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err; a.part = w.d_part;
     const int grid = std::max(1, std::min(w.n_work, sm_count));
     CUtensorMap em, wm;
     memcpy(&em, w.emap, sizeof em);
     memcpy(&wm, w.layer[layer].wmap, sizeof wm);
     tc::k_rela_fusion_tc<<<grid, tc::kThreads, tc::SMEM_BYTES, st>>>(em, wm, a);
     ++g_launches;
+    if (w.n_merge > 0) {
+        tc::k_merge_parts<<<w.n_merge * 16, 128, 0, st>>>(w.d_merge, w.d_part, w.layer[layer].params, attn_hi, attn_lo, w.Nmax);
+        ++g_launches;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;

@@ -13,7 +13,10 @@ struct TcHostLayer {
     const float *Win, *bin;                     // MHA in_proj [384,128], [384]
 };
 
-struct TcWork { int32_t b, j0, n, pad; };      // one work item: scene b, queries j0..j0+15, n tokens
+// one work item: scene b, queries j0..j0+15, n tokens, key chunks [ch0, ch1); slot >= 0: this item is one part of a
+// key-split item and parks its un-normalised softmax state in part_buf[slot] instead of writing the attention output
+struct TcWork { int32_t b, j0, n, ch0, ch1, slot, pad0, pad1; };
+struct TcMerge { int32_t b, j0, n, slot0, nparts, pad0, pad1, pad2; };   // merge job of one key-split item
 
 struct TcLayerDev {
     __half* Wcat = nullptr;     // [512][128] fp16 rows: W_e | W_pe | W_k | W_v   (K-major B operands)
@@ -27,10 +30,13 @@ struct TcWeights {
     bool packed = false;
     // per-forward state
     TcWork* d_work = nullptr; int work_cap = 0; int n_work = 0;
+    TcMerge* d_merge = nullptr; int merge_cap = 0; int n_merge = 0;
+    float* d_part = nullptr; int part_cap = 0;          // [slots][16 j][144]: acc[128] | m[8] | l[8]
     int* d_err = nullptr;
     alignas(64) unsigned char emap[128];   // CUtensorMap over the edge stream
     const void* emap_ptr = nullptr; int emap_B = 0, emap_N = 0;
     int B = 0, Nmax = 0;
+    int sm_count = 148;
 };
 
 // all return nullptr on success, else an error string

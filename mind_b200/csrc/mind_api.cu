@@ -99,6 +99,7 @@ extern "C" int mind_create(MindCtx** out, int device) {
     MindCtx* c = new MindCtx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->tc.sm_count = c->sm_count;
     *out = c;
     return 0;
 }
