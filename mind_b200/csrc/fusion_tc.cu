@@ -198,6 +198,34 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     __half2 h = *reinterpret_cast<__half2*>(&u);
     return __half22float2(h);
 }
+// packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of fp32 work)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2 pk2u(uint32_t a, uint32_t b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void upk2u(f2 v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float hsum2(f2 v) { float a, b; upk2(v, a, b); return a + b; }
+// (lo, hi) fp32 -> fp16 pair, lo in the low half; ReLU folded into the conversion
+__device__ __forceinline__ uint32_t cvt_rz_relu_h2(f2 v) {
+    float a, b; upk2(v, a, b); uint32_t d;
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a)); return d;
+}
+__device__ __forceinline__ uint32_t cvt_rn_relu_h2(f2 v) {
+    float a, b; upk2(v, a, b); uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a)); return d;
+}
+__device__ __forceinline__ uint32_t cvt_rn_h2(f2 v) {
+    float a, b; upk2(v, a, b); uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a)); return d;
+}
+__device__ __forceinline__ f2 h2_to_f2(uint32_t u) { const float2 f = unpack_h2(u); return pk2(f.x, f.y); }
+__device__ __forceinline__ void lds_2f2(uint32_t addr, f2& a, f2& b) {     // 4 consecutive floats as two pairs
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -414,6 +442,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         const uint32_t tile_off = (uint32_t)(q >> 1) * 16384u;      // k-block of this quarter inside an edge tile
         const int chunk0 = (q & 1) * 4;                              // first 16-byte chunk of this quarter in its k-block
         const float* Pm = sP;
+        const uint32_t aS = sbase + SM_S, aQ = sbase + SM_Q, aT = sbase + SM_T, aP = sbase + SM_P;
         uint32_t g = 0;                                              // tiles processed by this CTA
         for (int wi = blockIdx.x; wi < a.n_work; wi += stride) {
             const TcWork wk = a.work[wi];
@@ -432,43 +461,55 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = qv;
             }
             asm volatile("bar.sync 5, 512;" ::: "memory");         // epilogue warps only
-            float acc[32], mrun[2], lrun[2];
+            f2 acc2[16];                                           // un-normalised attention accumulators, 2 heads x 16 channels
+            float mrun[2], lrun[2];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+            for (int k = 0; k < 16; ++k) acc2[k] = 0ull;
             mrun[0] = mrun[1] = -INFINITY; lrun[0] = lrun[1] = 0.f;
 
             // ---- epilogue 2b: per-thread online softmax over this thread's key, 2 heads.  Runs one tile late
             // (right after the A operand of the NEXT tile is handed over) so that it overlaps the W_pe MMAs.
+            // The running maximum is only a reference point: it is moved (and the state rescaled) when a score
+            // exceeds it by more than 8, so the common case is one FFMA2 per channel pair.
             auto attend = [&](uint32_t tile_par, bool key_ok) {
                 mbar_wait(bar_m2b, tile_par, a.err, E_MMA2);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t rv[16];
-                    float s = 0.f;
+                    float s;
                     {
                         uint32_t rk[16];
                         TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
                         tmem_wait_ld();
+                        f2 sa = 0ull, sb = 0ull;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            const float4 qq = *reinterpret_cast<const float4*>(sQ + j_l * 132 + col0 + h * 16 + k4 * 4);
-                            s = fmaf(qq.x, __uint_as_float(rk[k4 * 4 + 0]), s);
-                            s = fmaf(qq.y, __uint_as_float(rk[k4 * 4 + 1]), s);
-                            s = fmaf(qq.z, __uint_as_float(rk[k4 * 4 + 2]), s);
-                            s = fmaf(qq.w, __uint_as_float(rk[k4 * 4 + 3]), s);
+                            f2 qa, qb;
+                            lds_2f2(aQ + (uint32_t)(j_l * 132 + col0 + h * 16 + k4 * 4) * 4u, qa, qb);
+                            sa = fma2(qa, pk2u(rk[k4 * 4 + 0], rk[k4 * 4 + 1]), sa);
+                            sb = fma2(qb, pk2u(rk[k4 * 4 + 2], rk[k4 * 4 + 3]), sb);
                         }
+                        s = hsum2(add2(sa, sb));
                     }
                     TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
                     tmem_wait_ld();
-                    if (!key_ok) continue;
-                    const float mnew = fmaxf(mrun[h], s);
-                    const float corr = __expf(mrun[h] - mnew);     // exp(-inf) = 0 on the first key
-                    const float p = __expf(s - mnew);
-                    lrun[h] = lrun[h] * corr + p;
-                    mrun[h] = mnew;
+                    const bool need = key_ok && (s > mrun[h] + 8.f);              // first valid key: mrun = -inf
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float corr = need ? __expf(mrun[h] - s) : 1.f;      // exp(-inf) = 0 on the first key
+                        if (need) mrun[h] = s;
+                        lrun[h] *= corr;
+                        const f2 c2 = pk2(corr, corr);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) acc[h * 16 + k] = fmaf(p, __uint_as_float(rv[k]), acc[h * 16 + k] * corr);
+                        for (int k = 0; k < 8; ++k) acc2[h * 8 + k] = mul2(acc2[h * 8 + k], c2);
+                    }
+                    if (key_ok) {
+                        const float p = __expf(s - mrun[h]);
+                        lrun[h] += p;
+                        const f2 p2 = pk2(p, p);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc2[h * 8 + k] = fma2(p2, pk2u(rv[2 * k], rv[2 * k + 1]), acc2[h * 8 + k]);
+                    }
                 }
                 tc_fence_before();
             };
@@ -486,7 +527,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 // (free until G2 of this tile is issued) so nothing has to live in registers across the barrier
                 const uint32_t scr_t = tmem + lane_base + 128 + col0;
                 {
-                    float s1 = 0.f, s2 = 0.f;
+                    f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         uint32_t r[16];
@@ -495,20 +536,19 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
-                            const float4 sv = *reinterpret_cast<const float4*>(sS + j_l * 132 + c);
-                            const float4 tv = *reinterpret_cast<const float4*>(sT + i_l * 132 + c);
-                            const float x0 = __uint_as_float(r[k4 * 4 + 0]) + sv.x + tv.x;
-                            const float x1 = __uint_as_float(r[k4 * 4 + 1]) + sv.y + tv.y;
-                            const float x2 = __uint_as_float(r[k4 * 4 + 2]) + sv.z + tv.z;
-                            const float x3 = __uint_as_float(r[k4 * 4 + 3]) + sv.w + tv.w;
-                            r[k4 * 4 + 0] = __float_as_uint(x0); r[k4 * 4 + 1] = __float_as_uint(x1);
-                            r[k4 * 4 + 2] = __float_as_uint(x2); r[k4 * 4 + 3] = __float_as_uint(x3);
-                            s1 += (x0 + x1) + (x2 + x3);
-                            s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                            f2 sa, sb, ta, tb;
+                            lds_2f2(aS + (uint32_t)(j_l * 132 + c) * 4u, sa, sb);
+                            lds_2f2(aT + (uint32_t)(i_l * 132 + c) * 4u, ta, tb);
+                            const f2 x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), ta);
+                            const f2 x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tb);
+                            upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
+                            upk2u(x1, r[k4 * 4 + 2], r[k4 * 4 + 3]);
+                            s1a = add2(s1a, x0); s1b = add2(s1b, x1);
+                            s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                         }
                         TMEM_ST_X16(scr_t + hf * 16, r);
                     }
-                    sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                    sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 tc_fence_before();
@@ -520,6 +560,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
+                    const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         uint32_t r[16], hi[8], lo[8];
@@ -528,18 +569,17 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
-                            const float4 gg = *reinterpret_cast<const float4*>(Pm + P_MEM_G * 128 + c);
-                            const float4 be = *reinterpret_cast<const float4*>(Pm + P_MEM_B * 128 + c);
-                            const float y0 = fmaxf((__uint_as_float(r[k4 * 4 + 0]) - mean) * rstd * gg.x + be.x, 0.f);
-                            const float y1 = fmaxf((__uint_as_float(r[k4 * 4 + 1]) - mean) * rstd * gg.y + be.y, 0.f);
-                            const float y2 = fmaxf((__uint_as_float(r[k4 * 4 + 2]) - mean) * rstd * gg.z + be.z, 0.f);
-                            const float y3 = fmaxf((__uint_as_float(r[k4 * 4 + 3]) - mean) * rstd * gg.w + be.w, 0.f);
-                            const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            hi[k4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-                            hi[k4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                            lo[k4 * 2 + 0] = pack_h2(y0 - f01.x, y1 - f01.y);
-                            lo[k4 * 2 + 1] = pack_h2(y2 - f23.x, y3 - f23.y);
+                            f2 ga, gb, ba, bb;
+                            lds_2f2(aP + (uint32_t)(P_MEM_G * 128 + c) * 4u, ga, gb);
+                            lds_2f2(aP + (uint32_t)(P_MEM_B * 128 + c) * 4u, ba, bb);
+                            const f2 y0 = fma2(fma2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), r2, n2), ga, ba);
+                            const f2 y1 = fma2(fma2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), r2, n2), gb, bb);
+                            // hi = ReLU(y) truncated to fp16 (<= y for y >= 0, 0 for y < 0); lo = ReLU(y - hi)
+                            const uint32_t h0 = cvt_rz_relu_h2(y0), h1 = cvt_rz_relu_h2(y1);
+                            hi[k4 * 2 + 0] = h0;
+                            hi[k4 * 2 + 1] = h1;
+                            lo[k4 * 2 + 0] = cvt_rn_relu_h2(sub2(y0, h2_to_f2(h0)));
+                            lo[k4 * 2 + 1] = cvt_rn_relu_h2(sub2(y1, h2_to_f2(h1)));
                         }
                         // K elements [32q + 16hf, +16) -> cells [16q + 8hf, +8) of the hi block and of the lo block
                         TMEM_ST_X8(tmem + lane_base + q * 16 + hf * 8, hi);
@@ -559,7 +599,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     mbar_wait(bar_m2a, par, a.err, E_MMA2);
                     tc_fence_after();
                     {   // pass A: statistics of Dpe + b
-                        float s1 = 0.f, s2 = 0.f;
+                        f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t r[16];
@@ -567,14 +607,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                             tmem_wait_ld();
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
-                                const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + col0 + hf * 16 + k4 * 4);
-                                const float x0 = __uint_as_float(r[k4 * 4 + 0]) + bb.x, x1 = __uint_as_float(r[k4 * 4 + 1]) + bb.y;
-                                const float x2 = __uint_as_float(r[k4 * 4 + 2]) + bb.z, x3 = __uint_as_float(r[k4 * 4 + 3]) + bb.w;
-                                s1 += (x0 + x1) + (x2 + x3);
-                                s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                                f2 ba, bb;
+                                lds_2f2(aP + (uint32_t)(P_BPE * 128 + col0 + hf * 16 + k4 * 4) * 4u, ba, bb);
+                                const f2 x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), ba);
+                                const f2 x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), bb);
+                                s1a = add2(s1a, x0); s1b = add2(s1b, x1);
+                                s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                             }
                         }
-                        sStat[(1 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                        sStat[(1 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                     }
                     row_group_sync(lg);
                     {   // pass B: x = edge + ReLU(LN_p(Dpe + b)) written back to the same cells, statistics of x
@@ -583,7 +624,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
-                        float s1 = 0.f, s2 = 0.f;
+                        const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
+                        f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t r[16];
@@ -593,28 +635,28 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                             for (int c8 = 0; c8 < 2; ++c8) {
                                 const int c = col0 + hf * 16 + c8 * 8;
                                 const uint4 eu = ld_shared_v4(tX + tile_off + sw128(row, chunk0 + hf * 2 + c8));
-                                const float2 e0 = unpack_h2(eu.x), e1 = unpack_h2(eu.y), e2 = unpack_h2(eu.z), e3 = unpack_h2(eu.w);
-                                const float ev[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+                                const uint32_t ev[4] = {eu.x, eu.y, eu.z, eu.w};
 #pragma unroll
                                 for (int h4 = 0; h4 < 2; ++h4) {
-                                    const float4 bb = *reinterpret_cast<const float4*>(Pm + P_BPE * 128 + c + h4 * 4);
-                                    const float4 ga = *reinterpret_cast<const float4*>(Pm + P_PE_G * 128 + c + h4 * 4);
-                                    const float4 ba = *reinterpret_cast<const float4*>(Pm + P_PE_B * 128 + c + h4 * 4);
-                                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, gv[4] = {ga.x, ga.y, ga.z, ga.w}, av[4] = {ba.x, ba.y, ba.z, ba.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const int k = c8 * 8 + h4 * 4 + e;
-                                        const float u = fmaxf((__uint_as_float(r[k]) + bv[e] - mean) * rstd * gv[e] + av[e], 0.f);
-                                        const float x = ev[h4 * 4 + e] + u;
-                                        r[k] = __float_as_uint(x);
-                                        s1 += x;
-                                        s2 += x * x;
-                                    }
+                                    f2 b0, b1, g0, g1, a0, a1;
+                                    lds_2f2(aP + (uint32_t)(P_BPE * 128 + c + h4 * 4) * 4u, b0, b1);
+                                    lds_2f2(aP + (uint32_t)(P_PE_G * 128 + c + h4 * 4) * 4u, g0, g1);
+                                    lds_2f2(aP + (uint32_t)(P_PE_B * 128 + c + h4 * 4) * 4u, a0, a1);
+                                    const int k = c8 * 8 + h4 * 4;
+                                    float u0, u1, u2, u3;
+                                    upk2(fma2(fma2(add2(pk2u(r[k + 0], r[k + 1]), b0), r2, n2), g0, a0), u0, u1);
+                                    upk2(fma2(fma2(add2(pk2u(r[k + 2], r[k + 3]), b1), r2, n2), g1, a1), u2, u3);
+                                    const f2 x0 = add2(h2_to_f2(ev[h4 * 2 + 0]), pk2(fmaxf(u0, 0.f), fmaxf(u1, 0.f)));
+                                    const f2 x1 = add2(h2_to_f2(ev[h4 * 2 + 1]), pk2(fmaxf(u2, 0.f), fmaxf(u3, 0.f)));
+                                    upk2u(x0, r[k + 0], r[k + 1]);
+                                    upk2u(x1, r[k + 2], r[k + 3]);
+                                    s1a = add2(s1a, x0); s1b = add2(s1b, x1);
+                                    s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                                 }
                             }
                             TMEM_ST_X16(scr_t + hf * 16, r);
                         }
-                        sStat[(0 * 4 + q) * 128 + row] = make_float2(s1, s2);
+                        sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
                     row_group_sync(lg);
@@ -624,6 +666,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
+                        const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t r[16];
@@ -632,16 +675,17 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                             for (int c8 = 0; c8 < 2; ++c8) {
                                 const int c = col0 + hf * 16 + c8 * 8;
-                                const float4 ga = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + c);
-                                const float4 gb = *reinterpret_cast<const float4*>(Pm + P_NE_G * 128 + c + 4);
-                                const float4 ba = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + c);
-                                const float4 bb = *reinterpret_cast<const float4*>(Pm + P_NE_B * 128 + c + 4);
+                                f2 g0, g1, g2, g3, b0, b1, b2, b3;
+                                lds_2f2(aP + (uint32_t)(P_NE_G * 128 + c) * 4u, g0, g1);
+                                lds_2f2(aP + (uint32_t)(P_NE_G * 128 + c + 4) * 4u, g2, g3);
+                                lds_2f2(aP + (uint32_t)(P_NE_B * 128 + c) * 4u, b0, b1);
+                                lds_2f2(aP + (uint32_t)(P_NE_B * 128 + c + 4) * 4u, b2, b3);
                                 const uint32_t* x = r + c8 * 8;
                                 uint4 u;
-                                u.x = pack_h2((__uint_as_float(x[0]) - mean) * rstd * ga.x + ba.x, (__uint_as_float(x[1]) - mean) * rstd * ga.y + ba.y);
-                                u.y = pack_h2((__uint_as_float(x[2]) - mean) * rstd * ga.z + ba.z, (__uint_as_float(x[3]) - mean) * rstd * ga.w + ba.w);
-                                u.z = pack_h2((__uint_as_float(x[4]) - mean) * rstd * gb.x + bb.x, (__uint_as_float(x[5]) - mean) * rstd * gb.y + bb.y);
-                                u.w = pack_h2((__uint_as_float(x[6]) - mean) * rstd * gb.z + bb.z, (__uint_as_float(x[7]) - mean) * rstd * gb.w + bb.w);
+                                u.x = cvt_rn_h2(fma2(fma2(pk2u(x[0], x[1]), r2, n2), g0, b0));
+                                u.y = cvt_rn_h2(fma2(fma2(pk2u(x[2], x[3]), r2, n2), g1, b1));
+                                u.z = cvt_rn_h2(fma2(fma2(pk2u(x[4], x[5]), r2, n2), g2, b2));
+                                u.w = cvt_rn_h2(fma2(fma2(pk2u(x[6], x[7]), r2, n2), g3, b3));
                                 st_shared_v4(tX + tile_off + sw128(row, chunk0 + hf * 2 + c8), u);
                             }
                         }
@@ -656,6 +700,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             }
 
             attend((g - 1) & 1, ((ch1 - 1) * 8 + i_l) < N);        // attention epilogue of the work item's last tile
+            float acc[32];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) upk2(acc2[k], acc[2 * k], acc[2 * k + 1]);
             // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
             // lanes l and l^16 hold key slots 2*lg and 2*lg+1 of the same query
 #pragma unroll
