@@ -23,6 +23,7 @@ namespace mind {
 namespace tc {
 
 constexpr int kThreads = 544;   // 16 epilogue warps + 1 issuer warp
+constexpr int kIssuerWarp = 0;  // warps 1..16 are the epilogue warps
 constexpr float kEps = 1e-5f;
 
 // ---- shared memory map (bytes, relative to a 1024-aligned base) ----
@@ -31,8 +32,8 @@ constexpr uint32_t SM_TILE0 = 131072;                 // [2 kblock][128 rows][12
 constexpr uint32_t SM_TILE1 = SM_TILE0 + 32768;
 constexpr uint32_t SM_S = SM_TILE1 + 32768;           // float [16][132]
 constexpr uint32_t SM_Q = SM_S + 16 * 132 * 4;        // float [16][132]
-constexpr uint32_t SM_T = SM_Q + 16 * 132 * 4;        // float [8][132]
-constexpr uint32_t SM_P = SM_T + 8 * 132 * 4;         // float [8][128] layer params
+constexpr uint32_t SM_T = SM_Q + 16 * 132 * 4;        // float [8][128], written by TMA (dense rows)
+constexpr uint32_t SM_P = SM_T + 8 * 128 * 4;         // float [8][128] layer params
 constexpr uint32_t SM_STAT = SM_P + 8 * 128 * 4;      // float2 [2 buf][4 quarter][128]
 constexpr uint32_t SM_BAR = SM_STAT + 2 * 4 * 128 * 8;
 constexpr uint32_t SM_TMEM = SM_BAR + 96;   // 10 mbarriers
@@ -74,6 +75,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+// non-suspending poll (mbarrier.test_wait): for the issuer's hand-off waits, where the time between the last arrival
+// and the first MMA is on the critical path of every tile
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity, int* err, int code) {
+    uint32_t n = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if (++n > 400000000u) {
             if (err) atomicExch(err, code);
             __threadfence_system();
             __trap();
@@ -150,6 +174,23 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
         : "r"(taddr)                                                                                             \
         : "memory")
+// same load without the compiler-level memory clobber: ordering against the matching wait comes from both being
+// volatile, ordering of the consumers from the wait naming the destination registers as in/out operands, so plain
+// shared-memory loads (parameters, S/T/q rows) may be scheduled across the TMEM round trip
+#define TMEM_LD_X16_NM(taddr, r)                                                                                 \
+    asm volatile(                                                                                                \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
+        : "r"(taddr))
+#define TMEM_WAIT_LD_R16(r)                                                                                      \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                \
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]))
+#define TMEM_PIN_R16(r)                                                                                          \
+    asm volatile(""                                                                                              \
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]))
 #define TMEM_ST_X32(taddr, r)                                                                                      \
     asm volatile(                                                                                                  \
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "                                                           \
@@ -181,6 +222,12 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// epilogue -> issuer hand-offs go through hardware named barriers (16 epilogue warps arrive, the issuer warp syncs):
+// an mbarrier poll from the issuer warp queues behind the shared-memory / TMEM traffic of the epilogue warps on its
+// scheduler (measured 1000-2900 cycles from the last arrival to the first MMA), a named barrier wakes it directly
+constexpr int kBarA = 6, kBarK = 7, kBarE = 8;
+__device__ __forceinline__ void handoff_arrive(int id) { asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void handoff_sync(int id) { asm volatile("bar.sync %0, 544;" ::"r"(id) : "memory"); }
 // barrier among the 4 warps (128 threads) that share the same 32 pair rows (same TMEM lane quadrant)
 __device__ __forceinline__ void row_group_sync(int lg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory"); }
 
@@ -223,8 +270,9 @@ __device__ __forceinline__ uint32_t cvt_rn_h2(f2 v) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a)); return d;
 }
 __device__ __forceinline__ f2 h2_to_f2(uint32_t u) { const float2 f = unpack_h2(u); return pk2(f.x, f.y); }
-__device__ __forceinline__ void lds_2f2(uint32_t addr, f2& a, f2& b) {     // 4 consecutive floats as two pairs
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+__device__ __forceinline__ void lds_2f2(const float* p, f2& a, f2& b) {     // 4 consecutive floats as two pairs
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    a = v.x; b = v.y;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -234,6 +282,29 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// optional timeline trace (build with -DMIND_TRACE -> libmind_b200_trace.so): CTA 0 records clock64()
+// at the hand-off points of tiles [kTraceG0, kTraceG0 + kTraceTiles); read back with mind_trace_read
+// ---------------------------------------------------------------------------------------------
+#ifdef MIND_TRACE
+constexpr int kTraceG0 = 40, kTraceTiles = 8, kTracePts = 32;
+__device__ long long g_trace[kTraceTiles * 17 * kTracePts];
+#define TR(id, gg)                                                                                        \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && a.has_edge && (threadIdx.x & 31) == 0 && (int)(gg) >= kTraceG0 && (int)(gg) < kTraceG0 + kTraceTiles) \
+            g_trace[(((int)(gg) - kTraceG0) * 17 + (((threadIdx.x >> 5) + 16) % 17)) * kTracePts + (id)] = clock64();  \
+    } while (0)
+#elif defined(MIND_PROGRESS)
+// deadlock finder: every warp posts (tile << 8 | point) into a mapped host array that survives a trapped launch
+__device__ volatile int* g_progress;
+#define TR(id, gg)                                                                                        \
+    do {                                                                                                  \
+        if ((threadIdx.x & 31) == 0) g_progress[blockIdx.x * 17 + (threadIdx.x >> 5)] = ((int)(gg) << 8) | (id); \
+    } while (0)
+#else
+#define TR(id, gg) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // the fused layer kernel
@@ -274,7 +345,8 @@ __device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_w
 }
 
 __global__ void __launch_bounds__(kThreads, 1)      // 17 warps are granted registers as 5 warpgroups -> 96 / thread
-k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap, LayerArgs a) {
+k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap,
+                 const __grid_constant__ CUtensorMap tmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));   // generic pointer to the aligned base
@@ -295,7 +367,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         mbar_init(bar_a, 16); mbar_init(bar_e, 16); mbar_init(bar_t, 1); mbar_init(bar_k, 16);
         fence_barrier_init();
     }
-    if (warp == 16) {
+    if (warp == kIssuerWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_TMEM), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -306,7 +378,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     const uint32_t tmem = *sTmem;
     const int stride = gridDim.x;
 
-    if (warp == 16) {
+    if (warp == kIssuerWarp) {
         // =============================== issuer warp ===============================
         if (lane == 0) {   // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
             mbar_expect_tx(bar_w, 131072u);
@@ -321,24 +393,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             tma_load_4d(dst, &emap, bl, 0, t.j0, t.ch * 8, t.b);
             tma_load_4d(dst + 16384, &emap, bl, 64, t.j0, t.ch * 8, t.b);
         };
-        float4 tpre[8];                                            // T rows of the NEXT tile, prefetched into registers
-        auto fetch_T = [&](const TileIt& t) {                     // whole warp: issue the global loads only
-            const int64_t tok0 = (int64_t)t.b * a.Nmax;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int idx = it * 32 + lane, ii = idx >> 5, c4 = idx & 31;
-                tpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t.ch * 8 + ii < t.n) tpre[it] = reinterpret_cast<const float4*>(a.stq + (tok0 + t.ch * 8 + ii) * 384 + 128)[c4];
-            }
-        };
-        auto publish_T = [&]() {                                  // whole warp: registers -> sT, then signal
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int idx = it * 32 + lane, ii = idx >> 5, c4 = idx & 31;
-                *reinterpret_cast<float4*>(sT + ii * 132 + c4 * 4) = tpre[it];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_t);
+        // T rows (tar term, per key i) of a tile: one TMA box [128 floats x 8 token rows] out of stq[:, 128:256).  Rows of
+        // padding tokens (i >= n) carry finite values and are masked in the softmax; rows past the tensor are zero-filled.
+        auto load_T = [&](const TileIt& t) {                      // lane 0 only
+            mbar_expect_tx(bar_t, 4096u);
+            tma_load_2d(sbase + SM_T, &tmap, bar_t, 128, t.b * a.Nmax + t.ch * 8);
         };
         auto issue_g1 = [&](int buf) {                            // lane 0 only
             const uint32_t tX = sbase + SM_TILE0 + buf * 32768, id128 = umma_idesc_f16(128);
@@ -360,9 +419,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 load_tile(cur_t, 0);
                 if (tile_valid(nxt, a.n_work)) load_tile(nxt, 1);
             }
-            fetch_T(cur_t);
-            publish_T();
             if (lane == 0) {
+                load_T(cur_t);
                 mbar_wait(bar_ld0, 0, a.err, E_LOAD_EDGE);
                 tc_fence_after();
                 issue_g1(0);
@@ -371,12 +429,13 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 const int buf = g & 1;
                 const uint32_t par = g & 1;
                 const bool has_next = tile_valid(nxt, a.n_work);
-                if (has_next) fetch_T(nxt);                       // global loads in flight while we wait for the A operand
+                // [A] A operand of this tile is in TMEM -> G2 (W_pe first: its epilogue overlaps the K|V MMAs)
+                TR(15, g);
+                handoff_sync(kBarA);
+                TR(16, g);
                 if (lane == 0) {
-                    // [A] A operand of this tile is in TMEM -> G2 (W_pe first: its epilogue overlaps the K|V MMAs)
-                    mbar_wait(bar_a, par, a.err, E_MMA2);
                     tc_fence_after();
-                    const uint32_t id128 = umma_idesc_f16(128), id256 = umma_idesc_f16(256);
+                    const uint32_t id128 = umma_idesc_f16(128);
                     if (a.has_edge) {
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk) {
@@ -387,8 +446,13 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         }
                     }
                     umma_commit(bar_m2a);
-                    mbar_wait(bar_k, par, a.err, E_MMA2 + 2);      // Dk/Dv of the previous tile have been consumed
+                }
+                TR(17, g);
+                handoff_sync(kBarK);                               // Dk/Dv of the previous tile have been consumed
+                TR(18, g);
+                if (lane == 0) {
                     tc_fence_after();
+                    const uint32_t id256 = umma_idesc_f16(256);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
@@ -397,23 +461,23 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         umma_f16_ts(tmem + 256, tmem + 64 + kk * 8, bd, id256, 1);
                     }
                     umma_commit(bar_m2b);
-                }
-                __syncwarp();
-                // [B] next tile: T rows (every epilogue warp is past epilogue 1 of this tile), then G1 behind G2
-                if (has_next) {
-                    if (lane == 0) {
+                    TR(19, g);
+                    // [B] next tile: T rows (every epilogue warp is past epilogue 1 of this tile), then G1 behind G2
+                    if (has_next) {
+                        load_T(nxt);
                         mbar_wait(bar_ld0 + 8 * (buf ^ 1), ((g + 1) >> 1) & 1, a.err, E_LOAD_EDGE);
+                        TR(20, g);
                         tc_fence_after();
                         issue_g1(buf ^ 1);
+                        TR(21, g);
                     }
-                    __syncwarp();
-                    publish_T();                                   // every epilogue warp is past epilogue 1 of this tile (bar_a)
                 }
                 // [C] edge' tile complete -> TMA store ; [D] buffer free -> load the tile after next
                 TileIt nn = nxt;
                 if (has_next) tile_next(nn, a.work, a.n_work, stride);
+                handoff_sync(kBarE);
+                TR(22, g);
                 if (lane == 0) {
-                    mbar_wait(bar_e, par, a.err, E_MMA2 + 1);
                     if (a.has_edge) {
                         const uint32_t tX = sbase + SM_TILE0 + buf * 32768;
                         tma_store_4d(&emap, tX, 0, cur_t.j0, cur_t.ch * 8, cur_t.b);
@@ -425,7 +489,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         load_tile(nn, buf);
                     }
                 }
-                __syncwarp();
                 if (!has_next) break;
                 cur_t = nxt; nxt = nn; ++g;
             }
@@ -433,8 +496,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         }
     } else {
         // =============================== epilogue warps ===============================
-        const int q = warp >> 2;                     // column quarter: channels [32q, 32q+32)
-        const int lg = warp & 3;
+        const int ew = warp - 1;                     // epilogue warp index 0..15
+        const int q = ew >> 2;                       // column quarter: channels [32q, 32q+32)
+        const int lg = warp & 3;                     // TMEM lane quadrant is fixed by the hardware warp id
         const int row = lg * 32 + lane;              // TMEM lane = pair row inside the tile
         const int i_l = row >> 4, j_l = row & 15;
         const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
@@ -450,7 +514,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             const int ch0 = wk.ch0, ch1 = wk.ch1;
             const int64_t tok0 = (int64_t)b * a.Nmax;
             {   // S (src term, per query j) and q tiles: 16 x 32 float4 each, one per epilogue thread
-                const int jj = tid >> 5, c4 = tid & 31;
+                const int jj = ew, c4 = tid & 31;
                 float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), qv = sv;
                 if (j0 + jj < N) {
                     const float* p = a.stq + (tok0 + j0 + jj) * 384;
@@ -460,7 +524,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 *reinterpret_cast<float4*>(sS + jj * 132 + c4 * 4) = sv;
                 *reinterpret_cast<float4*>(sQ + jj * 132 + c4 * 4) = qv;
             }
+            TR(24, g);
             asm volatile("bar.sync 5, 512;" ::: "memory");         // epilogue warps only
+            TR(25, g);
             f2 acc2[16];                                           // un-normalised attention accumulators, 2 heads x 16 channels
             float mrun[2], lrun[2];
 #pragma unroll
@@ -473,6 +539,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             // exceeds it by more than 8, so the common case is one FFMA2 per channel pair.
             auto attend = [&](uint32_t tile_par, bool key_ok) {
                 mbar_wait(bar_m2b, tile_par, a.err, E_MMA2);
+                TR(5, g);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -480,20 +547,20 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     float s;
                     {
                         uint32_t rk[16];
-                        TMEM_LD_X16(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
-                        tmem_wait_ld();
+                        TMEM_LD_X16_NM(tmem + lane_base + 256 + col0 + h * 16, rk);   // warp-collective: no lane guard
+                        TMEM_LD_X16_NM(tmem + lane_base + 384 + col0 + h * 16, rv);
+                        TMEM_WAIT_LD_R16(rk);
+                        TMEM_PIN_R16(rv);
                         f2 sa = 0ull, sb = 0ull;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             f2 qa, qb;
-                            lds_2f2(aQ + (uint32_t)(j_l * 132 + col0 + h * 16 + k4 * 4) * 4u, qa, qb);
+                            lds_2f2(sQ + (j_l * 132 + col0 + h * 16 + k4 * 4), qa, qb);
                             sa = fma2(qa, pk2u(rk[k4 * 4 + 0], rk[k4 * 4 + 1]), sa);
                             sb = fma2(qb, pk2u(rk[k4 * 4 + 2], rk[k4 * 4 + 3]), sb);
                         }
                         s = hsum2(add2(sa, sb));
                     }
-                    TMEM_LD_X16(tmem + lane_base + 384 + col0 + h * 16, rv);
-                    tmem_wait_ld();
                     const bool need = key_ok && (s > mrun[h] + 8.f);              // first valid key: mrun = -inf
                     if (__any_sync(0xffffffffu, need)) {
                         const float corr = need ? __expf(mrun[h] - s) : 1.f;      // exp(-inf) = 0 on the first key
@@ -518,8 +585,10 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 const int i0 = ch * 8;
                 const uint32_t par = g & 1;
                 const uint32_t tX = sbase + SM_TILE0 + (g & 1) * 32768;  // edge tile (in place -> edge')
+                TR(0, g);
                 mbar_wait(bar_t, par, a.err, E_LOAD_EDGE + 10);          // T rows staged by the issuer
                 mbar_wait(bar_m1, par, a.err, E_MMA1);
+                TR(1, g);
                 tc_fence_after();
 
                 // ---- epilogue 1: memory = ReLU(LN(D1 + S[j] + T[i])) -> fp16 (hi, lo) A operand in TMEM ----
@@ -528,17 +597,20 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 const uint32_t scr_t = tmem + lane_base + 128 + col0;
                 {
                     f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
+                    uint32_t rr[2][16];
+                    TMEM_LD_X16_NM(tmem + lane_base + col0, rr[0]);
+                    TMEM_LD_X16_NM(tmem + lane_base + col0 + 16, rr[1]);
+                    TMEM_WAIT_LD_R16(rr[0]);
+                    TMEM_PIN_R16(rr[1]);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t r[16];
-                        TMEM_LD_X16(tmem + lane_base + col0 + hf * 16, r);
-                        tmem_wait_ld();
+                        uint32_t (&r)[16] = rr[hf];
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
                             f2 sa, sb, ta, tb;
-                            lds_2f2(aS + (uint32_t)(j_l * 132 + c) * 4u, sa, sb);
-                            lds_2f2(aT + (uint32_t)(i_l * 132 + c) * 4u, ta, tb);
+                            lds_2f2(sS + (j_l * 132 + c), sa, sb);
+                            lds_2f2(sT + (i_l * 128 + c), ta, tb);
                             const f2 x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), ta);
                             const f2 x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tb);
                             upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
@@ -552,7 +624,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 tc_fence_before();
+                TR(2, g);
                 row_group_sync(lg);                                // statistics exchanged, D1 reads of these lanes retired
+                TR(3, g);
                 tc_fence_after();
                 {
                     const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
@@ -561,17 +635,21 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
                     const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
+                    uint32_t rr[2][16];
+                    TMEM_LD_X16_NM(scr_t, rr[0]);
+                    TMEM_LD_X16_NM(scr_t + 16, rr[1]);
+                    TMEM_WAIT_LD_R16(rr[0]);
+                    TMEM_PIN_R16(rr[1]);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t r[16], hi[8], lo[8];
-                        TMEM_LD_X16(scr_t + hf * 16, r);
-                        tmem_wait_ld();
+                        uint32_t (&r)[16] = rr[hf];
+                        uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
                             f2 ga, gb, ba, bb;
-                            lds_2f2(aP + (uint32_t)(P_MEM_G * 128 + c) * 4u, ga, gb);
-                            lds_2f2(aP + (uint32_t)(P_MEM_B * 128 + c) * 4u, ba, bb);
+                            lds_2f2(sP + (P_MEM_G * 128 + c), ga, gb);
+                            lds_2f2(sP + (P_MEM_B * 128 + c), ba, bb);
                             const f2 y0 = fma2(fma2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), r2, n2), ga, ba);
                             const f2 y1 = fma2(fma2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), r2, n2), gb, bb);
                             // hi = ReLU(y) truncated to fp16 (<= y for y >= 0, 0 for y < 0); lo = ReLU(y - hi)
@@ -588,27 +666,32 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a);                 // this warp's slice of the A operand is in TMEM
+                TR(4, g);
+                handoff_arrive(kBarA);                             // this warp's slice of the A operand is in TMEM
+                TR(13, g);
                 if (ch > ch0) attend(par ^ 1, (i0 - 8 + i_l) < N); // attention epilogue of the previous tile, under the W_pe MMAs
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_k);                 // Dk/Dv free: the issuer may run the K|V MMAs of this tile
+                TR(6, g);
+                handoff_arrive(kBarK);                             // Dk/Dv free: the issuer may run the K|V MMAs of this tile
 
                 // ---- epilogue 2a: edge' = LN_e(edge + ReLU(LN_p(Dpe + b_pe))) in place ----
                 if (a.has_edge) {
                     mbar_wait(bar_m2a, par, a.err, E_MMA2);
+                    TR(7, g);
                     tc_fence_after();
                     {   // pass A: statistics of Dpe + b
                         f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
+                        uint32_t rr[2][16];
+                        TMEM_LD_X16_NM(scr_t, rr[0]);
+                        TMEM_LD_X16_NM(scr_t + 16, rr[1]);
+                        TMEM_WAIT_LD_R16(rr[0]);
+                        TMEM_PIN_R16(rr[1]);
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t r[16];
-                            TMEM_LD_X16(scr_t + hf * 16, r);
-                            tmem_wait_ld();
+                            uint32_t (&r)[16] = rr[hf];
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
                                 f2 ba, bb;
-                                lds_2f2(aP + (uint32_t)(P_BPE * 128 + col0 + hf * 16 + k4 * 4) * 4u, ba, bb);
+                                lds_2f2(sP + (P_BPE * 128 + col0 + hf * 16 + k4 * 4), ba, bb);
                                 const f2 x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), ba);
                                 const f2 x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), bb);
                                 s1a = add2(s1a, x0); s1b = add2(s1b, x1);
@@ -617,7 +700,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         }
                         sStat[(1 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                     }
+                    TR(8, g);
                     row_group_sync(lg);
+                    TR(9, g);
                     {   // pass B: x = edge + ReLU(LN_p(Dpe + b)) written back to the same cells, statistics of x
                         const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
                         const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
@@ -626,11 +711,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float rstd = rsqrtf(var + kEps);
                         const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
                         f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
+                        uint32_t rr[2][16];
+                        TMEM_LD_X16_NM(scr_t, rr[0]);
+                        TMEM_LD_X16_NM(scr_t + 16, rr[1]);
+                        TMEM_WAIT_LD_R16(rr[0]);
+                        TMEM_PIN_R16(rr[1]);
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t r[16];
-                            TMEM_LD_X16(scr_t + hf * 16, r);
-                            tmem_wait_ld();
+                            uint32_t (&r)[16] = rr[hf];
 #pragma unroll
                             for (int c8 = 0; c8 < 2; ++c8) {
                                 const int c = col0 + hf * 16 + c8 * 8;
@@ -639,9 +727,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                                 for (int h4 = 0; h4 < 2; ++h4) {
                                     f2 b0, b1, g0, g1, a0, a1;
-                                    lds_2f2(aP + (uint32_t)(P_BPE * 128 + c + h4 * 4) * 4u, b0, b1);
-                                    lds_2f2(aP + (uint32_t)(P_PE_G * 128 + c + h4 * 4) * 4u, g0, g1);
-                                    lds_2f2(aP + (uint32_t)(P_PE_B * 128 + c + h4 * 4) * 4u, a0, a1);
+                                    lds_2f2(sP + (P_BPE * 128 + c + h4 * 4), b0, b1);
+                                    lds_2f2(sP + (P_PE_G * 128 + c + h4 * 4), g0, g1);
+                                    lds_2f2(sP + (P_PE_B * 128 + c + h4 * 4), a0, a1);
                                     const int k = c8 * 8 + h4 * 4;
                                     float u0, u1, u2, u3;
                                     upk2(fma2(fma2(add2(pk2u(r[k + 0], r[k + 1]), b0), r2, n2), g0, a0), u0, u1);
@@ -659,7 +747,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
+                    TR(10, g);
                     row_group_sync(lg);
+                    TR(11, g);
                     {   // pass C: edge' = LN_e(x) -> fp16, in place in the smem tile
                         const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
                         const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
@@ -667,19 +757,22 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
                         const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
+                        uint32_t rr[2][16];
+                        TMEM_LD_X16_NM(scr_t, rr[0]);
+                        TMEM_LD_X16_NM(scr_t + 16, rr[1]);
+                        TMEM_WAIT_LD_R16(rr[0]);
+                        TMEM_PIN_R16(rr[1]);
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t r[16];
-                            TMEM_LD_X16(scr_t + hf * 16, r);
-                            tmem_wait_ld();
+                            uint32_t (&r)[16] = rr[hf];
 #pragma unroll
                             for (int c8 = 0; c8 < 2; ++c8) {
                                 const int c = col0 + hf * 16 + c8 * 8;
                                 f2 g0, g1, g2, g3, b0, b1, b2, b3;
-                                lds_2f2(aP + (uint32_t)(P_NE_G * 128 + c) * 4u, g0, g1);
-                                lds_2f2(aP + (uint32_t)(P_NE_G * 128 + c + 4) * 4u, g2, g3);
-                                lds_2f2(aP + (uint32_t)(P_NE_B * 128 + c) * 4u, b0, b1);
-                                lds_2f2(aP + (uint32_t)(P_NE_B * 128 + c + 4) * 4u, b2, b3);
+                                lds_2f2(sP + (P_NE_G * 128 + c), g0, g1);
+                                lds_2f2(sP + (P_NE_G * 128 + c + 4), g2, g3);
+                                lds_2f2(sP + (P_NE_B * 128 + c), b0, b1);
+                                lds_2f2(sP + (P_NE_B * 128 + c + 4), b2, b3);
                                 const uint32_t* x = r + c8 * 8;
                                 uint4 u;
                                 u.x = cvt_rn_h2(fma2(fma2(pk2u(x[0], x[1]), r2, n2), g0, b0));
@@ -693,13 +786,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
 
                 if (a.has_edge) fence_proxy_async();               // edge' (generic stores) -> visible to the TMA store
+                else mbar_wait(bar_m2a, par, a.err, E_MMA2);       // keeps every warp within one tile of the issuer (named barrier kBarE)
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_e);                 // tile done: edge' in smem, all TMEM reads retired
+                TR(12, g);
+                handoff_arrive(kBarE);                             // tile done: edge' in smem, all TMEM reads retired
                 row_group_sync(lg);                                // statistics buffers can be reused by the next tile
             }
 
             attend((g - 1) & 1, ((ch1 - 1) * 8 + i_l) < N);        // attention epilogue of the work item's last tile
+            TR(26, g);
             float acc[32];
 #pragma unroll
             for (int k = 0; k < 16; ++k) upk2(acc2[k], acc[2 * k], acc[2 * k + 1]);
@@ -775,13 +870,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     }
                 }
             }
+            TR(27, g);
             asm volatile("bar.sync 5, 512;" ::: "memory");         // scratch consumed before the next S|q tiles are written
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == kIssuerWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
@@ -937,6 +1033,19 @@ const char* make_map_2d(void* out, const void* base, int rows) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? nullptr : tcfail("cuTensorMapEncodeTiled(2d)", (int)r);
 }
+// 2-D fp32 token tensor stq [rows][384] (S | T | q), box [128 floats][8 rows], no swizzle
+const char* make_map_stq(void* out, const void* base, int64_t rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+    cuuint64_t dims[2] = {384, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {384 * 4};
+    cuuint32_t box[2] = {128, 8};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : tcfail("cuTensorMapEncodeTiled(stq)", (int)r);
+}
 // 4-D fp16 edge stream [B][N(i)][N(j)][128], box [64 c][16 j][8 i][1]
 const char* make_map_edge(void* out, const void* base, int B, int N) {
     PFN_encodeTiled enc = get_encode();
@@ -962,7 +1071,8 @@ void tc_free(TcWeights& w) {
     if (w.d_merge) cudaFree(w.d_merge);
     if (w.d_part) cudaFree(w.d_part);
     w.d_merge = nullptr; w.d_part = nullptr; w.merge_cap = w.part_cap = 0;
-    if (w.d_err) cudaFree(w.d_err);
+    if (w.h_err) cudaFreeHost((void*)w.h_err);
+    w.h_err = nullptr;
     w.d_work = nullptr; w.d_err = nullptr; w.work_cap = 0; w.packed = false;
 }
 
@@ -999,8 +1109,10 @@ const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]) {
         if (const char* e = make_map_2d(d.wmap, d.Wcat, 512)) return e;
     }
     if (!w.d_err) {
-        if (cudaMalloc(&w.d_err, sizeof(int)) != cudaSuccess) return "cudaMalloc(err) failed";
-        cudaMemset(w.d_err, 0, sizeof(int));
+        // mapped host word: the code of a trapped launch stays readable after the context is gone
+        if (cudaHostAlloc((void**)&w.h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return "cudaHostAlloc(err) failed";
+        *w.h_err = 0;
+        if (cudaHostGetDevicePointer((void**)&w.d_err, (void*)w.h_err, 0) != cudaSuccess) return "cudaHostGetDevicePointer(err) failed";
     }
     w.packed = true;
     return nullptr;
@@ -1081,10 +1193,15 @@ const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* a
     a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn_hi = attn_hi; a.attn_lo = attn_lo;
     a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err; a.part = w.d_part;
     const int grid = std::max(1, std::min(w.n_work, sm_count));
-    CUtensorMap em, wm;
+    if (w.tmap_ptr != stq || w.tmap_rows != (int64_t)w.B * w.Nmax) {
+        if (const char* e = make_map_stq(w.tmap, stq, (int64_t)w.B * w.Nmax)) return e;
+        w.tmap_ptr = stq; w.tmap_rows = (int64_t)w.B * w.Nmax;
+    }
+    CUtensorMap em, wm, tm;
     memcpy(&em, w.emap, sizeof em);
     memcpy(&wm, w.layer[layer].wmap, sizeof wm);
-    tc::k_rela_fusion_tc<<<grid, tc::kThreads, tc::SMEM_BYTES, st>>>(em, wm, a);
+    memcpy(&tm, w.tmap, sizeof tm);
+    tc::k_rela_fusion_tc<<<grid, tc::kThreads, tc::SMEM_BYTES, st>>>(em, wm, tm, a);
     ++g_launches;
     if (w.n_merge > 0) {
         tc::k_merge_parts<<<w.n_merge * 16, 128, 0, st>>>(w.d_merge, w.d_part, w.layer[layer].params, attn_hi, attn_lo, w.Nmax);
@@ -1094,6 +1211,32 @@ const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* a
     if (e != cudaSuccess) return cudaGetErrorString(e);
     return nullptr;
 }
+
+#ifdef MIND_PROGRESS
+static volatile int* h_progress = nullptr;
+extern "C" int mind_progress_init() {
+    if (h_progress) return 0;
+    if (cudaHostAlloc((void**)&h_progress, 148 * 17 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return -1;
+    for (int i = 0; i < 148 * 17; ++i) h_progress[i] = -1;
+    int* d = nullptr;
+    if (cudaHostGetDevicePointer((void**)&d, (void*)h_progress, 0) != cudaSuccess) return -2;
+    return cudaMemcpyToSymbol(tc::g_progress, &d, sizeof d) == cudaSuccess ? 0 : -3;
+}
+extern "C" int mind_progress_read(int* out, int capacity) {
+    if (!h_progress || capacity < 148 * 17) return -1;
+    for (int i = 0; i < 148 * 17; ++i) out[i] = h_progress[i];
+    return 148 * 17;
+}
+#endif
+
+#ifdef MIND_TRACE
+extern "C" int mind_trace_read(long long* host, int capacity) {
+    const int n = tc::kTraceTiles * 17 * tc::kTracePts;
+    if (capacity < n) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(long long) * n) == cudaSuccess ? n : -2;
+}
+#endif
 
 const char* tc_selftest(const float* A_host, const float* W_host, float* D_host) {
     __half *dA = nullptr, *dW = nullptr;

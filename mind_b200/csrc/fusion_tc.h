@@ -32,9 +32,12 @@ struct TcWeights {
     TcWork* d_work = nullptr; int work_cap = 0; int n_work = 0;
     TcMerge* d_merge = nullptr; int merge_cap = 0; int n_merge = 0;
     float* d_part = nullptr; int part_cap = 0;          // [slots][16 j][144]: acc[128] | m[8] | l[8]
-    int* d_err = nullptr;
+    int* d_err = nullptr;                  // device alias of h_err
+    volatile int* h_err = nullptr;         // mapped host word: protocol error code of a trapped launch
     alignas(64) unsigned char emap[128];   // CUtensorMap over the edge stream
     const void* emap_ptr = nullptr; int emap_B = 0, emap_N = 0;
+    alignas(64) unsigned char tmap[128];   // CUtensorMap over stq (fp32 [B*Nmax, 384]): T rows of a tile
+    const void* tmap_ptr = nullptr; int64_t tmap_rows = 0;
     int B = 0, Nmax = 0;
     int sm_count = 148;
 };

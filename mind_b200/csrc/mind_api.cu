@@ -826,7 +826,7 @@ extern "C" int mind_sync_check(MindCtx* c) {
     if (!c) return fail("mind_sync_check: null ctx");
     cudaError_t e = cudaDeviceSynchronize();
     int code = 0;
-    if (c->tc.d_err) cudaMemcpy(&code, c->tc.d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (c->tc.h_err) code = *c->tc.h_err;
     if (e != cudaSuccess) return fail("device error: %s (kernel code %d)", cudaGetErrorString(e), code);
     if (code) return fail("kernel reported protocol error code %d", code);
     return 0;

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmind_b200.so")
+LIB_PATH = os.environ.get("MIND_B200_LIB") or os.path.join(_HERE, "libmind_b200.so")   # override: development builds only
 
 PREC_FP32 = 0
 PREC_F16TC = 1
