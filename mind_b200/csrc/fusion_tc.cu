@@ -220,6 +220,16 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// one elected lane of a converged warp.  Single-thread work of the issuer warp (tcgen05.mma, TMA, commits) is guarded
+// by this rather than by `lane == 0`: behind a data-dependent lane test the compiler wraps every UTCHMMA / UTMA
+// instruction in an ELECT / BRA.U.ANY serialisation loop (~7 dependent instructions, ~100 cycles per MMA measured),
+// behind elect.sync it emits them back to back.  The leader is deterministic for a given mask, so commits and bulk
+// groups always belong to the thread that issued the work.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // epilogue -> issuer hand-offs go through hardware named barriers (16 epilogue warps arrive, the issuer warp syncs):
@@ -271,6 +281,9 @@ __device__ __forceinline__ uint32_t cvt_rn_h2(f2 v) {
 }
 __device__ __forceinline__ f2 h2_to_f2(uint32_t u) { const float2 f = unpack_h2(u); return pk2(f.x, f.y); }
 __device__ __forceinline__ void lds_2f2(const float* p, f2& a, f2& b) {     // 4 consecutive floats as two pairs
+#ifdef MIND_EXP_NOLDS      // timing experiment only (wrong results): how much do the epilogue's LDS cost / slow the MMAs?
+    a = b = 0x3f8000003f800000ull; return;
+#endif
     const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
     a = v.x; b = v.y;
 }
@@ -380,7 +393,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 
     if (warp == kIssuerWarp) {
         // =============================== issuer warp ===============================
-        if (lane == 0) {   // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
+        if (elect_one()) {   // weights: 8 boxes of [128 rows x 64 k] -> SM_W[kblock][row]
             mbar_expect_tx(bar_w, 131072u);
             for (int kb = 0; kb < 2; ++kb)
                 for (int m = 0; m < 4; ++m) tma_load_2d(sbase + SM_W + kb * 65536 + m * 16384, &wmap, bar_w, kb * 64, m * 128);
@@ -415,11 +428,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             TileIt nxt = cur_t;
             tile_next(nxt, a.work, a.n_work, stride);
             uint32_t g = 0;                                       // tiles processed by this CTA
-            if (lane == 0) {
+            if (elect_one()) {
                 load_tile(cur_t, 0);
                 if (tile_valid(nxt, a.n_work)) load_tile(nxt, 1);
             }
-            if (lane == 0) {
+            if (elect_one()) {
                 load_T(cur_t);
                 mbar_wait(bar_ld0, 0, a.err, E_LOAD_EDGE);
                 tc_fence_after();
@@ -433,7 +446,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 TR(15, g);
                 handoff_sync(kBarA);
                 TR(16, g);
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
                     const uint32_t id128 = umma_idesc_f16(128);
                     if (a.has_edge) {
@@ -450,15 +463,20 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 TR(17, g);
                 handoff_sync(kBarK);                               // Dk/Dv of the previous tile have been consumed
                 TR(18, g);
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
-                    const uint32_t id256 = umma_idesc_f16(256);
+                    // K and V as two N=128 groups: with the A operand in TMEM an N=256 MMA measured ~170 cycles against
+                    // ~60 for N=128 (timeline trace), so 32 narrow MMAs finish well before 16 wide ones
+                    const uint32_t id128 = umma_idesc_f16(128);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
-                        const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + 256 * 128);
-                        umma_f16_ts(tmem + 256, tmem + kk * 8, bd, id256, kk > 0);
-                        umma_f16_ts(tmem + 256, tmem + 64 + kk * 8, bd, id256, 1);
+                    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint32_t kw = (uint32_t)(kk >> 2) * 65536u + (uint32_t)(kk & 3) * 32u;
+                            const uint64_t bd = umma_desc_sw128(sbase + SM_W + kw + (256 + 128 * m) * 128);
+                            umma_f16_ts(tmem + 256 + 128 * m, tmem + kk * 8, bd, id128, kk > 0);
+                            umma_f16_ts(tmem + 256 + 128 * m, tmem + 64 + kk * 8, bd, id128, 1);
+                        }
                     }
                     umma_commit(bar_m2b);
                     TR(19, g);
@@ -477,7 +495,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 if (has_next) tile_next(nn, a.work, a.n_work, stride);
                 handoff_sync(kBarE);
                 TR(22, g);
-                if (lane == 0) {
+                if (elect_one()) {
                     if (a.has_edge) {
                         const uint32_t tX = sbase + SM_TILE0 + buf * 32768;
                         tma_store_4d(&emap, tX, 0, cur_t.j0, cur_t.ch * 8, cur_t.b);
@@ -492,7 +510,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 if (!has_next) break;
                 cur_t = nxt; nxt = nn; ++g;
             }
-            if (lane == 0) tma_wait_all0();
+            if (elect_one()) tma_wait_all0();
         }
     } else {
         // =============================== epilogue warps ===============================
