@@ -296,7 +296,8 @@ def run_native(args):
 
         def mark(x):                                            # inputs are consumed on the compute stream
             if isinstance(x, torch.Tensor):
-                x.record_stream(comp_s)
+                if x.is_cuda:                                   # the index lists stay on the host
+                    x.record_stream(comp_s)
             elif isinstance(x, (list, tuple)):
                 for v in x:
                     mark(v)
@@ -305,14 +306,19 @@ def run_native(args):
                     mark(v)
         mark(staged[slot])
 
+    host_ms = {"upload": 0.0, "forward": 0.0, "download": 0.0}   # host wall time spent enqueueing each phase
+
     def run_e2e(n_steps):
         upload(0)
         for i in range(n_steps):
             slot = i & 1
+            t0 = time.perf_counter()
             if i + 1 < n_steps:
                 upload(slot ^ 1)
+            t1 = time.perf_counter()
             comp_s.wait_event(ev_in[slot])
             cls, reg, aux = net(staged[slot])                   # the call scenario_tree.py:71 makes
+            t2 = time.perf_counter()
             pk = net._last_packed
             if world > 1:
                 for g, x in zip(gather_bufs, pk[:3]):
@@ -327,11 +333,17 @@ def run_native(args):
                 ev_done[slot].record(copy_s)
             for t in pk[:3]:
                 t.record_stream(copy_s)
+            t3 = time.perf_counter()
+            host_ms["upload"] += (t1 - t0) * 1e3
+            host_ms["forward"] += (t2 - t1) * 1e3
+            host_ms["download"] += (t3 - t2) * 1e3
         comp_s.wait_stream(copy_s)
     run_e2e(max(3, args.warmup))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    for k in host_ms:
+        host_ms[k] = 0.0
     e0.record()
     run_e2e(args.steps)
     e1.record()
@@ -379,7 +391,8 @@ def run_native(args):
                        "collective": "all_gather(cls,reg,vel) per step" if world > 1 else "none",
                        "weights": "reference checkpoint 20240121-172745"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms2 / args.steps},
+                    "ms_per_step": ms2 / args.steps,
+                    "host_enqueue_ms_per_step": {k: round(v / args.steps, 3) for k, v in host_ms.items()}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "stage_ms_per_step": stage_ms,

@@ -105,6 +105,18 @@ int64_t mind_workspace_bytes(MindCtx* ctx, int32_t n_scenes, int32_t sum_actors,
 int mind_forward(MindCtx* ctx, const MindBatch* batch, const MindOutputs* out, void* workspace,
                  int64_t workspace_bytes, void* cuda_stream);
 
+/* ---- batched host->device staging:  gpu(data[...])   planners/mind/utils.py:9-20, network.py:597-606 ----
+ * The reference moves every per-scene tensor with its own .cuda() call (3 per scene: ACTOR_IDCS, LANE_IDCS,
+ * RPE['scene']); at 256 scenes that is ~770 framework calls per step and the host becomes the bottleneck.
+ * mind_upload_packed enqueues n host->device copies (host_ptrs[i], bytes[i]) into ONE caller-owned device
+ * buffer in a single library call; copy i lands at dev_dst + offsets_out[i] (offsets are 256-byte aligned,
+ * assigned in order; offsets_out is a HOST array of n entries).  Pinned sources copy asynchronously on
+ * cuda_stream, pageable ones as the CUDA runtime stages them.  mind_upload_packed_bytes returns the
+ * capacity needed for a given size list. */
+int64_t mind_upload_packed_bytes(const int64_t* bytes, int32_t n);
+int mind_upload_packed(const void* const* host_ptrs, const int64_t* bytes, int32_t n, void* dev_dst,
+                       int64_t dst_capacity, int64_t* offsets_out, void* cuda_stream);
+
 /* debug taps used by the stage-level parity tests: copy an internal stage buffer of the LAST
  * forward (still in the workspace) to a device buffer.  names: "actor_feat" [sumNa,128],
  * "lane_feat" [sumNl+B,128] (tgt polylines last), "actors_fused" [sumNa,128],

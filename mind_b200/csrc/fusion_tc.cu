@@ -1136,7 +1136,7 @@ const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]) {
     return nullptr;
 }
 
-const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, cudaStream_t st) {
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, HostStage& stage, cudaStream_t st) {
     if (!w.packed) return "weights not packed";
     std::vector<TcWork> work;
     for (int b = 0; b < B; ++b) {
@@ -1174,8 +1174,7 @@ const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, in
         if (cudaMalloc(&w.d_work, work.size() * sizeof(TcWork)) != cudaSuccess) return "cudaMalloc(work) failed";
         w.work_cap = (int)work.size();
     }
-    if (cudaMemcpyAsync(w.d_work, work.data(), work.size() * sizeof(TcWork), cudaMemcpyHostToDevice, st) != cudaSuccess)
-        return "copy work list failed";
+    if (const char* e = stage.upload(w.d_work, work.data(), work.size() * sizeof(TcWork), st)) return e;
     w.n_work = (int)work.size();
     w.n_merge = (int)merges.size();
     if (w.n_merge > 0) {
@@ -1189,8 +1188,7 @@ const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, in
             if (cudaMalloc(&w.d_part, (size_t)n_slots * 16 * 144 * sizeof(float)) != cudaSuccess) return "cudaMalloc(part) failed";
             w.part_cap = n_slots;
         }
-        if (cudaMemcpyAsync(w.d_merge, merges.data(), merges.size() * sizeof(TcMerge), cudaMemcpyHostToDevice, st) != cudaSuccess)
-            return "copy merge list failed";
+        if (const char* e = stage.upload(w.d_merge, merges.data(), merges.size() * sizeof(TcMerge), st)) return e;
     }
     if (w.emap_ptr != edge16 || w.emap_B != B || w.emap_N != Nmax) {
         if (const char* e = make_map_edge(w.emap, edge16, B, Nmax)) return e;

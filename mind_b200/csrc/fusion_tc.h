@@ -46,7 +46,7 @@ struct TcWeights {
 const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]);
 void tc_free(TcWeights& w);
 // per forward: work list + tensor map over edge16 [B,Nmax,Nmax,128] fp16
-const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, cudaStream_t st);
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, HostStage& stage, cudaStream_t st);
 // One fused layer over the whole batch: updates edge16 in place (layers 0-4), reads STQ
 // [B*Nmax,384] (S | T | q/4), writes the attention output (before out-proj) as an fp16 (hi, lo) pair [B*Nmax,128].
 const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* attn_hi, __half* attn_lo, int sm_count, cudaStream_t st);

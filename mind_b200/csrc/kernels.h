@@ -9,6 +9,21 @@ namespace mind {
 // running launch counter (bench.py gpu_launches)
 extern int64_t g_launches;
 
+// Pinned host staging for the small per-forward descriptor tables.  cudaMemcpyAsync from pageable memory stalls the
+// host until the stream reaches the copy once a table exceeds the driver's staging threshold (the 90 KB work list of
+// a 256-scene batch did: the serving loop lost its two-deep pipelining); from this ring every upload is truly
+// asynchronous.  One slot per in-flight forward; a slot is recycled after its event has completed.
+struct HostStage {
+    static constexpr int kSlots = 4;
+    struct Slot { char* host = nullptr; size_t cap = 0, used = 0; cudaEvent_t done = nullptr; bool pending = false; };
+    Slot slot[kSlots];
+    int cur = 0;
+    const char* begin();                                                        // next slot (waits only if 4 forwards are in flight)
+    const char* upload(void* dev_dst, const void* src, size_t bytes, cudaStream_t st);
+    void end(cudaStream_t st);                                                  // records the slot's event
+    void release();
+};
+
 struct GemmArgs {
     const float* A = nullptr; int lda = 0;      // [M,K]
     const float* W = nullptr; int ldw = 0;      // [N,K] (torch Linear layout), row stride ldw

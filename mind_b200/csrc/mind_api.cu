@@ -54,8 +54,53 @@ struct Profiler {
 #define PROF_BEGIN() cudaEvent_t pb_ = c->prof.on ? c->prof.begin(st) : nullptr
 #define PROF_NEXT(tag) do { if (c->prof.on) { c->prof.end(tag, pb_, st); pb_ = c->prof.begin(st); } } while (0)
 
+const char* HostStage::begin() {
+    cur = (cur + 1) % kSlots;
+    Slot& s = slot[cur];
+    if (!s.done && cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return "cudaEventCreate(stage) failed";
+    if (s.pending) {
+        if (cudaEventSynchronize(s.done) != cudaSuccess) return "cudaEventSynchronize(stage) failed";
+        s.pending = false;
+    }
+    s.used = 0;
+    return nullptr;
+}
+const char* HostStage::upload(void* dev_dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return nullptr;
+    Slot& s = slot[cur];
+    const size_t at = (s.used + 255) & ~(size_t)255;
+    if (at + bytes > s.cap) {                          // grow: earlier copies out of the old block must have executed first
+        const size_t ncap = std::max<size_t>((at + bytes) * 2, 1 << 20);
+        char* nh = nullptr;
+        if (cudaHostAlloc((void**)&nh, ncap, cudaHostAllocDefault) != cudaSuccess) return "cudaHostAlloc(stage) failed";
+        if (s.host) {
+            if (s.used > 0 && cudaStreamSynchronize(st) != cudaSuccess) return "cudaStreamSynchronize(stage) failed";
+            cudaFreeHost(s.host);
+        }
+        s.host = nh; s.cap = ncap; s.used = 0;
+        return upload(dev_dst, src, bytes, st);
+    }
+    memcpy(s.host + at, src, bytes);
+    s.used = at + bytes;
+    if (cudaMemcpyAsync(dev_dst, s.host + at, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return "cudaMemcpyAsync(stage) failed";
+    return nullptr;
+}
+void HostStage::end(cudaStream_t st) {
+    Slot& s = slot[cur];
+    if (s.done && cudaEventRecord(s.done, st) == cudaSuccess) s.pending = true;
+}
+void HostStage::release() {
+    for (Slot& s : slot) {
+        if (s.pending) cudaEventSynchronize(s.done);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.host) cudaFreeHost(s.host);
+        s = Slot{};
+    }
+}
+
 struct MindCtx {
     Profiler prof;
+    HostStage stage;
     int device = 0;
     std::map<std::string, std::vector<float>> host_w;
     float* arena = nullptr;
@@ -107,6 +152,7 @@ extern "C" int mind_create(MindCtx** out, int device) {
 extern "C" void mind_destroy(MindCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    c->stage.release();
     if (c->arena) cudaFree(c->arena);
     if (c->d_sd) cudaFree(c->d_sd);
     if (c->d_actor_scene) cudaFree(c->d_actor_scene);
@@ -715,8 +761,9 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         CUDA_OK(cudaMalloc(&c->d_actor_scene, sizeof(int32_t) * (size_t)A));
         c->as_cap = A;
     }
-    CUDA_OK(cudaMemcpyAsync(c->d_sd, sd.data(), sizeof(SceneDesc) * (size_t)B, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(c->d_actor_scene, actor_scene.data(), sizeof(int32_t) * (size_t)A, cudaMemcpyHostToDevice, st));
+    if (const char* e = c->stage.begin()) return fail("mind_forward: %s", e);
+    if (const char* e = c->stage.upload(c->d_sd, sd.data(), sizeof(SceneDesc) * (size_t)B, st)) return fail("mind_forward: %s", e);
+    if (const char* e = c->stage.upload(c->d_actor_scene, actor_scene.data(), sizeof(int32_t) * (size_t)A, st)) return fail("mind_forward: %s", e);
 
     Lin L{c, st};
     PROF_BEGIN();
@@ -772,7 +819,7 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         }
     } else {
         launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, st);
-        if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, w.edge16, st)) return fail("tc_prepare: %s", perr);
+        if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, w.edge16, c->stage, st)) return fail("tc_prepare: %s", perr);
         const int64_t TOKR = (int64_t)B * Nmax;
         launch_split_hl(w.x, w.xh, w.xl, TOKR * 128, st);                      // token state as fp16 hi/lo operand
         CUDA_OK(cudaMemsetAsync(w.ah, 0, sizeof(__half) * (size_t)TOKR * 128, st));   // padded token rows are never written by the fused kernel
@@ -794,6 +841,7 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     run_decoder(c, w, bt, out, B, A, tgt_feat, st);
     PROF_NEXT("decoder");
     if (c->prof.on && pb_) c->prof.pool.push_back(pb_);
+    c->stage.end(st);
     CUDA_OK(cudaGetLastError());
     c->taps.clear();
     c->taps["actor_feat"] = {w.actor_feat, (int64_t)A * 128};
@@ -818,6 +866,33 @@ extern "C" int64_t mind_debug_tap(MindCtx* c, const char* name, float* dst, int6
 extern "C" int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host) {
     const char* e = tc_selftest(A_host, W_host, D_host);
     if (e) return fail("tc_selftest: %s", e);
+    return 0;
+}
+
+// ---- batched host->device staging (reference: gpu(), planners/mind/utils.py:9-20) ----
+extern "C" int64_t mind_upload_packed_bytes(const int64_t* bytes, int32_t n) {
+    if (!bytes || n < 0) return -1;
+    int64_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        if (bytes[i] < 0) return -1;
+        off += (bytes[i] + 255) & ~(int64_t)255;
+    }
+    return off;
+}
+extern "C" int mind_upload_packed(const void* const* host_ptrs, const int64_t* bytes, int32_t n, void* dev_dst,
+                                  int64_t dst_capacity, int64_t* offsets_out, void* cuda_stream) {
+    if (n < 0 || (n > 0 && (!host_ptrs || !bytes || !dev_dst || !offsets_out))) return fail("mind_upload_packed: bad argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int64_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        if (bytes[i] < 0 || (bytes[i] > 0 && !host_ptrs[i])) return fail("mind_upload_packed: bad entry %d", i);
+        if (off + bytes[i] > dst_capacity) return fail("mind_upload_packed: destination too small (%lld needed at entry %d)",
+                                                       (long long)(off + bytes[i]), i);
+        offsets_out[i] = off;
+        if (bytes[i] > 0)
+            CUDA_OK(cudaMemcpyAsync((char*)dev_dst + off, host_ptrs[i], (size_t)bytes[i], cudaMemcpyHostToDevice, st));
+        off += (bytes[i] + 255) & ~(int64_t)255;
+    }
     return 0;
 }
 

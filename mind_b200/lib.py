@@ -49,7 +49,7 @@ class MindTreeUpdate(C.Structure):
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
-           "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check", "mind_profile_read",
+           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check", "mind_profile_read",
            "mind_tree_level", "mind_tree_update", "mind_tree_last_error"]
 
 _lib = None
@@ -82,6 +82,11 @@ def load(build_if_missing: bool = True):
     lib.mind_forward.argtypes = [C.c_void_p, C.POINTER(MindBatch), C.POINTER(MindOutputs), C.c_void_p,
                                  C.c_int64, C.c_void_p]
     lib.mind_forward.restype = C.c_int
+    lib.mind_upload_packed_bytes.argtypes = [C.POINTER(C.c_int64), C.c_int32]
+    lib.mind_upload_packed_bytes.restype = C.c_int64
+    lib.mind_upload_packed.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_int64,
+                                       C.POINTER(C.c_int64), C.c_void_p]
+    lib.mind_upload_packed.restype = C.c_int
     lib.mind_debug_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mind_debug_tap.restype = C.c_int64
     lib.mind_launch_count.argtypes = [C.c_void_p]

@@ -44,6 +44,15 @@ def _to_device(data, device):
     return data
 
 
+class _PackedRPE(list):
+    """data['RPE'] after pre_process: the usual list of {'scene': [5,M,M] device tensor, 'scene_mask': None}, whose
+    'scene' tensors are views into ONE device buffer filled by a single mind_upload_packed call.  forward_packed
+    reads the device pointers from `ptrs` instead of touching the per-scene tensors."""
+    base = None      # the packed device buffer (uint8)
+    ptrs = None      # ctypes array of per-scene device pointers
+    shapes = None    # per-scene (5, M, M)
+
+
 class ScenePredNetB200:
     def __init__(self, cfg: Optional[dict], device):
         self.device = torch.device(device)
@@ -127,8 +136,48 @@ class ScenePredNetB200:
 
     # ---- reference network.py:597-606 ----
     def pre_process(self, data):
-        keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
-        return tuple(_to_device(data[k], self.device) for k in keys)
+        """Host -> device staging of the 7 network inputs.  Same result structure as the reference, different
+        mechanics: the per-scene RPE tensors travel in one batched library call into one device buffer
+        (mind_upload_packed), and the index lists (only their lengths are used by this network) stay on the host."""
+        dev = self.device
+        rpe = data["RPE"]
+        packed = self._upload_rpe(rpe) if isinstance(rpe, (list, tuple)) and len(rpe) > 0 else None
+        return (_to_device(data["ACTORS"], dev), data["ACTOR_IDCS"], _to_device(data["LANES"], dev), data["LANE_IDCS"],
+                packed if packed is not None else _to_device(rpe, dev),
+                _to_device(data["TGT_NODES"], dev), _to_device(data["TGT_RPE"], dev))
+
+    def _upload_rpe(self, rpe):
+        scenes = []
+        for r in rpe:
+            t = r["scene"] if isinstance(r, dict) else r
+            if (not isinstance(t, torch.Tensor) or t.device.type != "cpu" or t.dtype != torch.float32
+                    or t.dim() != 3 or not t.is_contiguous()):
+                return None                                   # unusual input: per-tensor path
+            scenes.append(t)
+        n = len(scenes)
+        sizes = (C.c_int64 * n)(*[t.numel() * 4 for t in scenes])
+        srcs = (C.c_void_p * n)(*[t.data_ptr() for t in scenes])
+        total = self._lib.mind_upload_packed_bytes(sizes, n)
+        base = torch.empty(max(int(total), 256), dtype=torch.uint8, device=self.device)
+        offs = (C.c_int64 * n)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.mind_upload_packed(srcs, sizes, n, C.c_void_p(base.data_ptr()), base.numel(), offs,
+                                                    C.c_void_p(stream)), "mind_upload_packed")
+        out = _PackedRPE()
+        out.base, out.shapes = base, [tuple(t.shape) for t in scenes]
+        bp = base.data_ptr()
+        out.ptrs = (C.c_void_p * n)(*[bp + offs[i] for i in range(n)])
+        shp0 = out.shapes[0]
+        uniform = all(sh == shp0 for sh in out.shapes) and (sizes[0] % 256 == 0)
+        if uniform:                                           # one view op for the whole batch
+            views = base[:n * sizes[0]].view(torch.float32).view((n,) + shp0).unbind(0)
+        else:
+            views = [base[offs[i]:offs[i] + sizes[i]].view(torch.float32).view(out.shapes[i]) for i in range(n)]
+        for r, v in zip(rpe, views):
+            out.append({"scene": v, "scene_mask": r.get("scene_mask") if isinstance(r, dict) else None})
+        self._keep_host = scenes                              # pinned sources must outlive the asynchronous copies
+        return out
 
     # ---- reference network.py:582-595 ----
     def forward(self, data):
@@ -136,12 +185,10 @@ class ScenePredNetB200:
         self._last_packed = packed
         cls, reg, vel, cov_vel, param, a_off = packed
         B = cls.shape[0]
-        res_cls, res_reg, res_aux = [], [], []
-        for b in range(B):
-            s, e = a_off[b], a_off[b + 1]
-            res_cls.append(cls[b:b + 1])
-            res_reg.append(reg[s:e])
-            res_aux.append((vel[s:e], cov_vel[s:e], param[s:e].permute(1, 0, 2, 3)))
+        sizes = [a_off[b + 1] - a_off[b] for b in range(B)]  # per-scene views: one split call per output tensor
+        res_cls = list(cls.split(1))
+        res_reg = list(reg.split(sizes))
+        res_aux = [(v, c, p.permute(1, 0, 2, 3)) for v, c, p in zip(vel.split(sizes), cov_vel.split(sizes), param.split(sizes))]
         return res_cls, res_reg, res_aux
 
     __call__ = forward
@@ -184,6 +231,13 @@ class ScenePredNetB200:
             keep += [ctrs, vecs]
             bt.ctrs, bt.vecs = ctrs.data_ptr(), vecs.data_ptr()
             bt.rpe = None
+        elif isinstance(rpe, _PackedRPE) and len(rpe) == B and rpe.base.device == dev:
+            for b in range(B):
+                m = (a_off[b + 1] - a_off[b]) + (l_off[b + 1] - l_off[b])
+                if rpe.shapes[b] != (5, m, m):
+                    raise ValueError("RPE[%d] has shape %s, expected (5,%d,%d)" % (b, rpe.shapes[b], m, m))
+            keep.append(rpe.base)
+            bt.rpe = rpe.ptrs
         else:
             ptrs = (C.c_void_p * B)()
             for b in range(B):
