@@ -191,6 +191,12 @@ int mind_profile_read(MindCtx* ctx, char* buf, int64_t capacity);
 /* number of kernels the library launched since creation (bench.py's gpu_launches) */
 int64_t mind_launch_count(MindCtx* ctx);
 
+/* option "graph" = 1: a forward whose batch shape AND pointer set (inputs, outputs, workspace, stream) repeat is
+ * captured into a CUDA graph on its second appearance and replayed afterwards (one graph launch instead of ~170
+ * kernel launches; descriptor tables are private to the graph).  Meant for the scenario tree's small level batches
+ * with persistent buffers.  mind_graph_replays counts the forwards served by a replay. */
+int64_t mind_graph_replays(MindCtx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

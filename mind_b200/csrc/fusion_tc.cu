@@ -1079,19 +1079,22 @@ const char* make_map_edge(void* out, const void* base, int B, int N) {
 }
 }  // namespace
 
+void tc_free_forward_state(TcForwardState& f) {
+    if (f.d_work) cudaFree(f.d_work);
+    if (f.d_merge) cudaFree(f.d_merge);
+    if (f.d_part) cudaFree(f.d_part);
+    f = TcForwardState{};
+}
+
 void tc_free(TcWeights& w) {
     for (auto& l : w.layer) {
         if (l.Wcat) cudaFree(l.Wcat);
         if (l.params) cudaFree(l.params);
         l.Wcat = nullptr; l.params = nullptr;
     }
-    if (w.d_work) cudaFree(w.d_work);
-    if (w.d_merge) cudaFree(w.d_merge);
-    if (w.d_part) cudaFree(w.d_part);
-    w.d_merge = nullptr; w.d_part = nullptr; w.merge_cap = w.part_cap = 0;
+    tc_free_forward_state(w);
     if (w.h_err) cudaFreeHost((void*)w.h_err);
-    w.h_err = nullptr;
-    w.d_work = nullptr; w.d_err = nullptr; w.work_cap = 0; w.packed = false;
+    w.h_err = nullptr; w.d_err = nullptr; w.packed = false;
 }
 
 const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]) {

@@ -25,22 +25,27 @@ struct TcLayerDev {
     alignas(64) unsigned char wmap[128];   // CUtensorMap over Wcat
 };
 
-struct TcWeights {
-    TcLayerDev layer[6];
-    bool packed = false;
-    // per-forward state
+// per-forward state of the fused layers: descriptor tables on the device and the tensor maps built over the caller's
+// buffers.  Kept separate from the weights so that a captured CUDA graph can own a private copy (mind_api.cu).
+struct TcForwardState {
     TcWork* d_work = nullptr; int work_cap = 0; int n_work = 0;
     TcMerge* d_merge = nullptr; int merge_cap = 0; int n_merge = 0;
     float* d_part = nullptr; int part_cap = 0;          // [slots][16 j][144]: acc[128] | m[8] | l[8]
-    int* d_err = nullptr;                  // device alias of h_err
-    volatile int* h_err = nullptr;         // mapped host word: protocol error code of a trapped launch
     alignas(64) unsigned char emap[128];   // CUtensorMap over the edge stream
     const void* emap_ptr = nullptr; int emap_B = 0, emap_N = 0;
     alignas(64) unsigned char tmap[128];   // CUtensorMap over stq (fp32 [B*Nmax, 384]): T rows of a tile
     const void* tmap_ptr = nullptr; int64_t tmap_rows = 0;
     int B = 0, Nmax = 0;
+};
+
+struct TcWeights : TcForwardState {
+    TcLayerDev layer[6];
+    bool packed = false;
+    int* d_err = nullptr;                  // device alias of h_err
+    volatile int* h_err = nullptr;         // mapped host word: protocol error code of a trapped launch
     int sm_count = 148;
 };
+void tc_free_forward_state(TcForwardState& f);
 
 // all return nullptr on success, else an error string
 const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]);

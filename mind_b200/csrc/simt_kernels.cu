@@ -191,8 +191,54 @@ __global__ void __launch_bounds__(256) k_gemm_tn_big(GemmArgs g) {
     }
 }
 
+// few rows (tree-level batches: M = 6 modes x a handful of actors): one warp per output column, lanes split K, rows in
+// register chunks of 16.  The 64x64 tiled kernel above runs one or two CTAs through a serial K loop for these shapes
+// (25 us per launch measured at M = 48); this one spreads the N columns over the chip.
+__global__ void __launch_bounds__(128) k_gemm_small_m(GemmArgs g) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 4 + warp;
+    if (n >= g.N) return;
+    const float* __restrict__ wrow = g.W + (int64_t)n * g.ldw;
+    const int m_base = blockIdx.y * 64;
+    const int m_end = min(g.M, m_base + 64);
+    const float bn = g.bias ? g.bias[n] : 0.f;
+    for (int m0 = m_base; m0 < m_end; m0 += 16) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        for (int k = lane * 4; k < g.K; k += 128) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (m0 + i < m_end) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(g.A + (int64_t)(m0 + i) * g.lda + k));
+                    acc[i] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[i]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float v0 = warp_sum(acc[i]);
+            const int m = m0 + i;
+            if (lane == 0 && m < m_end) {
+                float v = v0 + bn;
+                if (g.gbias) v += g.gbias[(m / g.gsize) * (int64_t)g.ldg + n];
+                if (g.relu) v = fmaxf(v, 0.f);
+                g.C[(int64_t)m * g.ldc + n] = v;
+            }
+        }
+    }
+}
+
 void launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return;
+    if (g.M <= 256 && (g.K & 3) == 0 && (g.lda & 3) == 0 && (g.ldw & 3) == 0 &&
+        ((((uintptr_t)g.A) | ((uintptr_t)g.W)) & 15) == 0) {
+        dim3 grid((unsigned)((g.N + 3) / 4), (unsigned)((g.M + 63) / 64));
+        k_gemm_small_m<<<grid, 128, 0, st>>>(g);
+        ++g_launches;
+        return;
+    }
     const bool big = g.M >= 2048 && (g.N % HBN_) == 0 && (g.K % HBK_) == 0 && (g.lda & 3) == 0 && (g.ldw & 3) == 0 &&
                      (g.ldc & 3) == 0 && ((((uintptr_t)g.A) | ((uintptr_t)g.W) | ((uintptr_t)g.C)) & 15) == 0;
     if (big) {

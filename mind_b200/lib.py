@@ -49,7 +49,7 @@ class MindTreeUpdate(C.Structure):
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
-           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_tc_selftest", "mind_sync_check", "mind_profile_read",
+           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_sync_check", "mind_profile_read",
            "mind_tree_level", "mind_tree_update", "mind_tree_last_error"]
 
 _lib = None
@@ -91,6 +91,8 @@ def load(build_if_missing: bool = True):
     lib.mind_debug_tap.restype = C.c_int64
     lib.mind_launch_count.argtypes = [C.c_void_p]
     lib.mind_launch_count.restype = C.c_int64
+    lib.mind_graph_replays.argtypes = [C.c_void_p]
+    lib.mind_graph_replays.restype = C.c_int64
     lib.mind_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mind_tc_selftest.restype = C.c_int
     lib.mind_sync_check.argtypes = [C.c_void_p]

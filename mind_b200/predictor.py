@@ -71,6 +71,7 @@ class ScenePredNetB200:
         self._dev_index = idx
         self._sd: Dict[str, torch.Tensor] = {}
         self._ws = None
+        self._out_cache = {}
         self.training = False
         self.precision = _lib.PREC_FP32
 
@@ -107,6 +108,10 @@ class ScenePredNetB200:
         _lib.check(self._lib.mind_set_option(self._h, name.encode(), int(value)), name)
         return self
 
+    def use_graphs(self, on: bool = True):
+        """Capture each (batch shape, pointer set) into a CUDA graph on its second appearance and replay it afterwards."""
+        return self.set_option("graph", 1 if on else 0)
+
     def profile(self, on: bool = True):
         return self.set_option("profile", 1 if on else 0)
 
@@ -122,6 +127,9 @@ class ScenePredNetB200:
 
     def sync_check(self):
         _lib.check(self._lib.mind_sync_check(self._h), "mind_sync_check")
+
+    def graph_replays(self) -> int:
+        return int(self._lib.mind_graph_replays(self._h))
 
     def launch_count(self) -> int:
         return int(self._lib.mind_launch_count(self._h))
@@ -199,10 +207,13 @@ class ScenePredNetB200:
             self._ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward_packed(self, data, geom=None):
+    def forward_packed(self, data, geom=None, persistent_out=False):
         """Runs the library; returns packed (cls [B,6], reg [A,6,60,5], vel [A,6,60,2],
         cov_vel [A,6,60,3], param [A,6,8,5], actor_offsets list).  `geom` = (ctrs, vecs) device
-        tensors [sum M_b, 2] switches RPE evaluation to the device (the 'rpe' entry is ignored)."""
+        tensors [sum M_b, 2] switches RPE evaluation to the device (the 'rpe' entry is ignored).
+        `persistent_out` hands out the same output tensors for every call of a given (B, A) shape (the caller must be
+        done with the previous result): with option "graph" on, stable pointers let the library replay a captured
+        CUDA graph instead of enqueueing ~170 launches."""
         actors, actor_idcs, lanes, lane_idcs, rpe, tgt_nodes, tgt_rpe = data[:7]
         dev = self.device
         B = len(actor_idcs)
@@ -250,11 +261,13 @@ class ScenePredNetB200:
                 ptrs[b] = r.data_ptr()
             bt.rpe = ptrs
         bt.tgt_nodes, bt.tgt_rpe = tgt_nodes.data_ptr(), tgt_rpe.data_ptr()
-        cls = torch.empty(B, 6, device=dev)
-        reg = torch.empty(A, 6, 60, 5, device=dev)
-        vel = torch.empty(A, 6, 60, 2, device=dev)
-        cov_vel = torch.empty(A, 6, 60, 3, device=dev)
-        param = torch.empty(A, 6, 8, 5, device=dev)
+        outs = self._out_cache.get((B, A)) if persistent_out else None
+        if outs is None:
+            outs = (torch.empty(B, 6, device=dev), torch.empty(A, 6, 60, 5, device=dev), torch.empty(A, 6, 60, 2, device=dev),
+                    torch.empty(A, 6, 60, 3, device=dev), torch.empty(A, 6, 8, 5, device=dev))
+            if persistent_out:
+                self._out_cache[(B, A)] = outs
+        cls, reg, vel, cov_vel, param = outs
         out = _lib.MindOutputs(cls.data_ptr(), reg.data_ptr(), vel.data_ptr(), cov_vel.data_ptr(), param.data_ptr())
         need = self._lib.mind_workspace_bytes(self._h, B, A, L, nmax)
         if need < 0:

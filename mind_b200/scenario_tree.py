@@ -125,6 +125,11 @@ class ScenarioTreeGeneratorB200:
         self.front_end = None           # optional callable (lcl_smp, agent_obs) -> collated scene dict
         # benchmark mode: keep all 6 modes of every scene, branch at fixed times
         self.force_full = None          # e.g. (10, 20, 30): children of level d branch at force_full[d]
+        # device buffers that feed the network, kept across rollouts per (level, frontier size): stable pointers let
+        # the library replay one captured CUDA graph per level instead of ~170 launches (mind_set_option "graph")
+        self._pool = {}
+        self.graphs = True
+        self._graphs_on = False
 
     # ---- reference surface ------------------------------------------------------------------
     def reset(self):
@@ -148,6 +153,13 @@ class ScenarioTreeGeneratorB200:
             raise NotImplementedError("process_data needs av2/shapely; set generator.front_end = callable returning the "
                                       "collated scene dict, or call rollout(data)")
         return self.front_end(lcl_smp, agent_obs)
+
+    def _buf(self, key, name, shape, dtype=torch.float32):
+        d = self._pool.setdefault(key, {})
+        t = d.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = d[name] = torch.empty(shape, dtype=dtype, device=self.device)
+        return t
 
     def _tick(self, name, t0):
         import time
@@ -212,7 +224,7 @@ class ScenarioTreeGeneratorB200:
         L.cur_t = torch.zeros(1, dtype=torch.int32, device=dev)
         L.cur_t_host = [0]
         L.tgt_pts = d["TGT_PTS"][0].float().view(1, 11, 2)
-        L.net_in = self.network.pre_process(data)
+        L.net_in = self._root_inputs(data, d, pos.shape[0])
         L.geom = None
         L.parent_keys = ["root"]
         # constants of the tree
@@ -222,6 +234,24 @@ class ScenarioTreeGeneratorB200:
         self._lanes = d["LANES"].float().contiguous()
         self._n_lane = self._lanes.shape[0]
         return L
+
+    def _root_inputs(self, data, d, Na):
+        """network.pre_process for the root scene (:69), into persistent buffers (one scene: actors, lanes, RPE, target)."""
+        if self.graphs and not self._graphs_on and hasattr(self.network, "use_graphs"):
+            self.network.use_graphs(True)
+            self._graphs_on = True
+        rpe = data["RPE"][0]
+        rpe = rpe["scene"] if isinstance(rpe, dict) else rpe
+        src = (("actors", data["ACTORS"]), ("lanes", data["LANES"]), ("rpe", rpe), ("tgt_nodes", data["TGT_NODES"]),
+               ("tgt_rpe", data["TGT_RPE"]))
+        key = ("root", Na, int(data["LANES"].shape[0]))
+        out = {}
+        for name, t in src:
+            b = self._buf(key, name, t.shape)
+            b.copy_(t, non_blocking=True)
+            out[name] = b
+        return (out["actors"], data["ACTOR_IDCS"], out["lanes"], data["LANE_IDCS"], [{"scene": out["rpe"], "scene_mask": None}],
+                out["tgt_nodes"], out["tgt_rpe"])
 
     def init_scenario_tree(self, data):                                           # :60-67
         root = self._root_level(data)
@@ -235,7 +265,7 @@ class ScenarioTreeGeneratorB200:
 
     def predict_scenes(self, level: _Level):                                      # :69-71 (one batched call per level)
         self.net_batches.append(level.F)
-        pk = self.network.forward_packed(level.net_in, geom=level.geom)
+        pk = self.network.forward_packed(level.net_in, geom=level.geom, persistent_out=True)
         level.cls, level.reg, level.vel = pk[0], pk[1], pk[2]
         return pk
 
@@ -328,14 +358,16 @@ class ScenarioTreeGeneratorB200:
         f32 = dict(device=dev, dtype=torch.float32)
         N = _Level()
         N.F, N.Na = G, Na
-        N.hpos, N.hvel = torch.empty(G, Na, 50, 2, **f32), torch.empty(G, Na, 50, 2, **f32)
-        N.hang, N.hcov = torch.empty(G, Na, 50, **f32), torch.empty(G, Na, 50, **f32)
-        N.orig, N.rot = torch.empty(G, 2, **f32), torch.empty(G, 4, **f32)
-        N.ctrs, N.vecs = torch.empty(G, Na, 2, **f32), torch.empty(G, Na, 2, **f32)
-        actors = torch.empty(G * Na, 14, 48, **f32)
-        geom_c, geom_v = torch.empty(G, Na + Nl, 2, **f32), torch.empty(G, Na + Nl, 2, **f32)
-        tgt_nodes, tgt_rpe = torch.empty(G, 10, 16, **f32), torch.empty(G, 20, **f32)
-        N.tgt_pts = torch.empty(G, 11, 2, **f32)
+        key = ("level", len(self._levels), G, Na, Nl)
+        B_ = lambda name, *shape: self._buf(key, name, shape)
+        N.hpos, N.hvel = B_("hpos", G, Na, 50, 2), B_("hvel", G, Na, 50, 2)
+        N.hang, N.hcov = B_("hang", G, Na, 50), B_("hcov", G, Na, 50)
+        N.orig, N.rot = B_("orig", G, 2), B_("rot", G, 4)
+        N.ctrs, N.vecs = B_("ctrs", G, Na, 2), B_("vecs", G, Na, 2)
+        actors = B_("actors", G * Na, 14, 48)
+        geom_c, geom_v = B_("geom_c", G, Na + Nl, 2), B_("geom_v", G, Na + Nl, 2)
+        tgt_nodes, tgt_rpe = B_("tgt_nodes", G, 10, 16), B_("tgt_rpe", G, 20)
+        N.tgt_pts = B_("tgt_pts", G, 11, 2)
         N.pprob = torch.tensor([float(n.data.rec["prob"]) for n in nodes], **f32)
         N.cur_t_host = [int(n.data.rec["end_t"]) for n in nodes]
         N.cur_t = torch.tensor(N.cur_t_host, dtype=torch.int32, device=dev)
@@ -365,9 +397,13 @@ class ScenarioTreeGeneratorB200:
             if self._lib.mind_tree_update(C.byref(u), C.c_void_p(stream)) != 0:
                 raise RuntimeError(self._lib.mind_tree_last_error().decode())
             self._keep = src
-        a_idcs = [torch.arange(g * Na, (g + 1) * Na) for g in range(G)]
-        l_idcs = [torch.arange(g * Nl, (g + 1) * Nl) for g in range(G)]
-        lanes = self._lanes.unsqueeze(0).expand(G, -1, -1, -1).reshape(G * Nl, 10, 16)
+        idc = self._pool[key].get("idcs")
+        if idc is None:                                       # only their lengths matter to the network
+            idc = self._pool[key]["idcs"] = ([range(g * Na, (g + 1) * Na) for g in range(G)],
+                                             [range(g * Nl, (g + 1) * Nl) for g in range(G)])
+        a_idcs, l_idcs = idc
+        lanes = B_("lanes", G * Nl, 10, 16)
+        lanes.view(G, Nl, 10, 16).copy_(self._lanes.unsqueeze(0).expand(G, -1, -1, -1))
         N.net_in = (actors, a_idcs, lanes, l_idcs, None, tgt_nodes, tgt_rpe)
         N.geom = (geom_c.view(-1, 2), geom_v.view(-1, 2))
         for g, n in enumerate(nodes):
