@@ -436,23 +436,29 @@ class ScenarioTreeGeneratorB200:
                 for k in kids:
                     data_tree.add_node(Node(k.key, c.key, [np.asarray(k.data.rec["prob"]) / total * pp]))
                     queue.append(k)
-        host = {}                                                     # one D2H per level that contributes nodes
-
-        def level_host(lv):
-            if lv not in host:
-                L = self._levels[lv]
-                host[lv] = (L.cpos.cpu().numpy(), L.ccov.cpu().numpy(), L.tgt_pts.cpu().numpy())
-            return host[lv]
-        for key, dn in data_tree.nodes.items():                        # every labelled node gets its payload once
-            if key == root.key or len(dn.data) != 1:
-                continue
-            rec = self.tree.get_node(key).data.rec
+        # one asynchronous D2H per contributing level (predicted half of the child histories only) into pinned
+        # buffers kept across rollouts, a single synchronisation, then numpy views per node
+        todo = [(key, dn, self.tree.get_node(key).data.rec) for key, dn in data_tree.nodes.items()
+                if key != root.key and len(dn.data) == 1]
+        host = {}
+        for lv in sorted({rec["level"] for _, _, rec in todo}):
+            L = self._levels[lv]
+            ent = []
+            for name, t in (("cpos", L.cpos[:, :, :, self.obs_len:]), ("ccov", L.ccov[:, :, :, self.obs_len:]), ("tgt", L.tgt_pts)):
+                hk = ("host", lv, name)
+                h = self._pool.get(hk)
+                if h is None or tuple(h.shape) != tuple(t.shape):
+                    h = self._pool[hk] = torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory()
+                h.copy_(t, non_blocking=True)
+                ent.append(h)
+            host[lv] = ent
+        torch.cuda.current_stream(self.device).synchronize()
+        host = {lv: tuple(h.numpy().copy() for h in ent) for lv, ent in host.items()}   # own the data: the pinned buffers are reused
+        for key, dn, rec in todo:                                      # every labelled node gets its payload once
             dur = rec["end_t"] - rec["cur_t"]
-            cpos, ccov, tgt = level_host(rec["level"])
+            cpos, ccov, tgt = host[rec["level"]]
             f, k = rec["row"] // 6, rec["row"] % 6
-            dn.data += [cpos[f, k, :, self.obs_len:self.obs_len + dur, :],
-                        ccov[f, k, :, self.obs_len:self.obs_len + dur, None],
-                        tgt[f]]
+            dn.data += [cpos[f, k, :, :dur, :], ccov[f, k, :, :dur, None], tgt[f]]
         trees = []
         for key in data_tree.get_root().children_keys:
             st = Tree()

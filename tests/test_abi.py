@@ -40,3 +40,16 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_upload_packed_layout_math():
+    """mind_upload_packed_bytes: entries are laid out in order at 256-byte aligned offsets (no GPU needed)."""
+    import ctypes as C
+    from mind_b200 import lib
+    L = lib.load()
+    sizes = [1, 256, 257, 0, 5 * 160 * 160 * 4]
+    arr = (C.c_int64 * len(sizes))(*sizes)
+    assert L.mind_upload_packed_bytes(arr, len(sizes)) == 256 + 256 + 512 + 0 + 512000
+    assert L.mind_upload_packed_bytes(arr, 0) == 0
+    bad = (C.c_int64 * 1)(-4)
+    assert L.mind_upload_packed_bytes(bad, 1) == -1

@@ -167,3 +167,51 @@ def test_actor_net_tensor_core_stage(ckpt_sd, rand_sd, dev):
     e = rel_err(af, gold["actor_feat"])
     print("actor_feat (tc, rand) rel err %.3e" % e)
     assert e < 2e-5
+
+
+def test_pre_process_packed_upload_matches_per_tensor_path(ckpt_sd, dev):
+    """pre_process from HOST tensors (one mind_upload_packed call for all RPE tensors, index lists left on the host)
+    gives bit-identical outputs to the same inputs moved tensor by tensor; uniform and ragged batches."""
+    from mind_b200 import synth
+    from mind_b200.predictor import _PackedRPE
+    net = make_net(ckpt_sd, dev, "f16tc")
+    keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+    for data in (synth.batch_from_scenes([synth.scene_s1(70 + i, 6, 20) for i in range(5)]), synth.batch_ragged(6, seed=3)):
+        staged = net.pre_process(dict(zip(keys, data)))
+        assert isinstance(staged[4], _PackedRPE) and len(staged[4]) == len(data[4])
+        for r, src in zip(staged[4], data[4]):
+            assert r["scene"].is_cuda and torch.equal(r["scene"].cpu(), src["scene"])
+        a = [t.clone() for t in net.forward_packed(staged)[:3]]
+        b = [t.clone() for t in net.forward_packed(to_dev(data, dev))[:3]]
+        torch.cuda.synchronize()
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
+def test_cuda_graph_replay_is_bit_identical_and_reads_fresh_inputs(ckpt_sd, dev):
+    """option "graph": third and later forwards of a (shape, pointer set) are served by a graph replay; results are
+    bit-identical to the plain launch sequence, and new input CONTENTS in the same buffers are picked up."""
+    from mind_b200 import synth
+    keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+    plain, graph = make_net(ckpt_sd, dev, "f16tc"), make_net(ckpt_sd, dev, "f16tc")
+    graph.use_graphs(True)
+    d1 = synth.batch_from_scenes([synth.scene_s1(80 + i, 8, 24) for i in range(3)])
+    d2 = synth.batch_from_scenes([synth.scene_s1(90 + i, 8, 24) for i in range(3)])
+    staged = graph.pre_process(dict(zip(keys, d1)))
+    want1 = [t.clone() for t in plain.forward_packed(to_dev(d1, dev))[:3]]
+    want2 = [t.clone() for t in plain.forward_packed(to_dev(d2, dev))[:3]]
+    for it in range(4):
+        got = graph.forward_packed(staged, persistent_out=True)[:3]
+        torch.cuda.synchronize()
+        for x, y in zip(got, want1):
+            assert torch.equal(x, y), it
+    assert graph.graph_replays() == 2                      # first sight plain, second captured, then replays
+    # same buffers, new contents
+    staged[0].copy_(d2[0]); staged[2].copy_(d2[2]); staged[5].copy_(d2[5]); staged[6].copy_(d2[6])
+    for r, src in zip(staged[4], d2[4]):
+        r["scene"].copy_(src["scene"])
+    got = graph.forward_packed(staged, persistent_out=True)[:3]
+    torch.cuda.synchronize()
+    assert graph.graph_replays() == 3
+    for x, y in zip(got, want2):
+        assert torch.equal(x, y)
