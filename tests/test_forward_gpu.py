@@ -215,3 +215,20 @@ def test_cuda_graph_replay_is_bit_identical_and_reads_fresh_inputs(ckpt_sd, dev)
     assert graph.graph_replays() == 3
     for x, y in zip(got, want2):
         assert torch.equal(x, y)
+
+
+def test_repeated_forwards_keep_the_protocol_clean(ckpt_sd, dev):
+    """Regression for the tile-done hand-off (a 16-arrival barrier could complete two phases in the layer without
+    edge update and deadlock about once in six forwards at 64 scenes): twelve forwards, protocol error word checked
+    after each, results bit-identical from call to call."""
+    from mind_b200 import synth
+    net = make_net(ckpt_sd, dev, "f16tc")
+    data = to_dev(synth.batch_s2(64), dev)
+    ref = None
+    for it in range(12):
+        out = net.forward_packed(data)
+        net.sync_check()
+        reg = out[1].clone()
+        if ref is None:
+            ref = reg
+        assert torch.equal(reg, ref), it
