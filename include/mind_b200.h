@@ -179,6 +179,15 @@ const char* mind_tree_last_error(void);
  * All three are HOST buffers (A, W: 128*128 floats; D: 3*128*128 floats). */
 int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host);
 
+/* Host-only diagnostic (no device needed): the static schedule the fused rela-fusion layer would use for scenes
+ * of n_tokens[b] = actors + lanes + 1 tokens on sm_count CTAs.  work receives 8 int32 per entry
+ * {b, j0, n, ch0, ch1, slot, mode, 0}: first `grid` range headers {first item, one past the last item}, then the work
+ * items (mode 0: queries j0..j0+15, key chunks [ch0, ch1) of 8 keys; mode 1: query j0 only, chunks of 128 keys;
+ * slot >= 0: one part of a key-split item).  info receives {n_entries, grid, n_merge_jobs, n_slots}.  Returns 0, or
+ * -1 when capacity (in entries) is too small (info[0] then holds the required count). */
+int mind_debug_fusion_schedule(const int32_t* n_tokens, int32_t n_scenes, int32_t sm_count, int32_t* work,
+                               int32_t capacity, int32_t* info);
+
 /* cudaDeviceSynchronize + kernel-side protocol error flag (0 = clean) */
 int mind_sync_check(MindCtx* ctx);
 

@@ -4,7 +4,9 @@
 // _mha_block, planners/mind/networks/network.py:182-226.
 //
 // Work decomposition: one work item = (scene b, 16 queries j0..j0+15); the CTA walks the keys in
-// chunks of 8, so a tile is 8 keys x 16 queries = 128 pair rows = the 128 TMEM lanes.
+// chunks of 8, so a tile is 8 keys x 16 queries = 128 pair rows = the 128 TMEM lanes.  A scene's last
+// query block, when it holds a single query (n % 16 == 1: the cls token of a 32 x 128 scene), is a
+// single-query item instead: tiles of 128 keys x 1 query (tc_build_schedule).
 //   G1:  D1[128x128]  = edge_tile(fp16) . W_e^T                      (+S[j]+T[i], LN, ReLU -> memory)
 //   G2:  Dpe|Dk|Dv    = memory(fp16)   . [W_pe ; W_k ; W_v]^T
 //   edge' = LN(edge + ReLU(LN(Dpe + b)))  written back in place (fp16) by TMA
@@ -15,7 +17,9 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace mind {
@@ -301,7 +305,10 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 // at the hand-off points of tiles [kTraceG0, kTraceG0 + kTraceTiles); read back with mind_trace_read
 // ---------------------------------------------------------------------------------------------
 #ifdef MIND_TRACE
-constexpr int kTraceG0 = 40, kTraceTiles = 8, kTracePts = 32;
+#ifndef MIND_TRACE_G0
+#define MIND_TRACE_G0 40
+#endif
+constexpr int kTraceG0 = MIND_TRACE_G0, kTraceTiles = 8, kTracePts = 32;
 __device__ long long g_trace[kTraceTiles * 17 * kTracePts];
 #define TR(id, gg)                                                                                        \
     do {                                                                                                  \
@@ -343,23 +350,23 @@ struct LayerArgs {
 // column quarter q = w>>2); warp 16 = issuer (TMA loads / stores, every tcgen05.mma, T-tile staging).
 // Steady state has no CTA-wide barrier: issuer and epilogue meet only through mbarriers, the four
 // warps that share rows through a named 128-thread barrier.
-struct TileIt {          // walks (work item, key chunk) in the CTA's static schedule
-    int wi, ch, ch1, b, j0, n;
+struct TileIt {          // walks (work item, key chunk) over the CTA's contiguous range [wi, wi_end) of the work list
+    int wi, wi_end, ch, ch1, b, j0, mode;
 };
-__device__ __forceinline__ bool tile_valid(const TileIt& t, int n_work) { return t.wi < n_work; }
-__device__ __forceinline__ void tile_load_wi(TileIt& t, const TcWork* work, int n_work) {
-    if (t.wi < n_work) {
+__device__ __forceinline__ bool tile_valid(const TileIt& t) { return t.wi < t.wi_end; }
+__device__ __forceinline__ void tile_load_wi(TileIt& t, const TcWork* work) {
+    if (t.wi < t.wi_end) {
         const TcWork w = work[t.wi];
-        t.b = w.b; t.j0 = w.j0; t.n = w.n; t.ch = w.ch0; t.ch1 = w.ch1;
+        t.b = w.b; t.j0 = w.j0; t.ch = w.ch0; t.ch1 = w.ch1; t.mode = w.mode;
     }
 }
-__device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work, int n_work, int stride) {
-    if (++t.ch >= t.ch1) { t.wi += stride; tile_load_wi(t, work, n_work); }
+__device__ __forceinline__ void tile_next(TileIt& t, const TcWork* work) {
+    if (++t.ch >= t.ch1) { ++t.wi; tile_load_wi(t, work); }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)      // 17 warps are granted registers as 5 warpgroups -> 96 / thread
-k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap wmap,
-                 const __grid_constant__ CUtensorMap tmap, LayerArgs a) {
+k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CUtensorMap emapq,
+                 const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap tmap, LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));   // generic pointer to the aligned base
@@ -389,7 +396,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sTmem;
-    const int stride = gridDim.x;
+    // work[0 .. gridDim.x) are range headers: CTA c owns the work items [hdr.b, hdr.j0) (tc_prepare)
+    const int wi_begin = a.work[blockIdx.x].b, wi_end = a.work[blockIdx.x].j0;
 
     if (warp == kIssuerWarp) {
         // =============================== issuer warp ===============================
@@ -403,14 +411,20 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         auto load_tile = [&](const TileIt& t, int buf) {          // lane 0 only
             const uint32_t bl = bar_ld0 + 8 * buf, dst = sbase + SM_TILE0 + buf * 32768;
             mbar_expect_tx(bl, 32768u);
-            tma_load_4d(dst, &emap, bl, 0, t.j0, t.ch * 8, t.b);
-            tma_load_4d(dst + 16384, &emap, bl, 64, t.j0, t.ch * 8, t.b);
+            if (t.mode) {     // single-query item: box [64 c][1 j][128 i], tile row = key
+                tma_load_4d(dst, &emapq, bl, 0, t.j0, t.ch * 128, t.b);
+                tma_load_4d(dst + 16384, &emapq, bl, 64, t.j0, t.ch * 128, t.b);
+            } else {
+                tma_load_4d(dst, &emap, bl, 0, t.j0, t.ch * 8, t.b);
+                tma_load_4d(dst + 16384, &emap, bl, 64, t.j0, t.ch * 8, t.b);
+            }
         };
         // T rows (tar term, per key i) of a tile: one TMA box [128 floats x 8 token rows] out of stq[:, 128:256).  Rows of
         // padding tokens (i >= n) carry finite values and are masked in the softmax; rows past the tensor are zero-filled.
+        // Single-query items read their T rows from global memory; the box is still loaded to keep the protocol uniform.
         auto load_T = [&](const TileIt& t) {                      // lane 0 only
             mbar_expect_tx(bar_t, 4096u);
-            tma_load_2d(sbase + SM_T, &tmap, bar_t, 128, t.b * a.Nmax + t.ch * 8);
+            tma_load_2d(sbase + SM_T, &tmap, bar_t, 128, t.b * a.Nmax + (t.mode ? 0 : t.ch * 8));
         };
         auto issue_g1 = [&](int buf) {                            // lane 0 only
             const uint32_t tX = sbase + SM_TILE0 + buf * 32768, id128 = umma_idesc_f16(128);
@@ -422,15 +436,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             }
             umma_commit(bar_m1);
         };
-        TileIt cur_t{(int)blockIdx.x, 0, 0, 0, 0, 0};
-        tile_load_wi(cur_t, a.work, a.n_work);
-        if (tile_valid(cur_t, a.n_work)) {
+        TileIt cur_t{wi_begin, wi_end, 0, 0, 0, 0, 0};
+        tile_load_wi(cur_t, a.work);
+        if (tile_valid(cur_t)) {
             TileIt nxt = cur_t;
-            tile_next(nxt, a.work, a.n_work, stride);
+            tile_next(nxt, a.work);
             uint32_t g = 0;                                       // tiles processed by this CTA
             if (elect_one()) {
                 load_tile(cur_t, 0);
-                if (tile_valid(nxt, a.n_work)) load_tile(nxt, 1);
+                if (tile_valid(nxt)) load_tile(nxt, 1);
             }
             if (elect_one()) {
                 load_T(cur_t);
@@ -441,7 +455,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             while (true) {
                 const int buf = g & 1;
                 const uint32_t par = g & 1;
-                const bool has_next = tile_valid(nxt, a.n_work);
+                const bool has_next = tile_valid(nxt);
                 // [A] A operand of this tile is in TMEM -> G2 (W_pe first: its epilogue overlaps the K|V MMAs)
                 TR(15, g);
                 handoff_sync(kBarA);
@@ -492,17 +506,22 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
                 // [C] edge' tile complete -> TMA store ; [D] buffer free -> load the tile after next
                 TileIt nn = nxt;
-                if (has_next) tile_next(nn, a.work, a.n_work, stride);
+                if (has_next) tile_next(nn, a.work);
                 handoff_sync(kBarE);
                 TR(22, g);
                 if (elect_one()) {
                     if (a.has_edge) {
                         const uint32_t tX = sbase + SM_TILE0 + buf * 32768;
-                        tma_store_4d(&emap, tX, 0, cur_t.j0, cur_t.ch * 8, cur_t.b);
-                        tma_store_4d(&emap, tX + 16384, 64, cur_t.j0, cur_t.ch * 8, cur_t.b);
+                        if (cur_t.mode) {
+                            tma_store_4d(&emapq, tX, 0, cur_t.j0, cur_t.ch * 128, cur_t.b);
+                            tma_store_4d(&emapq, tX + 16384, 64, cur_t.j0, cur_t.ch * 128, cur_t.b);
+                        } else {
+                            tma_store_4d(&emap, tX, 0, cur_t.j0, cur_t.ch * 8, cur_t.b);
+                            tma_store_4d(&emap, tX + 16384, 64, cur_t.j0, cur_t.ch * 8, cur_t.b);
+                        }
                         tma_commit();
                     }
-                    if (has_next && tile_valid(nn, a.n_work)) {
+                    if (has_next && tile_valid(nn)) {
                         tma_wait_read0();
                         load_tile(nn, buf);
                     }
@@ -518,7 +537,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         const int q = ew >> 2;                       // column quarter: channels [32q, 32q+32)
         const int lg = warp & 3;                     // TMEM lane quadrant is fixed by the hardware warp id
         const int row = lg * 32 + lane;              // TMEM lane = pair row inside the tile
-        const int i_l = row >> 4, j_l = row & 15;
         const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
         const int col0 = q * 32;
         const uint32_t tile_off = (uint32_t)(q >> 1) * 16384u;      // k-block of this quarter inside an edge tile
@@ -526,10 +544,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         const float* Pm = sP;
         const uint32_t aS = sbase + SM_S, aQ = sbase + SM_Q, aT = sbase + SM_T, aP = sbase + SM_P;
         uint32_t g = 0;                                              // tiles processed by this CTA
-        for (int wi = blockIdx.x; wi < a.n_work; wi += stride) {
+        for (int wi = wi_begin; wi < wi_end; ++wi) {
             const TcWork wk = a.work[wi];
             const int N = wk.n, j0 = wk.j0, b = wk.b;
             const int ch0 = wk.ch0, ch1 = wk.ch1;
+            // tile row -> (key slot, query): 8 keys x 16 queries, or (single-query item) 128 keys x query j0
+            const int mode = wk.mode;
+            const int i_l = mode ? row : (row >> 4), j_l = mode ? 0 : (row & 15);
+            const int kstep = mode ? 128 : 8;
             const int64_t tok0 = (int64_t)b * a.Nmax;
             {   // S (src term, per query j) and q tiles: 16 x 32 float4 each, one per epilogue thread
                 const int jj = ew, c4 = tid & 31;
@@ -600,8 +622,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             };
 
             for (int ch = ch0; ch < ch1; ++ch, ++g) {
-                const int i0 = ch * 8;
+                const int i0 = ch * kstep;
                 const uint32_t par = g & 1;
+                // single-query item: this row's T (tar) vector comes straight from stq (row clamped: keys past the scene
+                // are masked in the softmax, their values only have to be finite)
+                const float* Tg = a.stq + (tok0 + min(i0 + i_l, a.Nmax - 1)) * 384 + 128;
                 const uint32_t tX = sbase + SM_TILE0 + (g & 1) * 32768;  // edge tile (in place -> edge')
                 TR(0, g);
                 mbar_wait(bar_t, par, a.err, E_LOAD_EDGE + 10);          // T rows staged by the issuer
@@ -613,7 +638,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 // streaming 16-column passes; x = D1 + S + T is parked in this thread's own Dpe cells
                 // (free until G2 of this tile is issued) so nothing has to live in registers across the barrier
                 const uint32_t scr_t = tmem + lane_base + 128 + col0;
-                {
+                auto e1_pass1 = [&](auto qtag) {                   // two straight-line copies: no branch inside the unrolled loops
+                    constexpr bool kQ = decltype(qtag)::value;
                     f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
                     uint32_t rr[2][16];
                     TMEM_LD_X16_NM(tmem + lane_base + col0, rr[0]);
@@ -628,7 +654,12 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                             const int c = col0 + hf * 16 + k4 * 4;
                             f2 sa, sb, ta, tb;
                             lds_2f2(sS + (j_l * 132 + c), sa, sb);
-                            lds_2f2(sT + (i_l * 128 + c), ta, tb);
+                            if constexpr (kQ) {
+                                const ulonglong2 tv = __ldg(reinterpret_cast<const ulonglong2*>(Tg + c));
+                                ta = tv.x; tb = tv.y;
+                            } else {
+                                lds_2f2(sT + (i_l * 128 + c), ta, tb);
+                            }
                             const f2 x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), ta);
                             const f2 x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tb);
                             upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
@@ -640,7 +671,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     }
                     sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                }
+                };
+                if (mode) e1_pass1(std::true_type{});
+                else e1_pass1(std::false_type{});
                 tc_fence_before();
                 TR(2, g);
                 row_group_sync(lg);                                // statistics exchanged, D1 reads of these lanes retired
@@ -687,7 +720,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 TR(4, g);
                 handoff_arrive(kBarA);                             // this warp's slice of the A operand is in TMEM
                 TR(13, g);
-                if (ch > ch0) attend(par ^ 1, (i0 - 8 + i_l) < N); // attention epilogue of the previous tile, under the W_pe MMAs
+                if (ch > ch0) attend(par ^ 1, (i0 - kstep + i_l) < N); // attention epilogue of the previous tile, under the W_pe MMAs
                 TR(6, g);
                 handoff_arrive(kBarK);                             // Dk/Dv free: the issuer may run the K|V MMAs of this tile
 
@@ -811,64 +844,79 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 row_group_sync(lg);                                // statistics buffers can be reused by the next tile
             }
 
-            attend((g - 1) & 1, ((ch1 - 1) * 8 + i_l) < N);        // attention epilogue of the work item's last tile
+            attend((g - 1) & 1, ((ch1 - 1) * kstep + i_l) < N);        // attention epilogue of the work item's last tile
             TR(26, g);
             float acc[32];
 #pragma unroll
             for (int k = 0; k < 16; ++k) upk2(acc2[k], acc[2 * k], acc[2 * k + 1]);
             // ---- merge the partial softmax states of the 8 key slots of every (query, head) ----
-            // lanes l and l^16 hold key slots 2*lg and 2*lg+1 of the same query
+            // lanes l and l^16 hold key slots 2*lg and 2*lg+1 of the same query; in a single-query item all 32 lanes hold
+            // keys of that query (full butterfly: lane 0 ends up with the warp's state, lanes 1..15 are ignored below)
+            const int off_min = mode ? 1 : 16;
+#pragma unroll 1
+            for (int off = 16; off >= off_min; off >>= 1) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float mo = __shfl_xor_sync(0xffffffffu, mrun[h], 16);
-                const float lo = __shfl_xor_sync(0xffffffffu, lrun[h], 16);
-                const float mn = fmaxf(mrun[h], mo);
-                const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
-                const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-                lrun[h] = lrun[h] * ca + lo * cb;
+                for (int h = 0; h < 2; ++h) {
+                    const float mo = __shfl_xor_sync(0xffffffffu, mrun[h], off);
+                    const float lo = __shfl_xor_sync(0xffffffffu, lrun[h], off);
+                    const float mn = fmaxf(mrun[h], mo);
+                    const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
+                    const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+                    lrun[h] = lrun[h] * ca + lo * cb;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float ao = __shfl_xor_sync(0xffffffffu, acc[h * 16 + k], 16);
-                    acc[h * 16 + k] = acc[h * 16 + k] * ca + ao * cb;
+                    for (int k = 0; k < 16; ++k) {
+                        const float ao = __shfl_xor_sync(0xffffffffu, acc[h * 16 + k], off);
+                        acc[h * 16 + k] = acc[h * 16 + k] * ca + ao * cb;
+                    }
+                    mrun[h] = mn;
                 }
-                mrun[h] = mn;
             }
             // three rounds through the (now dead) S|q tile area: row group r publishes, row group 0 accumulates
-            float* scr = sS;                                       // [4 quarter][16 j][40] floats = 10 KB <= S|q area
+            float* scr = sS;                                       // [4 quarter][16 j][36] floats = 9 KB <= S|q area
             for (int r = 1; r < 4; ++r) {
                 asm volatile("bar.sync 5, 512;" ::: "memory");
                 if (lg == r && lane < 16) {
-                    float* d = scr + (q * 16 + lane) * 40;
+                    float4* d = reinterpret_cast<float4*>(scr + (q * 16 + lane) * 36);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) d[k] = acc[k];
-                    d[32] = mrun[0]; d[33] = mrun[1]; d[34] = lrun[0]; d[35] = lrun[1];
+                    for (int k = 0; k < 8; ++k) d[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+                    d[8] = make_float4(mrun[0], mrun[1], lrun[0], lrun[1]);
                 }
                 asm volatile("bar.sync 5, 512;" ::: "memory");
                 if (lg == 0 && lane < 16) {
-                    const float* d = scr + (q * 16 + lane) * 40;
+                    const float4* d4 = reinterpret_cast<const float4*>(scr + (q * 16 + lane) * 36);
+                    const float4 ml = d4[8];
+                    const float mo2[2] = {ml.x, ml.y}, lo2[2] = {ml.z, ml.w};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float mo = d[32 + h], lo = d[34 + h];
-                        const float mn = fmaxf(mrun[h], mo);
+                        const float mn = fmaxf(mrun[h], mo2[h]);
                         const float ca = (mrun[h] == -INFINITY) ? 0.f : __expf(mrun[h] - mn);
-                        const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-                        lrun[h] = lrun[h] * ca + lo * cb;
+                        const float cb = (mo2[h] == -INFINITY) ? 0.f : __expf(mo2[h] - mn);
+                        lrun[h] = lrun[h] * ca + lo2[h] * cb;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) acc[h * 16 + k] = acc[h * 16 + k] * ca + d[h * 16 + k] * cb;
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 v = d4[h * 4 + k4];
+                            acc[h * 16 + k4 * 4 + 0] = acc[h * 16 + k4 * 4 + 0] * ca + v.x * cb;
+                            acc[h * 16 + k4 * 4 + 1] = acc[h * 16 + k4 * 4 + 1] * ca + v.y * cb;
+                            acc[h * 16 + k4 * 4 + 2] = acc[h * 16 + k4 * 4 + 2] * ca + v.z * cb;
+                            acc[h * 16 + k4 * 4 + 3] = acc[h * 16 + k4 * 4 + 3] * ca + v.w * cb;
+                        }
                         mrun[h] = mn;
                     }
                 }
             }
+            // writer of a query's state: lanes 0..15 of row group 0 (query j0 + lane)
+            const bool wr = (lg == 0 && lane < 16);
+            const int jo = lane;
             if (wk.slot >= 0) {
-                if (lg == 0 && lane < 16) {                        // key-split item: park the un-normalised state for k_merge_parts
-                    float* d = a.part + ((int64_t)wk.slot * 16 + lane) * 144;
+                if (wr) {                                          // key-split item: park the un-normalised state for k_merge_parts
+                    float* d = a.part + ((int64_t)wk.slot * 16 + jo) * 144;
 #pragma unroll
                     for (int k = 0; k < 32; ++k) d[col0 + k] = acc[k];
                     d[128 + q * 2] = mrun[0]; d[128 + q * 2 + 1] = mrun[1];
                     d[136 + q * 2] = lrun[0]; d[136 + q * 2 + 1] = lrun[1];
                 }
-            } else if (lg == 0 && lane < 16 && j0 + lane < N) {
-                const int64_t orow = (tok0 + j0 + lane) * 128 + col0;
+            } else if (wr && j0 + jo < N) {
+                const int64_t orow = (tok0 + j0 + jo) * 128 + col0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float inv = 1.f / lrun[h];
@@ -889,7 +937,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 }
             }
             TR(27, g);
-            asm volatile("bar.sync 5, 512;" ::: "memory");         // scratch consumed before the next S|q tiles are written
+            asm volatile("bar.sync 5, 512;" ::: "memory");         // every warp is done with this item's S|q tiles (and the scratch)
         }
     }
 
@@ -1064,13 +1112,13 @@ const char* make_map_stq(void* out, const void* base, int64_t rows) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? nullptr : tcfail("cuTensorMapEncodeTiled(stq)", (int)r);
 }
-// 4-D fp16 edge stream [B][N(i)][N(j)][128], box [64 c][16 j][8 i][1]
-const char* make_map_edge(void* out, const void* base, int B, int N) {
+// 4-D fp16 edge stream [B][N(i)][N(j)][128], box [64 c][bj queries][bi keys][1] (tile row = bj * key + query)
+const char* make_map_edge(void* out, const void* base, int B, int N, int bj, int bi) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
     cuuint64_t dims[4] = {128, (cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t strides[3] = {256, (cuuint64_t)N * 256, (cuuint64_t)N * N * 256};
-    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)bj, (cuuint32_t)bi, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1139,39 +1187,105 @@ const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]) {
     return nullptr;
 }
 
-const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, HostStage& stage, cudaStream_t st) {
-    if (!w.packed) return "weights not packed";
-    std::vector<TcWork> work;
+// Static schedule of the fused layer kernel.  Work items in scene order; a query block that holds one query only
+// (n % 16 == 1: the cls token of a 32 x 128 scene) becomes a single-query item of ceil(n / 128) tiles instead of
+// ceil(n / 8) tiles that are 15/16 padding.  Every CTA gets a contiguous run of the tile sequence, equal to within one
+// tile: an item that straddles a boundary is split along the key axis and the partial softmax states of its parts are
+// merged by k_merge_parts.  work[0 .. grid) are the per-CTA range headers.
+#ifdef MIND_EXP_NOQ      // timing experiment: schedule without single-query items
+static const bool kSingleQueryItems = false;
+#else
+static const bool kSingleQueryItems = true;
+#endif
+// Default: every CTA gets one contiguous run of the scene-ordered tile sequence.  MIND_TC_SCHED=deal (development) deals
+// whole items round by round first and balances only the remainder; measured slower (single-query items pile up on the
+// last CTAs: 9.99 vs 9.84 ms per 5 launches).
+static bool deal_rounds() { const char* e = getenv("MIND_TC_SCHED"); return e && !strcmp(e, "deal"); }
+void tc_build_schedule(const int* n_tokens, int B, int sm_count, std::vector<TcWork>& work, std::vector<TcMerge>& merges,
+                       int& n_slots, int& grid) {
+    std::vector<TcWork> items;
+    int64_t total = 0;
     for (int b = 0; b < B; ++b) {
-        const int n = sd[b].n_actor + sd[b].n_lane + 1;
-        for (int j0 = 0; j0 < n; j0 += 16) work.push_back(TcWork{b, j0, n, 0, (n + 7) >> 3, -1, 0, 0});
-    }
-    // longest work items first (static round-robin over persistent CTAs)
-    std::stable_sort(work.begin(), work.end(), [](const TcWork& x, const TcWork& y) { return x.n > y.n; });
-    // tail: the items of the last, partially filled round are split along the key axis into parts that keep
-    // every CTA busy; their partial softmax states are merged by k_merge_parts
-    std::vector<TcMerge> merges;
-    int n_slots = 0;
-    const int grid = std::max(1, std::min((int)work.size(), w.sm_count));
-    const int rem = (int)(work.size() % (size_t)grid);
-    if ((int)work.size() > grid && rem > 0 && rem * 2 <= grid) {
-        std::vector<TcWork> tail(work.end() - rem, work.end());
-        work.resize(work.size() - rem);
-        const int per = grid / rem;                                  // parts per leftover item
-        for (const TcWork& t : tail) {
-            const int nch = t.ch1 - t.ch0;
-            const int parts = std::max(1, std::min(per, nch));
-            if (parts == 1) { work.push_back(t); continue; }
-            merges.push_back(TcMerge{t.b, t.j0, t.n, n_slots, parts, 0, 0, 0});
-            for (int p = 0; p < parts; ++p) {
-                TcWork x = t;
-                x.ch0 = t.ch0 + (int)((int64_t)nch * p / parts);
-                x.ch1 = t.ch0 + (int)((int64_t)nch * (p + 1) / parts);
-                x.slot = n_slots++;
-                work.push_back(x);
-            }
+        const int n = n_tokens[b];
+        for (int j0 = 0; j0 < n; j0 += 16) {
+            if (kSingleQueryItems && n - j0 == 1 && n > 16) items.push_back(TcWork{b, j0, n, 0, (n + 127) >> 7, -1, 1, 0});
+            else items.push_back(TcWork{b, j0, n, 0, (n + 7) >> 3, -1, 0, 0});
+            total += items.back().ch1;
         }
     }
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(total, sm_count));
+    merges.clear();
+    n_slots = 0;
+    // per-CTA lists.  Bulk: whole 16-query items dealt round by round (largest first, serpentine), so that at any time
+    // neighbouring CTAs stream neighbouring query blocks of the same scenes.  Remainder (last rounds + single-query
+    // items): handed out at tile granularity so that every CTA ends within about one tile of the mean.
+    const bool kDealRounds = deal_rounds();
+    std::vector<std::vector<TcWork>> lists((size_t)grid);
+    std::vector<int64_t> load((size_t)grid, 0);
+    std::vector<TcWork> bulk, rest;
+    for (const TcWork& t : items) (t.mode ? rest : bulk).push_back(t);
+    std::stable_sort(bulk.begin(), bulk.end(), [](const TcWork& x, const TcWork& y) { return x.ch1 > y.ch1; });
+    const bool uniform = bulk.empty() || bulk.front().ch1 == bulk.back().ch1;
+    int rounds = (int)(bulk.size() / (size_t)grid);
+    if (!uniform) rounds = std::max(0, rounds - 1);
+    if (!kDealRounds) rounds = 0;
+    for (int k = 0; k < rounds; ++k)
+        for (int c = 0; c < grid; ++c) {
+            const int cc = (k & 1) ? grid - 1 - c : c;
+            const TcWork& t = bulk[(size_t)k * grid + c];
+            lists[cc].push_back(t);
+            load[cc] += t.ch1;
+        }
+    rest.insert(rest.begin(), bulk.begin() + (size_t)rounds * grid, bulk.end());
+    if (!kDealRounds)      // contiguous mode: scene order
+        std::stable_sort(rest.begin(), rest.end(), [](const TcWork& x, const TcWork& y) { return x.b != y.b ? x.b < y.b : x.j0 < y.j0; });
+    // fill every CTA up to its share of the total
+    size_t ri = 0;          // next item of `rest`
+    int c0 = 0;             // first chunk of rest[ri] not handed out yet
+    bool split_open = false;
+    for (int c = 0; c < grid && ri < rest.size(); ++c) {
+        const int64_t target = total * (c + 1) / grid - total * c / grid;
+        const bool last = (c == grid - 1);
+        while (ri < rest.size()) {
+            const TcWork& t = rest[ri];
+            const int64_t need = last ? (int64_t)1 << 40 : target - load[c];
+            if (need <= 0) break;
+            const int left = t.ch1 - c0;
+            if (t.mode || (c0 == 0 && left <= need)) {               // whole item (single-query items are never split)
+                lists[c].push_back(t);
+                load[c] += left;
+                ++ri;
+                continue;
+            }
+            if (c0 == 0) { merges.push_back(TcMerge{t.b, t.j0, t.n, n_slots, 0, 0, 0, 0}); split_open = true; }
+            const int take = (int)std::min<int64_t>(left, need);
+            TcWork x = t;
+            x.ch0 = c0; x.ch1 = c0 + take; x.slot = n_slots++;
+            lists[c].push_back(x);
+            ++merges.back().nparts;
+            load[c] += take;
+            c0 += take;
+            if (c0 == t.ch1) { c0 = 0; ++ri; split_open = false; }
+        }
+    }
+    (void)split_open;
+    work.assign((size_t)grid, TcWork{0, 0, 0, 0, 0, -1, 0, 0});
+    for (int c = 0; c < grid; ++c) {
+        work[c].b = (int)work.size();
+        work.insert(work.end(), lists[c].begin(), lists[c].end());
+        work[c].j0 = (int)work.size();
+    }
+}
+
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, HostStage& stage, cudaStream_t st) {
+    if (!w.packed) return "weights not packed";
+    std::vector<int> ntok((size_t)B);
+    for (int b = 0; b < B; ++b) ntok[b] = sd[b].n_actor + sd[b].n_lane + 1;
+    std::vector<TcWork> work;
+    std::vector<TcMerge> merges;
+    int n_slots = 0, grid = 1;
+    tc_build_schedule(ntok.data(), B, w.sm_count, work, merges, n_slots, grid);
+    w.grid = grid;
     if ((int)work.size() > w.work_cap) {
         if (w.d_work) cudaFree(w.d_work);
         if (cudaMalloc(&w.d_work, work.size() * sizeof(TcWork)) != cudaSuccess) return "cudaMalloc(work) failed";
@@ -1194,7 +1308,8 @@ const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, in
         if (const char* e = stage.upload(w.d_merge, merges.data(), merges.size() * sizeof(TcMerge), st)) return e;
     }
     if (w.emap_ptr != edge16 || w.emap_B != B || w.emap_N != Nmax) {
-        if (const char* e = make_map_edge(w.emap, edge16, B, Nmax)) return e;
+        if (const char* e = make_map_edge(w.emap, edge16, B, Nmax, 16, 8)) return e;
+        if (const char* e = make_map_edge(w.emapq, edge16, B, Nmax, 1, 128)) return e;
         w.emap_ptr = edge16; w.emap_B = B; w.emap_N = Nmax;
     }
     w.B = B; w.Nmax = Nmax;
@@ -1211,16 +1326,18 @@ const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* a
     tc::LayerArgs a;
     a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn_hi = attn_hi; a.attn_lo = attn_lo;
     a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err; a.part = w.d_part;
-    const int grid = std::max(1, std::min(w.n_work, sm_count));
+    const int grid = w.grid;
+    (void)sm_count;
     if (w.tmap_ptr != stq || w.tmap_rows != (int64_t)w.B * w.Nmax) {
         if (const char* e = make_map_stq(w.tmap, stq, (int64_t)w.B * w.Nmax)) return e;
         w.tmap_ptr = stq; w.tmap_rows = (int64_t)w.B * w.Nmax;
     }
-    CUtensorMap em, wm, tm;
+    CUtensorMap em, eq, wm, tm;
     memcpy(&em, w.emap, sizeof em);
+    memcpy(&eq, w.emapq, sizeof eq);
     memcpy(&wm, w.layer[layer].wmap, sizeof wm);
     memcpy(&tm, w.tmap, sizeof tm);
-    tc::k_rela_fusion_tc<<<grid, tc::kThreads, tc::SMEM_BYTES, st>>>(em, wm, tm, a);
+    tc::k_rela_fusion_tc<<<grid, tc::kThreads, tc::SMEM_BYTES, st>>>(em, eq, wm, tm, a);
     ++g_launches;
     if (w.n_merge > 0) {
         tc::k_merge_parts<<<w.n_merge * 16, 128, 0, st>>>(w.d_merge, w.d_part, w.layer[layer].params, attn_hi, attn_lo, w.Nmax);

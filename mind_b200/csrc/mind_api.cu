@@ -1019,6 +1019,20 @@ extern "C" int mind_tc_selftest(const float* A_host, const float* W_host, float*
     return 0;
 }
 
+extern "C" int mind_debug_fusion_schedule(const int32_t* n_tokens, int32_t B, int32_t sm_count, int32_t* work_out,
+                                          int32_t capacity, int32_t* info) {
+    if (!n_tokens || B <= 0 || sm_count <= 0 || !info) return fail("mind_debug_fusion_schedule: bad argument");
+    std::vector<TcWork> work;
+    std::vector<TcMerge> merges;
+    int n_slots = 0, grid = 1;
+    tc_build_schedule(n_tokens, B, sm_count, work, merges, n_slots, grid);
+    info[0] = (int32_t)work.size(); info[1] = grid; info[2] = (int32_t)merges.size(); info[3] = n_slots;
+    if (!work_out || capacity < (int32_t)work.size()) return -1;
+    static_assert(sizeof(TcWork) == 32, "TcWork is 8 int32");
+    memcpy(work_out, work.data(), work.size() * sizeof(TcWork));
+    return 0;
+}
+
 // ---- batched host->device staging (reference: gpu(), planners/mind/utils.py:9-20) ----
 extern "C" int64_t mind_upload_packed_bytes(const int64_t* bytes, int32_t n) {
     if (!bytes || n < 0) return -1;

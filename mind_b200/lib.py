@@ -49,7 +49,7 @@ class MindTreeUpdate(C.Structure):
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
-           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_sync_check", "mind_profile_read",
+           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_sync_check", "mind_profile_read",
            "mind_tree_level", "mind_tree_update", "mind_tree_last_error"]
 
 _lib = None
@@ -95,6 +95,9 @@ def load(build_if_missing: bool = True):
     lib.mind_graph_replays.restype = C.c_int64
     lib.mind_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mind_tc_selftest.restype = C.c_int
+    lib.mind_debug_fusion_schedule.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                               C.POINTER(C.c_int32)]
+    lib.mind_debug_fusion_schedule.restype = C.c_int
     lib.mind_sync_check.argtypes = [C.c_void_p]
     lib.mind_sync_check.restype = C.c_int
     lib.mind_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
