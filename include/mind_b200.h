@@ -164,7 +164,9 @@ typedef struct {
     float tar_time_ahead;
     const int32_t* src;
     const float *cpos, *cang, *cvel, *ccov;
-    const float* ttype;                     /* [Na,7] actor type one-hot */
+    const float* ttype;                     /* [Na,50,7] TRAJS_TYPE of the ROOT observation, per step: the reference carries
+                                             * it unchanged into every child scene (scenario_tree.py:486,524), including the
+                                             * all-zero rows of steps at which the actor was not observed */
     const float *lane_ctrs, *lane_vecs;     /* [Nl,2] anchors of the stored lane graph */
     const float *tlane, *tinfo;             /* [n_tlane,2], [n_tlane,12] */
     float *npos, *nang, *nvel, *ncov, *norig, *nrot, *nctrs, *nvecs;

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) k_tree_update(MindTreeUpdate u) {
                 feat[0 * 48 + tt] = px - ppx; feat[1 * 48 + tt] = py - ppy;     // displacement (first step would be 0)
                 feat[2 * 48 + tt] = cosf(an); feat[3 * 48 + tt] = sinf(an);
                 feat[4 * 48 + tt] = vx; feat[5 * 48 + tt] = vy;
-                for (int c7 = 0; c7 < 7; ++c7) feat[(6 + c7) * 48 + tt] = u.ttype[i * 7 + c7];
+                for (int c7 = 0; c7 < 7; ++c7) feat[(6 + c7) * 48 + tt] = u.ttype[((int64_t)i * 50 + t) * 7 + c7];   // root's per-step rows (:486,524)
                 feat[13 * 48 + tt] = 1.f;
             }
             ppx = px; ppy = py;

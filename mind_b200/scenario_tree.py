@@ -224,7 +224,7 @@ class ScenarioTreeGeneratorB200:
                  ("orig", orig, (1, 2)), ("rot", rot, (1, 4)), ("ctrs", ctrs, (1, Na, 2)), ("vecs", vecs, (1, Na, 2)),
                  ("pprob", torch.ones(1), (1,)),
                  ("tgt_pts", cpu(data["TGT_PTS"][0]), (1, 11, 2)),
-                 ("ttype", cpu(tj["TRAJS_TYPE"])[:, 0, :], None),
+                 ("ttype", cpu(tj["TRAJS_TYPE"]), None),           # [Na,50,7]: carried per step into every child scene (:486,524)
                  ("lane_ctrs", cpu(graph["lane_ctrs"]), None), ("lane_vecs", cpu(graph["lane_vecs"]), None)]
         flat = [t.reshape(-1) for _, t, _ in parts]
         sizes = [((f.numel() + 63) // 64) * 64 for f in flat]            # 256-byte aligned pieces
