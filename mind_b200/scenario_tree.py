@@ -122,7 +122,7 @@ class ScenarioTreeGeneratorB200:
         self._lib = _lib.load()
         self._levels: List[_Level] = []
         self.timing = {}                # seconds per phase of the last rollout (host wall clock)
-        self.front_end = None           # optional callable (lcl_smp, agent_obs) -> collated scene dict
+        self.front_end = None           # callable (lcl_smp, agent_obs) -> collated scene dict; default ArgoFrontEnd
         # benchmark mode: keep all 6 modes of every scene, branch at fixed times
         self.force_full = None          # e.g. (10, 20, 30): children of level d branch at force_full[d]
         # device buffers that feed the network, kept across rollouts per (level, frontier size): stable pointers let
@@ -147,11 +147,12 @@ class ScenarioTreeGeneratorB200:
         return self.rollout(data)
 
     def process_data(self, lcl_smp, agent_obs):
-        """:122-206 is the av2 / shapely front end (out of this path's scope); plug the
-        reference's own process_data (or any equivalent) in through `front_end`."""
+        """:122-206: observation tracks + static map -> collated scene dict.  Default: mind_b200.front_end.ArgoFrontEnd
+        (host restatement with the map-dependent work cached per map); any callable (lcl_smp, agent_obs) -> dict can
+        be plugged in through `front_end`, e.g. the reference's own bound process_data."""
         if self.front_end is None:
-            raise NotImplementedError("process_data needs av2/shapely; set generator.front_end = callable returning the "
-                                      "collated scene dict, or call rollout(data)")
+            from .front_end import ArgoFrontEnd
+            self.front_end = ArgoFrontEnd(self)
         return self.front_end(lcl_smp, agent_obs)
 
     def _buf(self, key, name, shape, dtype=torch.float32):

@@ -89,6 +89,7 @@ class TreeOracle:
 
     def reset(self):
         self.branch_depth = 0
+        self.merge_margins = []
         self.tree = Tree()
         self.net_batches = []
 
@@ -225,6 +226,9 @@ class TreeOracle:
             while cands:                                                   # greedy merge (:396-410)
                 sel, st = cands[0]
                 res.append(sel)
+                # test infrastructure: how far each keep / merge decision sits from the pi/6 threshold (rad); a tree whose
+                # smallest |margin| is below the noise of the inputs has no well-defined node set
+                self.merge_margins += [(self.branch_depth, b, float((wrap(st - c[1]).abs() - math.pi / 6).max())) for c in cands[1:]]
                 cands = [c for c in cands[1:] if bool(((wrap(st - c[1]).abs() - math.pi / 6) > 0).sum() > 0)]
         return res
 

