@@ -166,6 +166,31 @@ def bench_tree(net, dev, reps=5):
         out[name] = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches),
                      "nodes": gen.tree.size(), "trees": len(trees),
                      "host_phase_ms_last": {k: round(v * 1e3, 3) for k, v in gen.timing.items()}}
+    # BASELINE.json configs[2] itself: the demo_2 Argoverse-2 scene (45 actors x 37 lane polylines at sim time 5.0 s) as
+    # the unmodified reference's process_data built it (tests/golden/real_demo_2.pt, oracle/make_golden_real.py)
+    fx = os.path.join(ROOT, "tests", "golden", "real_demo_2.pt")
+    if os.path.exists(fx):
+        gold = torch.load(fx, weights_only=False)
+        for name, ff in (("demo_2_natural", None), ("demo_2_forced_full", (10, 20, 30))):
+            gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
+            gen.force_full = ff
+            times = []
+            try:
+                for r in range(reps + 2):
+                    data = copy.deepcopy(gold["data"])
+                    gen.reset(); gen.set_target_lane(gold["lane"], gold["info"]); gen.lane_graph = copy.deepcopy(gold["graph"])
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    trees = gen.rollout(data)
+                    torch.cuda.synchronize()
+                    times.append((time.perf_counter() - t0) * 1e3)
+            except Exception as e:                                  # reported, never fatal for the headline line
+                out[name] = {"error": repr(e)[:300]}
+                continue
+            out[name] = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches),
+                         "nodes": gen.tree.size(), "trees": len(trees), "actors": int(gold["data"]["ACTORS"].shape[0]),
+                         "lane_polylines": int(gold["data"]["LANES"].shape[0]), "input": "host tensors (collated scene dict on the CPU)",
+                         "host_phase_ms_last": {k: round(v * 1e3, 3) for k, v in gen.timing.items()}}
     return out
 
 
@@ -396,7 +421,7 @@ def run_native(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "stage_ms_per_step": stage_ms,
-            "tree_rollout": {"unit": "ms/scene", "scene": "S3 kinematic, 8 actors x 60 lane polylines", **tree}}
+            "tree_rollout": {"unit": "ms/scene", "scene": "natural / forced_full: S3 kinematic, 8 actors x 60 lane polylines; demo_2_*: the Argoverse-2 demo_2 scene of BASELINE.json configs[2]", **tree}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -380,7 +380,13 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
     const uint32_t bar_m1 = bar_w + 8, bar_m2a = bar_w + 16, bar_m2b = bar_w + 24, bar_ld0 = bar_w + 32;   // +32, +40
     const uint32_t bar_a = bar_w + 48, bar_e = bar_w + 56, bar_t = bar_w + 64, bar_k = bar_w + 72;
 
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (TMEM
+    // addresses, barrier ids, role tests) in uniform registers instead of an R2UR in front of every tcgen05.ld / st
+#ifdef MIND_EXP_NOUNI      // A/B build: plain warp index
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#else
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+#endif
     if (tid == 0) {
         mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2a, 1); mbar_init(bar_m2b, 1);
         mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
@@ -984,7 +990,9 @@ k_tc_selftest(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + 65536 + 64);
     const uint32_t bar_l = sbase + 65536, bar_m = bar_l + 8, bar_m2 = bar_l + 16;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (TMEM
+    // addresses, barrier ids, role tests) in uniform registers instead of an R2UR in front of every tcgen05.ld / st
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) { mbar_init(bar_l, 1); mbar_init(bar_m, 1); mbar_init(bar_m2, 1); fence_barrier_init(); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + 65536 + 64), "r"(256u) : "memory");
