@@ -460,7 +460,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
             }
             while (true) {
                 const int buf = g & 1;
-                const uint32_t par = g & 1;
                 const bool has_next = tile_valid(nxt);
                 // [A] A operand of this tile is in TMEM -> G2 (W_pe first: its epilogue overlaps the K|V MMAs)
                 TR(15, g);
@@ -548,7 +547,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
         const uint32_t tile_off = (uint32_t)(q >> 1) * 16384u;      // k-block of this quarter inside an edge tile
         const int chunk0 = (q & 1) * 4;                              // first 16-byte chunk of this quarter in its k-block
         const float* Pm = sP;
-        const uint32_t aS = sbase + SM_S, aQ = sbase + SM_Q, aT = sbase + SM_T, aP = sbase + SM_P;
         uint32_t g = 0;                                              // tiles processed by this CTA
         for (int wi = wi_begin; wi < wi_end; ++wi) {
             const TcWork wk = a.work[wi];

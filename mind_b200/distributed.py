@@ -47,3 +47,39 @@ def all_gather_predictions(cls: torch.Tensor, reg: torch.Tensor, vel: torch.Tens
     """The path's single collective: every rank ends with all scenes' (cls [B,6], reg [A,6,60,5],
     vel [A,6,60,2]) in scene order."""
     return all_gather_rows(cls, group), all_gather_rows(reg, group), all_gather_rows(vel, group)
+
+
+# ---- tree mode (SURVEY.md 8e): the frontier of one depth level sharded over ranks ------------------------------
+def shard_level_inputs(net_in, geom, n_frontier: int, rank: int, world: int):
+    """Contiguous block of frontier scenes for `rank`.  `net_in` is the level's network input tuple
+    (actors [F*Na,14,48], actor index lists, lanes [F*Nl,10,16], lane index lists, rpe | None, tgt_nodes [F,10,16],
+    tgt_rpe [F,20]); all scenes of a level have the same actor / lane counts (they are copies of one root scene), so
+    the shard is a set of views: no copy.  `geom` = (ctrs, vecs) [F*(Na+Nl), 2] or None.  Returns (net_in, geom, (s, e))."""
+    actors, a_idcs, lanes, l_idcs, rpe, tgt_nodes, tgt_rpe = net_in[:7]
+    F = n_frontier
+    s, e = shard_range(F, rank, world)
+    na, nl = actors.shape[0] // F, lanes.shape[0] // F
+    if actors.shape[0] != F * na or lanes.shape[0] != F * nl:
+        raise ValueError("level inputs are not uniform over the frontier")
+    sub = (actors[s * na:e * na], list(a_idcs[s:e]), lanes[s * nl:e * nl], list(l_idcs[s:e]),
+           None if rpe is None else list(rpe[s:e]), tgt_nodes[s:e], tgt_rpe[s:e])
+    g = None
+    if geom is not None:
+        m = geom[0].shape[0] // F
+        g = (geom[0][s * m:e * m], geom[1][s * m:e * m])
+    return sub, g, (s, e)
+
+
+def sharded_level_forward(forward, net_in, geom, n_frontier: int, group=None):
+    """One depth level of the scenario tree on all ranks: every rank predicts its block of the frontier with
+    `forward(net_in, geom) -> (cls [f,6], reg [f*Na,6,60,5], vel [f*Na,6,60,2], ...)` and ONE all-gather of the decoded
+    outputs leaves every rank with the whole level, in frontier order.  The tree bookkeeping that follows (prune / merge /
+    branch decisions) is replicated: all ranks see identical gathered tensors and therefore build identical trees.
+    Falls back to a replicated forward when the frontier is smaller than the world (root, natural trees)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1 or n_frontier < world:
+        out = forward(net_in, geom)
+        return out[0], out[1], out[2]
+    sub, g, _ = shard_level_inputs(net_in, geom, n_frontier, dist.get_rank(group), world)
+    out = forward(sub, g)
+    return all_gather_predictions(out[0], out[1], out[2], group)

@@ -129,6 +129,8 @@ class ScenarioTreeGeneratorB200:
         # the library replay one captured CUDA graph per level instead of ~170 launches (mind_set_option "graph")
         self._pool = {}
         self.graphs = True
+        # one process per GPU: shard every level's frontier over the ranks of `group` (torch.distributed, NCCL)
+        self.distributed, self.group = False, None
         self._graphs_on = False
 
     # ---- reference surface ------------------------------------------------------------------
@@ -293,7 +295,14 @@ class ScenarioTreeGeneratorB200:
 
     def predict_scenes(self, level: _Level):                                      # :69-71 (one batched call per level)
         self.net_batches.append(level.F)
-        pk = self.network.forward_packed(level.net_in, geom=level.geom, persistent_out=True)
+        if self.distributed:
+            # tree mode of SURVEY.md 8e: frontier sharded over ranks, one all-gather of (cls, reg, vel) per level;
+            # frontiers smaller than the world are predicted replicated
+            from .distributed import sharded_level_forward
+            fwd = lambda net_in, geom: self.network.forward_packed(net_in, geom=geom, persistent_out=True)
+            pk = sharded_level_forward(fwd, level.net_in, level.geom, level.F, self.group)
+        else:
+            pk = self.network.forward_packed(level.net_in, geom=level.geom, persistent_out=True)
         level.cls, level.reg, level.vel = pk[0], pk[1], pk[2]
         return pk
 
