@@ -29,6 +29,8 @@ from oracle.tree_oracle import flatten_trees
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT_DIR = os.path.join(ROOT, "tests", "golden")
 DEMOS = {"demo_1": 5.0, "demo_2": 5.0, "demo_3": 5.0, "demo_4": 5.0}      # sim time of the captured plan call
+# the closed-loop agent's FIRST plan call (enable_timestep 4.0 s): only 41 observed steps, every track is front-padded
+EXTRA = {"demo_3_t4": ("demo_3", 4.0)}
 
 
 def load_reference_sim():
@@ -125,6 +127,8 @@ def main():
     ns = load_reference_sim()
     for name, t_plan in DEMOS.items():
         torch.save(capture(ns, name, t_plan), os.path.join(OUT_DIR, "real_%s.pt" % name))
+    for tag, (name, t_plan) in EXTRA.items():
+        torch.save(capture(ns, name, t_plan), os.path.join(OUT_DIR, "real_%s.pt" % tag))
 
 
 if __name__ == "__main__":

@@ -90,6 +90,7 @@ class TreeOracle:
     def reset(self):
         self.branch_depth = 0
         self.merge_margins = []
+        self.prune_margins = []
         self.tree = Tree()
         self.net_batches = []
 
@@ -211,11 +212,16 @@ class TreeOracle:
                            TRAJS_ANG_HIST=torch.cat([data["TRAJS_ANG_HIST"][b], ang], 1)[:, :self.seq_len],
                            TRAJS_VEL_HIST=torch.cat([data["TRAJS_VEL_HIST"][b], vel], 1)[:, :self.seq_len],
                            TGT_PTS=data["TGT_PTS"][b])
+                # test infrastructure: distance of every prune decision from its threshold (relative for the probability,
+                # metres for the target-lane test), next to merge_margins
+                self.prune_margins.append((self.branch_depth, b, "prob", float(cur["SCEN_PROB"]) / 0.001 - 1.0))
                 if cur["SCEN_PROB"] < 0.001:
                     continue
                 if self.target_lane is not None and self.ego_idx is not None:
                     ego_mean = cur["TRAJS_POS_HIST"][self.ego_idx][-1]
                     ego_cov = cur["TRAJS_COV_HIST"][self.ego_idx][-1]
+                    over = dist_to_polyline(self.target_lane, ego_mean) - ego_cov - self.config.tar_dist_thres
+                    self.prune_margins.append((self.branch_depth, b, "lane", float(over)))
                     if dist_to_polyline(self.target_lane, ego_mean) - ego_cov > self.config.tar_dist_thres:
                         continue
                 rel = pos[1:] - pos[0:1]                                   # exo - ego over the 60 predicted steps

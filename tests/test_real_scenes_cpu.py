@@ -14,6 +14,8 @@ from conftest import GOLDEN, rel_err
 from test_tree_oracle import OracleNet, TreeCfg
 
 DEMOS = ["demo_1", "demo_2", "demo_3", "demo_4"]
+# the closed-loop agent's first plan call (sim time 4.0 s): 41 observed steps, every track front-padded, 6 first-level nodes
+FIRST_PLAN = ["demo_3_t4"]
 
 
 def load_real(name):
@@ -49,6 +51,42 @@ def compare_tree(flat, levels, gold, tol):
         assert np.abs(np.asarray(g[4]) - np.asarray(tgt)).max() < 1e-4 * max(1.0, np.abs(np.asarray(tgt)).max())
 
 
+def oracle_margins(ckpt_sd, gold):
+    """merge decisions of the oracle tree on this scene: [(depth, scene, margin in rad from the pi/6 threshold)]"""
+    from oracle.tree_oracle import TreeOracle
+    t = TreeOracle(OracleNet(ckpt_sd), 50, 50, TreeCfg())
+    t.reset()
+    t.set_target_lane(gold["lane"], gold["info"])
+    t.lane_graph = copy.deepcopy(gold["graph"])
+    t.rollout(copy.deepcopy(gold["data"]))
+    return t.merge_margins
+
+
+def compare_tree_with_margins(flat, levels, gold, tol, margins, delta=0.15):
+    """compare_tree, except that a node may be present on one side only when its parent scene has a greedy-merge decision
+    (:396-410) within `delta` rad of the pi/6 threshold.  The topology signature is the angle swept by (exo - ego); at
+    depth >= 1 the reference's own fp32 noise on positions is ~0.1 m (see compare_tree), i.e. ~0.1 rad for an actor 1-2 m
+    from the ego, so such a decision has no well-defined outcome.  A flip is only tolerated where it does not renumber
+    the next frontier (equal level sizes); returns the tolerated keys."""
+    fragile = {(d, b) for d, b, m in margins if abs(m) < delta}
+    want = gold["tree"]
+    odd = sorted(set(flat) ^ set(want))
+    if not odd:
+        compare_tree(flat, levels, gold, tol)
+        return []
+    assert list(levels) == list(gold["levels"]), "a flipped decision changed the frontier sizes"
+    for k in odd:
+        d, b, _ = (int(x) for x in k.split("_"))
+        assert (d, b) in fragile, "node %s differs although no merge decision of scene (%d, %d) is near its threshold" % (k, d, b)
+    common = {k: v for k, v in want.items() if k in flat}
+    # sibling probabilities are renormalised over the kept siblings (:240-262): a flip changes them for that family
+    fam = {want.get(k, flat.get(k))[0] for k in odd}
+    fam |= {flat[k][0] for k in odd if k in flat}
+    keep = {k: v for k, v in common.items() if v[0] not in fam}
+    compare_tree({k: flat[k] for k in keep}, levels, dict(gold, tree=keep), tol)
+    return odd
+
+
 def coord_ulp(gold):
     """fp32 spacing at the scene's global coordinates (the reference's own resolution limit for level >= 1 inputs)"""
     return float(np.spacing(np.float32(np.abs(gold["data"]["ORIG"][0].numpy()).max())))
@@ -71,7 +109,7 @@ def compare_level_inputs(got, want, ulp):
         assert (r1.float().cpu() - r2.float()).abs().max() < 2e-3, "RPE"   # values up to ~70 (root-frame lanes, utils.py:171-177)
 
 
-@pytest.mark.parametrize("name", DEMOS)
+@pytest.mark.parametrize("name", DEMOS + FIRST_PLAN)
 def test_oracle_forward_on_real_scene(ckpt_sd, name):
     from oracle.scene_pred_oracle import ScenePredOracle
     gold = load_real(name)
@@ -82,7 +120,7 @@ def test_oracle_forward_on_real_scene(ckpt_sd, name):
     assert rel_err(reg[0], gold["reg"][0]) < 5e-5 and rel_err(aux[0][0], gold["vel"][0]) < 5e-5
 
 
-@pytest.mark.parametrize("name", DEMOS)
+@pytest.mark.parametrize("name", DEMOS + FIRST_PLAN)
 def test_oracle_tree_on_real_scene(ckpt_sd, name):
     from oracle.tree_oracle import TreeOracle, flatten_trees
     gold = load_real(name)
@@ -91,10 +129,11 @@ def test_oracle_tree_on_real_scene(ckpt_sd, name):
     t.set_target_lane(gold["lane"], gold["info"])
     t.lane_graph = copy.deepcopy(gold["graph"])
     flat = flatten_trees(t.rollout(copy.deepcopy(gold["data"])))
-    compare_tree(flat, t.net_batches, gold, 1e-4)
+    flips = compare_tree_with_margins(flat, t.net_batches, gold, 1e-4, t.merge_margins)
+    assert flips == ([] if name in DEMOS else ["1_0_3"])      # first-plan scene: one decision 0.06 rad from its threshold
 
 
-@pytest.mark.parametrize("name", DEMOS)
+@pytest.mark.parametrize("name", DEMOS + FIRST_PLAN)
 def test_oracle_level_inputs_on_real_scene(ckpt_sd, name):
     """update_obser (:467-567) of the oracle tree vs the level inputs the reference built, to a few ulp of the coordinates"""
     from oracle.tree_oracle import TreeOracle
