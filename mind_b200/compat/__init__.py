@@ -1,7 +1,8 @@
 """Minimal stand-ins for the third-party packages MIND imports around the hot path.
 
 The reference needs `av2==0.2.1` (map JSON -> lane segments / 10-point centrelines, scenario parquet -> tracks),
-`shapely==2.0.6` (arc-length resampling of centrelines) and `Theano` (iLQR Jacobians; not covered here).  None of them
+`shapely==2.0.6` (arc-length resampling of centrelines) and `Theano==1.0.5` (symbolic bicycle model -> f, f_x, f_u of the
+tree iLQR).  None of them
 is a hot-path dependency, but without them `ScenarioTreeGenerator.process_data`, `SemanticMap` and `ArgoAgentLoader`
 cannot be imported, so real Argoverse-2 scenes cannot reach the predictor.  `install()` registers pure numpy / pandas
 implementations of exactly the API surface MIND touches under the original module names, unless the real packages are
@@ -51,4 +52,12 @@ def install(force: bool = False) -> dict:
         used["shapely"] = "lite"
     else:
         used["shapely"] = "real"
+    if force or not _have("theano"):
+        from . import theano_lite
+        pk = types.ModuleType("theano"); pk.__path__ = []
+        pk.tensor, pk.function = theano_lite.tensor, theano_lite.function
+        sys.modules.update({"theano": pk, "theano.tensor": theano_lite.tensor})
+        used["theano"] = "lite"
+    else:
+        used["theano"] = "real"
     return used

@@ -3,8 +3,9 @@ reference: SemanticMap, ArgoAgentLoader, the agents' replay loop of simulator.py
 resample_target_lane, ScenarioTreeGenerator.process_data, ScenePredNet and branch_aime.      python -m oracle.make_golden_real
 
 Test infrastructure, build container only (needs /root/reference).  av2 / shapely come from mind_b200.compat (the real
-packages are not in the image: that boundary is parity-unpinned); Theano is stubbed, so the iLQR half of the planner is
-never constructed and the ego vehicle stays on its recorded trajectory (open loop).  At sim time T the script does
+packages are not in the image: that boundary is parity-unpinned).  The closed-loop agent is never enabled here, so the
+ego vehicle stays on its recorded trajectory (open loop; oracle/run_closed_loop.py drives it closed loop).  At sim time T
+the script does
 exactly what MINDPlanner.plan does up to the scenario trees (planner.py:104-112).
 
 Writes tests/golden/real_<demo>.pt per demo scene:
@@ -35,10 +36,7 @@ EXTRA = {"demo_3_t4": ("demo_3", 4.0)}
 
 def load_reference_sim():
     from mind_b200 import compat
-    compat.install()
-    for name in ("theano", "theano.tensor"):                  # imported at module level by planners/ilqr/*, never called here
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["theano"].tensor = sys.modules["theano.tensor"]
+    compat.install()                                          # av2 / shapely / theano stand-ins where the real ones are absent
     if ref_loader.REF_ROOT not in sys.path:
         sys.path.insert(0, ref_loader.REF_ROOT)
     import importlib
@@ -48,8 +46,6 @@ def load_reference_sim():
     ns.agent = importlib.import_module("agent")
     ns.loader = importlib.import_module("loader")
     ns.utils = importlib.import_module("planners.mind.utils")
-    # the trajectory-tree optimiser needs Theano: leave it out (the scenario-tree half is complete without it)
-    ns.planner.MINDPlanner.init_traj_tree_opt = lambda self: None
     return ns
 
 

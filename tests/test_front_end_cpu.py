@@ -123,3 +123,56 @@ def test_front_end_vs_reference_process_data(name):
         _same(got, gold["data"])
         _same(gen.lane_graph, gold["graph"])
     assert len(fe._maps) == 1
+
+
+def test_theano_lite_bicycle_model_jacobians():
+    """the symbolic slice MIND's tree iLQR needs (trajectory_tree.py:153-177 through ilqr/autodiff.py): exact Jacobians of
+    the 6-state kinematic bicycle model, checked against central finite differences; numpy scalars mix into expressions"""
+    from mind_b200.compat import theano_lite as TL
+    T = TL.tensor
+    dt, wb = np.float64(0.2), 2.5
+    x = [T.dscalar(n) for n in ("x", "y", "v", "q", "a", "theta")]
+    u = [T.dscalar(n) for n in ("da", "dtheta")]
+    i = T.dscalar("i")
+    f = T.stack([x[0] + x[2] * T.cos(x[3]) * dt, x[1] + x[2] * T.sin(x[3]) * dt, x[2] + x[4] * dt,
+                 x[3] + x[2] / wb * T.tan(x[5]) * dt, x[4] + u[0] * dt, x[5] + u[1] * dt])
+    inputs = np.hstack([x, u, i]).tolist()                                   # dynamics.py:167-168
+    wrt = np.hstack([x, u]).tolist()
+    J = T.stack([T.grad(f[k], wrt, disconnected_inputs="ignore") for k in range(6)])     # autodiff.jacobian_vector
+    F = TL.function(inputs, f, on_unused_input="ignore", name="f")
+    Fx = TL.function(inputs, J[:, :6], on_unused_input="ignore", name="f_x")
+    Fu = TL.function(inputs, J[:, 6:], on_unused_input="ignore", name="f_u")
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        z = np.concatenate([rng.normal(size=3) * 5, rng.uniform(-1, 1, 3), rng.normal(size=2), [0.0]])
+        fz = F(*z)
+        assert fz.shape == (6,) and abs(fz[0] - (z[0] + z[2] * np.cos(z[3]) * 0.2)) < 1e-12
+        num = np.zeros((6, 8))
+        for k in range(8):
+            e = np.zeros(9); e[k] = 1e-6
+            num[:, k] = (F(*(z + e)) - F(*(z - e))) / 2e-6
+        assert Fx(*z).shape == (6, 6) and Fu(*z).shape == (6, 2)
+        assert np.abs(Fx(*z) - num[:, :6]).max() < 1e-6 and np.abs(Fu(*z) - num[:, 6:]).max() < 1e-6
+    with pytest.raises(NotImplementedError):
+        T.dvector("v")
+    with pytest.raises(NotImplementedError):
+        T.grad(cost=None, wrt=x, known_grads={})
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs the reference tree (build container only)")
+def test_reference_trajectory_optimizer_builds_on_theano_lite():
+    """the UNMODIFIED TrajectoryTreeOptimizer constructs its AutoDiffDynamics on the stand-in and reproduces one Euler step"""
+    import sys
+    from mind_b200 import compat
+    assert compat.install()["theano"] in ("lite", "real")
+    if ref_loader.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REF_ROOT)
+    from planners.mind.trajectory_tree import TrajectoryTreeOptimizer
+    from planners.mind.configs.planning.demo_1 import TrajTreeCfg
+    cfg = TrajTreeCfg()
+    dyn = TrajectoryTreeOptimizer(cfg).ilqr.dynamics
+    x, u = np.array([1.0, 2.0, 5.0, 0.3, 0.5, 0.1]), np.array([0.2, -0.1])
+    nxt = dyn.f(x, u, 0)
+    want = np.array([x[0] + x[2] * np.cos(x[3]) * cfg.dt, x[1] + x[2] * np.sin(x[3]) * cfg.dt, x[2] + x[4] * cfg.dt,
+                     x[3] + x[2] / 2.5 * np.tan(x[5]) * cfg.dt, x[4] + u[0] * cfg.dt, x[5] + u[1] * cfg.dt])
+    assert np.abs(nxt - want).max() < 1e-12 and dyn.f_x(x, u, 0).shape == (6, 6) and dyn.f_u(x, u, 0).shape == (6, 2)
