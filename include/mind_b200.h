@@ -175,6 +175,35 @@ typedef struct {
 int mind_tree_update(const MindTreeUpdate* u, void* cuda_stream);
 const char* mind_tree_last_error(void);
 
+/* ---- cost fields of the trajectory-tree optimiser (the step right after the scenario tree) -------
+ * mind_cost_fields  replaces gen_dist_field (planners/ilqr/utils.py:5-22) and the per-node field assembly of
+ * TrajectoryTreeOptimizer.init_warm_start_cost_tree / init_cost_tree (planners/mind/trajectory_tree.py:20-56, :58-124).
+ * Grid: gx columns x gy rows of cell centres, cell (r, c) at (xs[c], ys[r]); the caller forms xs / ys with the
+ * reference's own linspace + offset (utils.py:7-14) so that the coordinates are the same doubles.
+ *   quad [gy,gx]            = (min over polyline segments of the clamped point-segment distance)^2
+ *   fields [n_nodes,gy,gx]  = coef_tgt[n] * quad
+ *                             + w_exo * sum_{e>=1} g(radius[n,e] - |p - mean[n,e]|),  g(f) = f + exo_cost_offset if f > 0 else 0
+ *                             + w_ego * max(|p - mean[n,0]| - radius[n,0], 0)
+ * n_actor = 0 gives the warm-start fields (first term only).  The caller forms coef_tgt = w_tgt * prob and
+ * radius = cov + offset exactly as the reference does (fp32 sums) and passes them as fp64; node order = creation
+ * order of the trajectory tree.  All arrays are DEVICE pointers, fp64 (the reference computes these in numpy fp64).
+ * Asynchronous on the stream; error text from mind_cost_fields_last_error(). */
+typedef struct {
+    int32_t gx, gy;
+    const double *xs, *ys;       /* [gx], [gy] cell-centre coordinates */
+    int32_t n_lane_pts;
+    const double* lane;          /* [n_lane_pts,2] target lane */
+    int32_t n_nodes, n_actor;
+    const double* coef_tgt;      /* [n_nodes] */
+    const double* mean;          /* [n_nodes,n_actor,2], actor 0 = ego */
+    const double* radius;        /* [n_nodes,n_actor] */
+    double w_ego, w_exo, exo_cost_offset;
+    double* quad;                /* out [gy,gx] */
+    double* fields;              /* out [n_nodes,gy,gx] */
+} MindCostFields;
+int mind_cost_fields(const MindCostFields* a, void* cuda_stream);
+const char* mind_cost_fields_last_error(void);
+
 /* bring-up self test of the TMA + tcgen05 + TMEM plumbing: D[0:128*128] = A . W^T (fp16 operands,
  * fp32 accumulate), D[128*128: 2*128*128] = the A tile read back through the software swizzle,
  * D[2*128*128: 3*128*128] = the same product with the A operand staged in tensor memory.

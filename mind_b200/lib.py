@@ -39,6 +39,14 @@ class MindTreeLevel(C.Structure):
                                            "keep", "tb")])
 
 
+class MindCostFields(C.Structure):
+    _fields_ = [("gx", C.c_int32), ("gy", C.c_int32), ("xs", C.c_void_p), ("ys", C.c_void_p),
+                ("n_lane_pts", C.c_int32), ("lane", C.c_void_p), ("n_nodes", C.c_int32), ("n_actor", C.c_int32),
+                ("coef_tgt", C.c_void_p), ("mean", C.c_void_p), ("radius", C.c_void_p),
+                ("w_ego", C.c_double), ("w_exo", C.c_double), ("exo_cost_offset", C.c_double),
+                ("quad", C.c_void_p), ("fields", C.c_void_p)]
+
+
 class MindTreeUpdate(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_new", "n_actor", "n_lane", "n_tlane")] + [("tar_time_ahead", C.c_float)] +
                 [(n, C.c_void_p) for n in ("src", "cpos", "cang", "cvel", "ccov", "ttype", "lane_ctrs", "lane_vecs", "tlane",
@@ -50,7 +58,7 @@ class MindTreeUpdate(C.Structure):
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
            "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_sync_check", "mind_profile_read",
-           "mind_tree_level", "mind_tree_update", "mind_tree_last_error"]
+           "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error"]
 
 _lib = None
 
@@ -107,6 +115,9 @@ def load(build_if_missing: bool = True):
     lib.mind_tree_update.argtypes = [C.POINTER(MindTreeUpdate), C.c_void_p]
     lib.mind_tree_update.restype = C.c_int
     lib.mind_tree_last_error.restype = C.c_char_p
+    lib.mind_cost_fields.argtypes = [C.POINTER(MindCostFields), C.c_void_p]
+    lib.mind_cost_fields.restype = C.c_int
+    lib.mind_cost_fields_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

@@ -56,6 +56,17 @@ def main():
         t_ilqr.append(time.perf_counter() - t0)
         return out
     pl.scen_tree_gen.branch_aime, pl.get_traj_tree = timed_branch, timed_traj
+    # finer split of the iLQR half (trajectory_tree.py:20-124 cost trees vs :125-147 solves)
+    opt, t_parts = pl.traj_tree_opt, {}
+    for meth in ("init_warm_start_cost_tree", "init_cost_tree", "warm_start_solve", "solve"):
+        def wrap(fn, key):
+            def run(*a, **k):
+                t0 = time.perf_counter()
+                out = fn(*a, **k)
+                t_parts[key] = t_parts.get(key, 0.0) + time.perf_counter() - t0
+                return out
+            return run
+        setattr(opt, meth, wrap(getattr(opt, meth), meth))
     sim_time, step, plans, n_trees = 0.0, 0.02, 0, []
     min_gap, lane_dev = 1e9, []
     t_start = time.perf_counter()
@@ -87,6 +98,7 @@ def main():
     print("%s: %.1f s simulated in %.1f s wall, %d plan calls (%.0f ms each: scenario tree %.0f ms, tree iLQR %.0f ms over %.1f trees)" %
           (args.demo, sim_time, wall, plans, 1e3 * (sum(t_tree) + sum(t_ilqr)) / max(plans, 1), 1e3 * np.mean(t_tree),
            1e3 * sum(t_ilqr) / max(plans, 1), len(t_ilqr) / max(plans, 1)))
+    print("iLQR half per plan call [ms]:", {k: round(1e3 * v / max(plans, 1), 1) for k, v in t_parts.items()})
     print("ego final state (x, y, v, heading):", np.round(ego.state, 3), "| target velocity", ego.lcl_smp.target_velocity)
     print("closest other agent while enabled: %.2f m; distance to the target lane: mean %.2f m, max %.2f m" %
           (min_gap, float(np.mean(lane_dev)), float(np.max(lane_dev))))
