@@ -1,14 +1,14 @@
 """GPU: mind_cost_fields (csrc/cost_field.cu) vs the oracle and vs the golden fields of the unmodified reference optimiser
 (tests/golden/cost_fields_demo_2.npz), fp64, 1e-12 relative; at the reference's full 256 x 256 grid through
-size-independent properties.  The kernels were written after this round's GPU budget was spent: their first run on
-hardware is the round-end test run, hence the non-strict xfail marker (XPASS = they work)."""
+size-independent properties.  First hardware run (profiles/r01_v8_cost_field_gpu_tests.log): warm-start fields bit-exact,
+full fields within 1.8e-16 relative of the reference's."""
 import numpy as np
 import pytest
 import torch
 
 from test_cost_field_cpu import cfg_of, demo2_tree_objects, demo2_trees, golden
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first run on hardware happens at round end")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("warm", [True, False])
