@@ -194,6 +194,88 @@ def bench_tree(net, dev, reps=5):
     return out
 
 
+def bench_cost_fields(dev, reps=5):
+    """SURVEY.md 8f-3 (the step right after the path): cost fields of the trajectory-tree optimiser for the demo_2 scenario
+    trees at the reference's 256 x 256 x 0.4 m grid (planners/mind/configs/planning/demo_*.py:73-81).  GPU: wall time of
+    mind_b200.cost_field.cost_fields per tree (tables H2D + mind_cost_fields + fields D2H) and CUDA-event time of the two
+    kernels alone; CPU: the oracle's numpy restatement of trajectory_tree.py:58-124 on one tree.  Never fatal."""
+    try:
+        import ctypes as C
+        import numpy as np
+        from mind_b200 import cost_field as CF, lib as L
+        from oracle import cost_field_oracle as O
+        fx = os.path.join(ROOT, "tests", "golden", "real_demo_2.pt")
+        flat = torch.load(fx, weights_only=False)
+        lane, flat = np.asarray(flat["lane"], dtype=np.float64), flat["tree"]
+        kids = {}
+        for k, v in flat.items():
+            kids.setdefault(v[0], []).append(k)
+
+        class N:
+            def __init__(self, k):
+                self.key, self.parent_key, self.children_keys = k, flat[k][0], sorted(kids.get(k, []))
+                self.data = [flat[k][1], flat[k][2], flat[k][3], None]
+
+        class T:
+            def __init__(self, root):
+                self.root, self.nodes = root, {}
+                todo = [root]
+                while todo:
+                    k = todo.pop()
+                    self.nodes[k] = N(k)
+                    todo += self.nodes[k].children_keys
+            get_root = lambda self: self.nodes[self.root]
+            get_node = lambda self, k: self.nodes[k]
+        trees = [T(k) for k in sorted(k for k, v in flat.items() if v[0] is None)]
+        cfg = dict(w_tgt=1.0, w_ego=1.0, w_ego_cov_offset=1.0, w_exo=10.0, w_exo_cov_offset=2.5, w_exo_cost_offset=10.0,
+                   smooth_grid_size=(256, 256), smooth_grid_res=0.4)
+        ego = flat[trees[0].root][2][0, 0]
+        x0 = np.array([ego[0], ego[1], 6.0, 0.1, 0.2, 0.01])
+        wall, nodes = [], 0
+        for r in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nodes = 0
+            for t in trees:
+                nodes += len(CF.cost_fields(t, x0, lane, cfg, dev, warm=False)["links"])
+            torch.cuda.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3 / len(trees))
+        # kernels alone: same tables, device-resident, CUDA events on the launching stream
+        t = trees[0]
+        coef, mean, rad, links, _ = CF.node_tables(t, cfg, False)
+        off, xs, ys = CF.grid_frame(x0, cfg["smooth_grid_size"], cfg["smooth_grid_res"])
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        bufs = [d(xs), d(ys), d(lane), d(coef), d(mean), d(rad), torch.empty(256, 256, dtype=torch.float64, device=dev),
+                torch.empty(len(coef), 256, 256, dtype=torch.float64, device=dev)]
+        a = L.MindCostFields()
+        a.gx, a.gy, a.xs, a.ys, a.n_lane_pts, a.lane = 256, 256, bufs[0].data_ptr(), bufs[1].data_ptr(), len(lane), bufs[2].data_ptr()
+        a.n_nodes, a.n_actor, a.coef_tgt, a.mean, a.radius = len(coef), mean.shape[1], bufs[3].data_ptr(), bufs[4].data_ptr(), bufs[5].data_ptr()
+        a.w_ego, a.w_exo, a.exo_cost_offset, a.quad, a.fields = 1.0, 10.0, 10.0, bufs[6].data_ptr(), bufs[7].data_ptr()
+        lib = L.load()
+        st = torch.cuda.current_stream(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for r in range(3):
+            lib.mind_cost_fields(C.byref(a), C.c_void_p(st.cuda_stream))
+        ev[0].record(st)
+        for r in range(10):
+            lib.mind_cost_fields(C.byref(a), C.c_void_p(st.cuda_stream))
+        ev[1].record(st)
+        torch.cuda.synchronize()
+        k_ms = ev[0].elapsed_time(ev[1]) / 10
+        by = len(coef) * 256 * 256 * 8.0
+        # CPU: numpy restatement on the same tree (the reference's own loop structure), one pass
+        onodes = {k: (n.parent_key, n.data[0], n.data[1], n.data[2], n.children_keys) for k, n in t.nodes.items()}
+        t0 = time.perf_counter()
+        O.cost_fields(onodes, t.root, x0, lane, cfg, warm=False)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        return {"workload": "demo_2 scenario trees (%d trees, %d trajectory-tree nodes, 45 actors), 256x256 cells of 0.4 m, fp64" % (len(trees), nodes),
+                "gpu_ms_per_tree_incl_copies": statistics.median(wall[1:]), "kernels_ms_per_tree": k_ms, "nodes_in_timed_tree": len(coef),
+                "field_bytes_per_tree": by, "achieved_write_gbs": by / (k_ms * 1e-3) / 1e9,
+                "cpu_numpy_ms_per_tree": cpu_ms, "cpu_kind": "port (oracle/cost_field_oracle.py, 1 numpy thread)"}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -406,6 +488,7 @@ def run_native(args):
                 "flops_per_launch": flops, "bytes_per_launch": B * fusion_bytes_per_scene(True)}
     cpu_v, cores, sample = cpu_port_rate(sd)
     tree = bench_tree(net, dev)
+    cost = bench_cost_fields(dev) if rank == 0 else None
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -421,6 +504,7 @@ def run_native(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "stage_ms_per_step": stage_ms,
+            "cost_fields": cost,
             "tree_rollout": {"unit": "ms/scene", "scene": "natural / forced_full: S3 kinematic, 8 actors x 60 lane polylines; demo_2_*: the Argoverse-2 demo_2 scene of BASELINE.json configs[2]", **tree}}
     print(json.dumps(line))
     if world > 1:
