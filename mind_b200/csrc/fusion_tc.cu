@@ -634,6 +634,21 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 const uint32_t tX = sbase + SM_TILE0 + (g & 1) * 32768;  // edge tile (in place -> edge')
                 TR(0, g);
                 mbar_wait(bar_t, par, a.err, E_LOAD_EDGE + 10);          // T rows staged by the issuer
+#ifdef MIND_EXP_STPRE
+                // A/B build for the next round (profiles/r01_v8_stall_analysis.md, item 1): S[j] + T[i] of this thread's 32
+                // channels is formed in the shadow of the wait for G1, so that after the TMEM load one FADD2 per channel pair
+                // remains and no shared-memory load sits on the critical path of epilogue 1.  Not yet run on hardware.
+                f2 st2[16];
+                if (!mode) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        f2 sa, sb, ta, tb;
+                        lds_2f2(sS + (j_l * 132 + col0 + k4 * 4), sa, sb);
+                        lds_2f2(sT + (i_l * 128 + col0 + k4 * 4), ta, tb);
+                        st2[2 * k4] = add2(sa, ta); st2[2 * k4 + 1] = add2(sb, tb);
+                    }
+                }
+#endif
                 mbar_wait(bar_m1, par, a.err, E_MMA1);
                 TR(1, g);
                 tc_fence_after();
@@ -656,6 +671,19 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
+#ifdef MIND_EXP_STPRE
+                            f2 x0, x1;
+                            if constexpr (kQ) {
+                                f2 sa, sb;
+                                lds_2f2(sS + (j_l * 132 + c), sa, sb);
+                                const ulonglong2 tv = __ldg(reinterpret_cast<const ulonglong2*>(Tg + c));
+                                x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), tv.x);
+                                x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tv.y);
+                            } else {
+                                x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), st2[2 * (hf * 4 + k4)]);
+                                x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), st2[2 * (hf * 4 + k4) + 1]);
+                            }
+#else
                             f2 sa, sb, ta, tb;
                             lds_2f2(sS + (j_l * 132 + c), sa, sb);
                             if constexpr (kQ) {
@@ -666,6 +694,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                             }
                             const f2 x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), ta);
                             const f2 x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tb);
+#endif
                             upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
                             upk2u(x1, r[k4 * 4 + 2], r[k4 * 4 + 3]);
                             s1a = add2(s1a, x0); s1b = add2(s1b, x1);
@@ -680,6 +709,16 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 else e1_pass1(std::false_type{});
                 tc_fence_before();
                 TR(2, g);
+#ifdef MIND_EXP_P2PRE
+                // A/B build for the next round (profiles/r01_v8_stall_analysis.md, item 2): LN_mem gamma / beta of the first 16
+                // channels are loaded in front of the row-group barrier instead of behind it.  Not yet run on hardware.
+                f2 pg2[8], pb2[8];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    lds_2f2(sP + (P_MEM_G * 128 + col0 + k4 * 4), pg2[2 * k4], pg2[2 * k4 + 1]);
+                    lds_2f2(sP + (P_MEM_B * 128 + col0 + k4 * 4), pb2[2 * k4], pb2[2 * k4 + 1]);
+                }
+#endif
                 row_group_sync(lg);                                // statistics exchanged, D1 reads of these lanes retired
                 TR(3, g);
                 tc_fence_after();
@@ -703,8 +742,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
                             f2 ga, gb, ba, bb;
-                            lds_2f2(sP + (P_MEM_G * 128 + c), ga, gb);
-                            lds_2f2(sP + (P_MEM_B * 128 + c), ba, bb);
+#ifdef MIND_EXP_P2PRE
+                            if (hf == 0) {
+                                ga = pg2[2 * k4]; gb = pg2[2 * k4 + 1]; ba = pb2[2 * k4]; bb = pb2[2 * k4 + 1];
+                            } else
+#endif
+                            {
+                                lds_2f2(sP + (P_MEM_G * 128 + c), ga, gb);
+                                lds_2f2(sP + (P_MEM_B * 128 + c), ba, bb);
+                            }
                             const f2 y0 = fma2(fma2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), r2, n2), ga, ba);
                             const f2 y1 = fma2(fma2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), r2, n2), gb, bb);
                             // hi = ReLU(y) truncated to fp16 (<= y for y >= 0, 0 for y < 0); lo = ReLU(y - hi)
