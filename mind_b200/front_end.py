@@ -54,20 +54,20 @@ def agent_trajectories(agent_obs) -> Dict[str, object]:
         if st[-1].observed is False:
             continue
         n = len(st)
+        # one pass over the states: (observed, x, y, heading, vx, vy); unobserved steps contribute zeros / no type row
+        rows = np.array([(s.observed, s.position[0], s.position[1], s.heading, s.velocity[0], s.velocity[1]) for s in st],
+                        dtype=np.float64)
         seen50 = np.zeros(OBS_LEN, dtype=bool)
-        p50, a50, v50 = np.zeros((OBS_LEN, 2)), np.zeros(OBS_LEN), np.zeros((OBS_LEN, 2))
-        for k, s in enumerate(st):
-            if s.observed:
-                t = OBS_LEN - n + k
-                seen50[t] = True
-                p50[t], a50[t], v50[t] = s.position, s.heading, s.velocity
+        seen50[OBS_LEN - n:] = rows[:, 0] != 0
+        full = np.zeros((OBS_LEN, 5))
+        full[OBS_LEN - n:] = np.where(rows[:, :1] != 0, rows[:, 1:], 0.0)
         one_hot = np.zeros(7)
         one_hot[_TYPE_SLOT.get(str(_val(agent_obs[key].object_type)).lower(), 6)] = 1
         t50 = np.zeros((OBS_LEN, 7))
         t50[seen50] = one_hot
-        pos.append(_fill_nearest(p50, seen50))
-        ang.append(_fill_nearest(a50, seen50))
-        vel.append(v50)
+        pos.append(_fill_nearest(full[:, 0:2], seen50))
+        ang.append(_fill_nearest(full[:, 2], seen50))
+        vel.append(full[:, 3:5])
         typ.append(t50)
         flags.append(seen50.astype(np.int64))
         tids.append(key)
