@@ -637,7 +637,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #ifdef MIND_EXP_STPRE
                 // A/B build for the next round (profiles/r01_v8_stall_analysis.md, item 1): S[j] + T[i] of this thread's 32
                 // channels is formed in the shadow of the wait for G1, so that after the TMEM load one FADD2 per channel pair
-                // remains and no shared-memory load sits on the critical path of epilogue 1.  Not yet run on hardware.
+                // remains and no shared-memory load sits on the critical path of epilogue 1; a single-query item's T row
+                // (global memory: E1 pass 1 of such a tile takes ~8,000 cycles today) is fetched there as well.
+                // Not yet run on hardware.
                 f2 st2[16];
                 if (!mode) {
 #pragma unroll
@@ -646,6 +648,16 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         lds_2f2(sS + (j_l * 132 + col0 + k4 * 4), sa, sb);
                         lds_2f2(sT + (i_l * 128 + col0 + k4 * 4), ta, tb);
                         st2[2 * k4] = add2(sa, ta); st2[2 * k4 + 1] = add2(sb, tb);
+                    }
+                } else {     // single-query item: the T row comes from global memory; eight independent loads in flight during the wait
+                    ulonglong2 tv[8];
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) tv[k4] = __ldg(reinterpret_cast<const ulonglong2*>(Tg + col0 + k4 * 4));
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        f2 sa, sb;
+                        lds_2f2(sS + (j_l * 132 + col0 + k4 * 4), sa, sb);
+                        st2[2 * k4] = add2(sa, tv[k4].x); st2[2 * k4 + 1] = add2(sb, tv[k4].y);
                     }
                 }
 #endif
@@ -672,17 +684,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
 #ifdef MIND_EXP_STPRE
-                            f2 x0, x1;
-                            if constexpr (kQ) {
-                                f2 sa, sb;
-                                lds_2f2(sS + (j_l * 132 + c), sa, sb);
-                                const ulonglong2 tv = __ldg(reinterpret_cast<const ulonglong2*>(Tg + c));
-                                x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), tv.x);
-                                x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tv.y);
-                            } else {
-                                x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), st2[2 * (hf * 4 + k4)]);
-                                x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), st2[2 * (hf * 4 + k4) + 1]);
-                            }
+                            (void)c;
+                            const f2 x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), st2[2 * (hf * 4 + k4)]);
+                            const f2 x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), st2[2 * (hf * 4 + k4) + 1]);
 #else
                             f2 sa, sb, ta, tb;
                             lds_2f2(sS + (j_l * 132 + c), sa, sb);
@@ -1294,7 +1298,6 @@ void tc_build_schedule(const int* n_tokens, int B, int sm_count, std::vector<TcW
     // fill every CTA up to its share of the total
     size_t ri = 0;          // next item of `rest`
     int c0 = 0;             // first chunk of rest[ri] not handed out yet
-    bool split_open = false;
     for (int c = 0; c < grid && ri < rest.size(); ++c) {
         const int64_t target = total * (c + 1) / grid - total * c / grid;
         const bool last = (c == grid - 1);
@@ -1309,7 +1312,7 @@ void tc_build_schedule(const int* n_tokens, int B, int sm_count, std::vector<TcW
                 ++ri;
                 continue;
             }
-            if (c0 == 0) { merges.push_back(TcMerge{t.b, t.j0, t.n, n_slots, 0, 0, 0, 0}); split_open = true; }
+            if (c0 == 0) merges.push_back(TcMerge{t.b, t.j0, t.n, n_slots, 0, 0, 0, 0});
             const int take = (int)std::min<int64_t>(left, need);
             TcWork x = t;
             x.ch0 = c0; x.ch1 = c0 + take; x.slot = n_slots++;
@@ -1317,10 +1320,9 @@ void tc_build_schedule(const int* n_tokens, int B, int sm_count, std::vector<TcW
             ++merges.back().nparts;
             load[c] += take;
             c0 += take;
-            if (c0 == t.ch1) { c0 = 0; ++ri; split_open = false; }
+            if (c0 == t.ch1) { c0 = 0; ++ri; }
         }
     }
-    (void)split_open;
     work.assign((size_t)grid, TcWork{0, 0, 0, 0, 0, -1, 0, 0});
     for (int c = 0; c < grid; ++c) {
         work[c].b = (int)work.size();
