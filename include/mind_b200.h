@@ -204,6 +204,39 @@ typedef struct {
 int mind_cost_fields(const MindCostFields* a, void* cuda_stream);
 const char* mind_cost_fields_last_error(void);
 
+/* ---- tree iLQR of the trajectory-tree optimiser (HOST code, no device needed) ------------------------
+ * mind_ilqr_tree_solve  replaces iLQR.fit (planners/ilqr/solver.py:80-167 with its forward rollout, recursive backward
+ * pass, regularisation schedule and backtracking line search) on a TreeCost (planners/ilqr/cost.py:326-446) whose nodes
+ * carry [PotentialField, StatePotential, StateConstraint] + [ControlPotential] (planners/ilqr/potential.py), for the
+ * 6-state kinematic bicycle model of planners/mind/trajectory_tree.py:153-177 (state x, y, v, heading, a, steer; controls
+ * da, dsteer).  Nodes are numbered in creation order; parent[0] = -1 (child of the root state x0), parent[i] < i.
+ * All pointers are HOST pointers, fp64, row-major.  fields are the per-node cost fields (mind_cost_fields output copied
+ * to the host, or any other source) on the grid xs_grid [gx] x ys_grid [gy] with cell size res and offset field_offset.
+ * Returns 0 and writes the optimised state / control paths; error text from mind_ilqr_last_error(). */
+typedef struct {
+    int32_t n_nodes;
+    const int32_t* parent;       /* [n] */
+    const double* x0;            /* [6] */
+    double dt, wheelbase;
+    int32_t gx, gy;
+    double res;
+    const double* field_offset;  /* [2] */
+    const double *xs_grid, *ys_grid;
+    const double* fields;        /* [n,gy,gx] */
+    const double* w_state;       /* [n,6,6]  StatePotential weight */
+    const double* des_state;     /* [n,6] */
+    const double* w_con;         /* [n,6,6]  StateConstraint weight */
+    const double *lower, *upper; /* [6] */
+    const double* w_ctrl;        /* [n,2,2]  ControlPotential weight */
+    int32_t max_iter;            /* <= 0: 100 (solver.py:80) */
+    const double* us_init;       /* [n,2] */
+    double *xs_out, *us_out;     /* [n,6], [n,2] */
+    int32_t* iterations;         /* out, may be NULL */
+    double* cost;                /* out: trajectory cost of the last forward rollout, may be NULL */
+} MindIlqrTree;
+int mind_ilqr_tree_solve(const MindIlqrTree* p);
+const char* mind_ilqr_last_error(void);
+
 /* bring-up self test of the TMA + tcgen05 + TMEM plumbing: D[0:128*128] = A . W^T (fp16 operands,
  * fp32 accumulate), D[128*128: 2*128*128] = the A tile read back through the software swizzle,
  * D[2*128*128: 3*128*128] = the same product with the A operand staged in tensor memory.

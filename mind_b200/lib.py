@@ -47,6 +47,15 @@ class MindCostFields(C.Structure):
                 ("quad", C.c_void_p), ("fields", C.c_void_p)]
 
 
+class MindIlqrTree(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("parent", C.c_void_p), ("x0", C.c_void_p), ("dt", C.c_double), ("wheelbase", C.c_double),
+                ("gx", C.c_int32), ("gy", C.c_int32), ("res", C.c_double), ("field_offset", C.c_void_p),
+                ("xs_grid", C.c_void_p), ("ys_grid", C.c_void_p), ("fields", C.c_void_p), ("w_state", C.c_void_p),
+                ("des_state", C.c_void_p), ("w_con", C.c_void_p), ("lower", C.c_void_p), ("upper", C.c_void_p),
+                ("w_ctrl", C.c_void_p), ("max_iter", C.c_int32), ("us_init", C.c_void_p), ("xs_out", C.c_void_p),
+                ("us_out", C.c_void_p), ("iterations", C.c_void_p), ("cost", C.c_void_p)]
+
+
 class MindTreeUpdate(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_new", "n_actor", "n_lane", "n_tlane")] + [("tar_time_ahead", C.c_float)] +
                 [(n, C.c_void_p) for n in ("src", "cpos", "cang", "cvel", "ccov", "ttype", "lane_ctrs", "lane_vecs", "tlane",
@@ -58,7 +67,7 @@ class MindTreeUpdate(C.Structure):
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
            "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_sync_check", "mind_profile_read",
-           "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error"]
+           "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error", "mind_ilqr_tree_solve", "mind_ilqr_last_error"]
 
 _lib = None
 
@@ -118,6 +127,9 @@ def load(build_if_missing: bool = True):
     lib.mind_cost_fields.argtypes = [C.POINTER(MindCostFields), C.c_void_p]
     lib.mind_cost_fields.restype = C.c_int
     lib.mind_cost_fields_last_error.restype = C.c_char_p
+    lib.mind_ilqr_tree_solve.argtypes = [C.POINTER(MindIlqrTree)]
+    lib.mind_ilqr_tree_solve.restype = C.c_int
+    lib.mind_ilqr_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

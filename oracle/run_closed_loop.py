@@ -20,6 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("demo")
     ap.add_argument("--horizon", type=float, default=6.0, help="simulated seconds (reference: 10.0)")
+    ap.add_argument("--native-ilqr", action="store_true",
+                    help="swap the reference's numpy tree iLQR for mind_ilqr_tree_solve (cost fields from the numpy oracle: no GPU here)")
     args = ap.parse_args()
     from oracle import ref_loader
     from mind_b200 import compat
@@ -56,6 +58,19 @@ def main():
         t_ilqr.append(time.perf_counter() - t0)
         return out
     pl.scen_tree_gen.branch_aime, pl.get_traj_tree = timed_branch, timed_traj
+    if args.native_ilqr:
+        # the product's optimiser class with the field source redirected to the CPU oracle (test infrastructure: the
+        # product computes the fields with mind_cost_fields on the GPU)
+        from mind_b200 import traj_opt as TO
+        from oracle import cost_field_oracle as O
+
+        def oracle_fields(scen_tree, x0, lane, cfg, device, warm=False):
+            nodes = {k: (n.parent_key, n.data[0], n.data[1], n.data[2], list(n.children_keys)) for k, n in scen_tree.nodes.items()}
+            root = scen_tree.get_root().key
+            off, xx, yy, fields, links = O.cost_fields(nodes, root, x0, lane, cfg, warm=warm)
+            return dict(offset=off, xx=xx, yy=yy, fields=fields, links=links, probs=[p for _, _, p, _, _ in O.walk(nodes, root)])
+        TO.CF.cost_fields = oracle_fields
+        pl.traj_tree_opt = TO.TrajectoryTreeOptimizerB200(pl.traj_tree_opt.config, device="cpu")
     # finer split of the iLQR half (trajectory_tree.py:20-124 cost trees vs :125-147 solves)
     opt, t_parts = pl.traj_tree_opt, {}
     for meth in ("init_warm_start_cost_tree", "init_cost_tree", "warm_start_solve", "solve"):

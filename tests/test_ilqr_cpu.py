@@ -1,0 +1,93 @@
+"""CPU: the native tree iLQR (mind_ilqr_tree_solve, csrc/ilqr_tree.cpp; host code) vs the solutions of the UNMODIFIED
+reference optimiser on the demo_2 scenario trees (tests/golden/ilqr_demo_2.npz, oracle/make_golden_ilqr.py):
+warm-start solve from zero controls, then the full solve started from the warm-start controls.  Cost fields come from the
+cost-field oracle (numpy), so no GPU is involved.  Tolerance 1e-6 on states / controls (fp64; BLAS vs plain-loop
+summation orders differ in the last bits and the solver runs tens of iterations)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_cost_field_cpu import CFG, demo2_tree_objects, demo2_trees
+
+W_DES = np.diag([0, 0, 0.1, 0, 1.0, 10.0])                          # planning/demo_*.py:21-24 / 49-52
+W_CON = np.diag([0, 0, 50.0, 0, 50.0, 500.0])
+UPPER = np.array([100000.0, 100000.0, 8.0, 10.0, 4.0, 0.2])
+LOWER = np.array([-100000.0, -100000.0, 0.0, -10.0, -6.0, -0.2])
+
+
+def opt_cfg(g):
+    return dict(CFG, smooth_grid_size=tuple(int(v) for v in g["grid"]), smooth_grid_res=float(g["res"]), w_des_state=W_DES,
+                w_state_con=W_CON, state_upper_bound=UPPER, state_lower_bound=LOWER, w_ctrl=5.0 * np.eye(2))
+
+
+def golden():
+    return dict(np.load(os.path.join(GOLDEN, "ilqr_demo_2.npz")))
+
+
+def fields_from_oracle(nodes, root, tree, x0, lane, cfg, warm):
+    from oracle import cost_field_oracle as O
+    off, xx, yy, fields, links = O.cost_fields(nodes, root, x0, lane, cfg, warm=warm)
+    probs = [p for _, _, p, _, _ in O.walk(nodes, root)]
+    return dict(offset=off, xx=xx, yy=yy, fields=fields, links=links, probs=probs)
+
+
+@pytest.mark.parametrize("ti", [0, 1, 2])
+def test_native_ilqr_vs_reference(ti):
+    from mind_b200.traj_opt import solve_tree
+    g = golden()
+    cfg = opt_cfg(g)
+    x0 = np.concatenate([g["state"], g["ctrl"]])
+    (root, nodes), tree = demo2_trees()[ti], demo2_tree_objects()[ti]
+    fw = fields_from_oracle(nodes, root, tree, x0, g["lane"], cfg, True)
+    xs_w, us_w, info_w = solve_tree(tree, x0, g["lane"], float(g["target_vel"]), cfg, float(g["dt"]), warm=True, fields=fw)
+    assert np.abs(xs_w - g["t%d/warm/xs" % ti]).max() < 1e-6 and np.abs(us_w - g["t%d/warm/us" % ti]).max() < 1e-6
+    ff = fields_from_oracle(nodes, root, tree, x0, g["lane"], cfg, False)
+    xs, us, info = solve_tree(tree, x0, g["lane"], float(g["target_vel"]), cfg, float(g["dt"]), us_init=g["t%d/warm/us" % ti], warm=False, fields=ff)
+    print("tree %d: warm %d iterations, full %d iterations, max |dx| %.2e |du| %.2e" %
+          (ti, info_w["iterations"], info["iterations"], np.abs(xs - g["t%d/full/xs" % ti]).max(), np.abs(us - g["t%d/full/us" % ti]).max()))
+    assert np.abs(xs - g["t%d/full/xs" % ti]).max() < 1e-6 and np.abs(us - g["t%d/full/us" % ti]).max() < 1e-6
+
+
+def test_ilqr_argument_checks():
+    from mind_b200.traj_opt import ilqr_solve
+    n = 3
+    ok = dict(parent=[-1, 0, 1], x0=np.zeros(6), dt=0.2, offset=np.zeros(2), xs_grid=np.arange(4.0), ys_grid=np.arange(4.0), res=1.0,
+              fields=np.zeros((n, 4, 4)), w_state=np.zeros((n, 6, 6)), des_state=np.zeros((n, 6)), w_con=np.zeros((n, 6, 6)),
+              lower=-np.ones(6) * 1e5, upper=np.ones(6) * 1e5, w_ctrl=np.tile(np.eye(2), (n, 1, 1)), us_init=np.zeros((n, 2)))
+    xs, us, it, cost = ilqr_solve(**ok)
+    assert xs.shape == (3, 6) and np.abs(us).max() == 0 and cost == 0.0        # zero cost everywhere: zero controls are optimal
+    with pytest.raises(RuntimeError):
+        ilqr_solve(**dict(ok, parent=[-1, 2, 0]))                              # a parent must precede its child
+    with pytest.raises(RuntimeError):
+        ilqr_solve(**dict(ok, parent=[0, 0, 1]))                               # node 0 hangs off the root state
+
+
+def test_optimizer_class_surface(monkeypatch):
+    """TrajectoryTreeOptimizerB200 keeps the reference class's call sequence (planner.py:171-175) and returns the same
+    tree of [state, control] nodes; the field source is redirected to the numpy oracle here (the product uses the GPU)."""
+    import types
+    from mind_b200 import traj_opt as TO
+    from oracle import cost_field_oracle as O
+    g = golden()
+    (root, nodes), tree = demo2_trees()[1], demo2_tree_objects()[1]
+
+    def oracle_fields(scen_tree, x0, lane, cfg, device, warm=False):
+        off, xx, yy, fields, links = O.cost_fields(nodes, root, x0, lane, cfg, warm=warm)
+        return dict(offset=off, xx=xx, yy=yy, fields=fields, links=links, probs=[p for _, _, p, _, _ in O.walk(nodes, root)])
+    monkeypatch.setattr(TO.CF, "cost_fields", oracle_fields)
+    base = opt_cfg(g)
+    config = types.SimpleNamespace(dt=float(g["dt"]), state_size=6, action_size=2, w_opt_cfg=dict(base), opt_cfg=dict(base))
+    opt = TO.TrajectoryTreeOptimizerB200(config, device="cpu")
+    opt.init_warm_start_cost_tree(tree, g["state"], g["ctrl"], g["lane"], float(g["target_vel"]))
+    xs, us = opt.warm_start_solve()
+    assert np.abs(us - g["t1/warm/us"]).max() < 1e-6
+    opt.init_cost_tree(tree, g["state"], g["ctrl"], g["lane"], float(g["target_vel"]))
+    tt = opt.solve(us)
+    n = len(g["t1/full/xs"])
+    assert sorted(tt.nodes, key=lambda k: (k != -1, k)) == [-1] + list(range(n))
+    assert tt.nodes[-1].parent_key is None and np.array_equal(tt.nodes[-1].data[0], np.concatenate([g["state"], g["ctrl"]]))
+    assert tt.nodes[0].parent_key == -1
+    for k in range(n):
+        assert np.abs(tt.nodes[k].data[0] - g["t1/full/xs"][k]).max() < 1e-6 and np.abs(tt.nodes[k].data[1] - g["t1/full/us"][k]).max() < 1e-6
