@@ -44,3 +44,21 @@ def test_cost_fields_full_grid_properties():
     _, _, _, want, links = O.cost_fields(nodes, root, x0, g["lane"], cfg, warm=False)
     assert links == full["links"]
     assert np.abs(full["fields"] - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("ti", [0, 1, 2])
+def test_optimizer_on_gpu_fields_vs_reference_solution(ti):
+    """the whole accelerated optimiser step: cost fields on the GPU (mind_cost_fields) + native tree iLQR, against the
+    solutions of the unmodified reference optimiser (tests/golden/ilqr_demo_2.npz); warm start, then the full solve"""
+    from mind_b200.traj_opt import solve_tree
+    from test_ilqr_cpu import golden as ilqr_golden, opt_cfg
+    g = ilqr_golden()
+    cfg = opt_cfg(g)
+    x0 = np.concatenate([g["state"], g["ctrl"]])
+    tree = demo2_tree_objects()[ti]
+    dev = torch.device("cuda", 0)
+    xs_w, us_w, _ = solve_tree(tree, x0, g["lane"], float(g["target_vel"]), cfg, float(g["dt"]), warm=True, device=dev)
+    assert np.abs(xs_w - g["t%d/warm/xs" % ti]).max() < 1e-6 and np.abs(us_w - g["t%d/warm/us" % ti]).max() < 1e-6
+    xs, us, info = solve_tree(tree, x0, g["lane"], float(g["target_vel"]), cfg, float(g["dt"]), us_init=us_w, warm=False, device=dev)
+    print("tree %d: %d iterations, max |dx| %.2e" % (ti, info["iterations"], np.abs(xs - g["t%d/full/xs" % ti]).max()))
+    assert np.abs(xs - g["t%d/full/xs" % ti]).max() < 1e-6 and np.abs(us - g["t%d/full/us" % ti]).max() < 1e-6
