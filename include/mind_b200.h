@@ -236,6 +236,9 @@ typedef struct {
 } MindIlqrTree;
 int mind_ilqr_tree_solve(const MindIlqrTree* p);
 const char* mind_ilqr_last_error(void);
+/* diagnostic: PotentialField.get_potential / get_gradient / get_hessian (potential.py:71-104) of node `node` at (x, y);
+ * only the grid members of p are read.  out6 = {value, d/dx, d/dy, d2/dx2, d2/dxdy, d2/dy2}. */
+int mind_debug_field_eval(const MindIlqrTree* p, int32_t node, double x, double y, double* out6);
 
 /* bring-up self test of the TMA + tcgen05 + TMEM plumbing: D[0:128*128] = A . W^T (fp16 operands,
  * fp32 accumulate), D[128*128: 2*128*128] = the A tile read back through the software swizzle,

@@ -389,6 +389,23 @@ struct Solver {
 
 extern "C" const char* mind_ilqr_last_error(void) { return g_ierr; }
 
+// diagnostic: value, gradient and Hessian of one node's PotentialField at a position (potential.py:71-104)
+extern "C" int mind_debug_field_eval(const MindIlqrTree* p, int32_t node, double x, double y, double* out6) {
+    if (!p || !out6 || node < 0 || node >= p->n_nodes || !p->fields || !p->xs_grid || !p->ys_grid || !p->field_offset || p->gx < 2 ||
+        p->gy < 2 || !(p->res > 0)) {
+        snprintf(g_ierr, sizeof g_ierr, "mind_debug_field_eval: bad argument");
+        return 1;
+    }
+    Problem P;
+    P.p = p; P.n = p->n_nodes;
+    const double pos[NX] = {x, y, 0, 0, 0, 0};
+    const Problem::Patch q = P.patch(node, pos);
+    out6[0] = P.field_value(q);
+    P.field_grad(q, &out6[1], &out6[2]);
+    P.field_hess(q, &out6[3], &out6[4], &out6[5]);       // xx, xy, yy
+    return 0;
+}
+
 extern "C" int mind_ilqr_tree_solve(const MindIlqrTree* p) {
     if (!p || p->n_nodes <= 0 || !p->parent || !p->x0 || !p->fields || !p->xs_grid || !p->ys_grid || !p->field_offset ||
         !p->w_state || !p->des_state || !p->w_con || !p->lower || !p->upper || !p->w_ctrl || !p->us_init || !p->xs_out || !p->us_out ||

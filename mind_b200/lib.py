@@ -67,7 +67,7 @@ class MindTreeUpdate(C.Structure):
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
            "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_sync_check", "mind_profile_read",
-           "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error", "mind_ilqr_tree_solve", "mind_ilqr_last_error"]
+           "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error", "mind_ilqr_tree_solve", "mind_ilqr_last_error", "mind_debug_field_eval"]
 
 _lib = None
 
@@ -130,6 +130,8 @@ def load(build_if_missing: bool = True):
     lib.mind_ilqr_tree_solve.argtypes = [C.POINTER(MindIlqrTree)]
     lib.mind_ilqr_tree_solve.restype = C.c_int
     lib.mind_ilqr_last_error.restype = C.c_char_p
+    lib.mind_debug_field_eval.argtypes = [C.POINTER(MindIlqrTree), C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    lib.mind_debug_field_eval.restype = C.c_int
     _lib = lib
     return lib
 

@@ -91,3 +91,46 @@ def test_optimizer_class_surface(monkeypatch):
     assert tt.nodes[0].parent_key == -1
     for k in range(n):
         assert np.abs(tt.nodes[k].data[0] - g["t1/full/xs"][k]).max() < 1e-6 and np.abs(tt.nodes[k].data[1] - g["t1/full/us"][k]).max() < 1e-6
+
+
+def _field_eval(field, xs, ys, res, off, x, y):
+    import ctypes as C
+    from mind_b200 import lib
+    L = lib.load()
+    f = np.ascontiguousarray(field[None], dtype=np.float64)
+    xs, ys, off = (np.ascontiguousarray(a, dtype=np.float64) for a in (xs, ys, off))
+    p = lib.MindIlqrTree()
+    p.n_nodes, p.gx, p.gy, p.res = 1, len(xs), len(ys), float(res)
+    p.fields, p.xs_grid, p.ys_grid, p.field_offset = f.ctypes.data, xs.ctypes.data, ys.ctypes.data, off.ctypes.data
+    out = (C.c_double * 6)()
+    assert L.mind_debug_field_eval(C.byref(p), 0, float(x), float(y), out) == 0
+    return np.array(out[:])
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="needs the reference tree (build container only)")
+def test_field_patch_vs_reference_potential_field():
+    """interior, edge and corner cells, positions outside the grid: value / gradient / Hessian of the native patch code vs
+    the reference's PotentialField (potential.py:62-264), including its zero-padded border neighbourhoods"""
+    import sys
+    from oracle import ref_loader
+    if ref_loader.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REF_ROOT)
+    from planners.ilqr.potential import PotentialField
+    rng = np.random.default_rng(3)
+    gx, gy, res = 9, 7, 0.8
+    off = np.array([100.0, -50.0])
+    xs, ys = np.linspace(0, (gx - 1) * res, gx) + off[0], np.linspace(0, (gy - 1) * res, gy) + off[1]
+    xx, yy = np.meshgrid(xs, ys)
+    field = rng.uniform(0, 10, size=(gy, gx))
+    pf = PotentialField(off, res, xx, yy, field)
+    pts = [(xs[i] + dx, ys[j] + dy) for i in (0, 1, 4, gx - 2, gx - 1) for j in (0, 1, 3, gy - 2, gy - 1)
+           for dx, dy in ((0.0, 0.0), (0.3, -0.25), (-0.39, 0.39))]
+    pts += [(xs[0] - 5.0, ys[2]), (xs[-1] + 7.0, ys[-1] + 3.0), (xs[3] + 0.4, ys[3] - 0.4), (xs[2] + 0.4000001, ys[2])]
+    worst = 0.0
+    for x, y in pts:
+        st = np.array([x, y, 1.0, 0.2, 0.0, 0.0])
+        want = np.concatenate([[pf.get_potential(st)], pf.get_gradient(st)[:2],
+                               [pf.get_hessian(st)[0, 0], pf.get_hessian(st)[0, 1], pf.get_hessian(st)[1, 1]]])
+        got = _field_eval(field, xs, ys, res, off, x, y)
+        worst = max(worst, np.abs(got - want).max() / max(1.0, np.abs(want).max()))
+    assert worst < 1e-13, worst
