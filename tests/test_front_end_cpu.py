@@ -176,3 +176,28 @@ def test_reference_trajectory_optimizer_builds_on_theano_lite():
     want = np.array([x[0] + x[2] * np.cos(x[3]) * cfg.dt, x[1] + x[2] * np.sin(x[3]) * cfg.dt, x[2] + x[4] * cfg.dt,
                      x[3] + x[2] / 2.5 * np.tan(x[5]) * cfg.dt, x[4] + u[0] * cfg.dt, x[5] + u[1] * cfg.dt])
     assert np.abs(nxt - want).max() < 1e-12 and dyn.f_x(x, u, 0).shape == (6, 6) and dyn.f_u(x, u, 0).shape == (6, 2)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs the demo maps of the reference tree (build container only)")
+def test_centerlines_agree_with_the_maps_own_centerline_field():
+    """weak pin of the unpinned av2 boundary: every AV2 map JSON also ships a `centerline` polyline per lane segment; the
+    10-point midpoint line of the resampled boundaries (what av2's get_lane_segment_centerline returns) must run along it"""
+    import glob
+    from mind_b200.compat import av2_lite as A
+    worst = 0.0
+    n = 0
+    for path in glob.glob(os.path.join(ref_loader.REF_ROOT, "data", "*", "log_map_archive_*.json")):
+        raw = json.load(open(path))["lane_segments"]
+        m = A.ArgoverseStaticMap.from_json(path)
+        for key, ls in raw.items():
+            ref = np.array([[p["x"], p["y"]] for p in ls["centerline"]])
+            got = m.get_lane_segment_centerline(ls["id"])[:, :2]
+            assert got.shape == (10, 2)
+            # distance of each of our points to the map's polyline
+            a, b = ref[:-1], ref[1:]
+            d = b - a
+            t = np.clip(((got[:, None] - a[None]) * d[None]).sum(-1) / (d * d).sum(-1)[None], 0, 1)
+            dist = np.linalg.norm(got[:, None] - (a[None] + t[..., None] * d[None]), axis=-1).min(axis=1)
+            worst = max(worst, float(dist.max()))
+            n += 1
+    assert n > 100 and worst < 0.6, (n, worst)          # lanes are ~3.5 m wide; the two constructions differ by centimetres
