@@ -669,6 +669,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 // streaming 16-column passes; x = D1 + S + T is parked in this thread's own Dpe cells
                 // (free until G2 of this tile is issued) so nothing has to live in registers across the barrier
                 const uint32_t scr_t = tmem + lane_base + 128 + col0;
+#ifdef MIND_EXP_XREG
+                // A/B build for the next round: x stays in 32 registers across the row-group barrier instead of a round trip
+                // through the TMEM scratch cells (2 tcgen05.st + wait::st + 2 tcgen05.ld per thread-tile).  Not yet run on hardware.
+                uint32_t xr[32];
+#endif
                 auto e1_pass1 = [&](auto qtag) {                   // two straight-line copies: no branch inside the unrolled loops
                     constexpr bool kQ = decltype(qtag)::value;
                     f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
@@ -704,10 +709,17 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                             s1a = add2(s1a, x0); s1b = add2(s1b, x1);
                             s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                         }
+#ifdef MIND_EXP_XREG
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) xr[hf * 16 + e] = r[e];
+#else
                         TMEM_ST_X16(scr_t + hf * 16, r);
+#endif
                     }
                     sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
+#ifndef MIND_EXP_XREG
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
                 };
                 if (mode) e1_pass1(std::true_type{});
                 else e1_pass1(std::false_type{});
@@ -733,14 +745,22 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
                     const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
+#ifdef MIND_EXP_XREG
+                    uint32_t (&rr)[32] = xr;
+#else
                     uint32_t rr[2][16];
                     TMEM_LD_X16_NM(scr_t, rr[0]);
                     TMEM_LD_X16_NM(scr_t + 16, rr[1]);
                     TMEM_WAIT_LD_R16(rr[0]);
                     TMEM_PIN_R16(rr[1]);
+#endif
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
+#ifdef MIND_EXP_XREG
+                        uint32_t* r = rr + hf * 16;
+#else
                         uint32_t (&r)[16] = rr[hf];
+#endif
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
