@@ -803,9 +803,18 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     mbar_wait(bar_m2a, par, a.err, E_MMA2);
                     TR(7, g);
                     tc_fence_after();
+#ifdef MIND_EXP_XREG2
+                    // A/B build for the next round: Dpe + b stays in 32 registers from pass A to pass C (no TMEM scratch round
+                    // trips, b_pe loaded and added once instead of twice).  Not yet run on hardware.
+                    uint32_t er[2][16];
+#endif
                     {   // pass A: statistics of Dpe + b
                         f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
+#ifdef MIND_EXP_XREG2
+                        uint32_t (&rr)[2][16] = er;
+#else
                         uint32_t rr[2][16];
+#endif
                         TMEM_LD_X16_NM(scr_t, rr[0]);
                         TMEM_LD_X16_NM(scr_t + 16, rr[1]);
                         TMEM_WAIT_LD_R16(rr[0]);
@@ -819,6 +828,10 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                 lds_2f2(sP + (P_BPE * 128 + col0 + hf * 16 + k4 * 4), ba, bb);
                                 const f2 x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), ba);
                                 const f2 x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), bb);
+#ifdef MIND_EXP_XREG2
+                                upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
+                                upk2u(x1, r[k4 * 4 + 2], r[k4 * 4 + 3]);
+#endif
                                 s1a = add2(s1a, x0); s1b = add2(s1b, x1);
                                 s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                             }
@@ -836,11 +849,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float rstd = rsqrtf(var + kEps);
                         const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
                         f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
+#ifdef MIND_EXP_XREG2
+                        uint32_t (&rr)[2][16] = er;
+#else
                         uint32_t rr[2][16];
                         TMEM_LD_X16_NM(scr_t, rr[0]);
                         TMEM_LD_X16_NM(scr_t + 16, rr[1]);
                         TMEM_WAIT_LD_R16(rr[0]);
                         TMEM_PIN_R16(rr[1]);
+#endif
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t (&r)[16] = rr[hf];
@@ -851,14 +868,20 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                 const uint32_t ev[4] = {eu.x, eu.y, eu.z, eu.w};
 #pragma unroll
                                 for (int h4 = 0; h4 < 2; ++h4) {
-                                    f2 b0, b1, g0, g1, a0, a1;
-                                    lds_2f2(sP + (P_BPE * 128 + c + h4 * 4), b0, b1);
+                                    f2 g0, g1, a0, a1;
                                     lds_2f2(sP + (P_PE_G * 128 + c + h4 * 4), g0, g1);
                                     lds_2f2(sP + (P_PE_B * 128 + c + h4 * 4), a0, a1);
                                     const int k = c8 * 8 + h4 * 4;
                                     float u0, u1, u2, u3;
+#ifdef MIND_EXP_XREG2
+                                    upk2(fma2(fma2(pk2u(r[k + 0], r[k + 1]), r2, n2), g0, a0), u0, u1);
+                                    upk2(fma2(fma2(pk2u(r[k + 2], r[k + 3]), r2, n2), g1, a1), u2, u3);
+#else
+                                    f2 b0, b1;
+                                    lds_2f2(sP + (P_BPE * 128 + c + h4 * 4), b0, b1);
                                     upk2(fma2(fma2(add2(pk2u(r[k + 0], r[k + 1]), b0), r2, n2), g0, a0), u0, u1);
                                     upk2(fma2(fma2(add2(pk2u(r[k + 2], r[k + 3]), b1), r2, n2), g1, a1), u2, u3);
+#endif
                                     const f2 x0 = add2(h2_to_f2(ev[h4 * 2 + 0]), pk2(fmaxf(u0, 0.f), fmaxf(u1, 0.f)));
                                     const f2 x1 = add2(h2_to_f2(ev[h4 * 2 + 1]), pk2(fmaxf(u2, 0.f), fmaxf(u3, 0.f)));
                                     upk2u(x0, r[k + 0], r[k + 1]);
@@ -867,10 +890,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                     s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                                 }
                             }
+#ifndef MIND_EXP_XREG2
                             TMEM_ST_X16(scr_t + hf * 16, r);
+#endif
                         }
                         sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
+#ifndef MIND_EXP_XREG2
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
                     }
                     TR(10, g);
                     row_group_sync(lg);
@@ -882,11 +909,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
                         const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
+#ifdef MIND_EXP_XREG2
+                        uint32_t (&rr)[2][16] = er;
+#else
                         uint32_t rr[2][16];
                         TMEM_LD_X16_NM(scr_t, rr[0]);
                         TMEM_LD_X16_NM(scr_t + 16, rr[1]);
                         TMEM_WAIT_LD_R16(rr[0]);
                         TMEM_PIN_R16(rr[1]);
+#endif
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t (&r)[16] = rr[hf];
