@@ -134,3 +134,49 @@ def test_field_patch_vs_reference_potential_field():
         got = _field_eval(field, xs, ys, res, off, x, y)
         worst = max(worst, np.abs(got - want).max() / max(1.0, np.abs(want).max()))
     assert worst < 1e-13, worst
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_native_ilqr_vs_live_reference_on_random_trees(seed):
+    """random tree shapes, random rough cost fields, tight state bounds (constraint potentials active), states that leave
+    the grid: the reference's iLQR.fit on a TreeCost built from its own potentials vs mind_ilqr_tree_solve"""
+    import sys
+    from oracle import ref_loader
+    from mind_b200 import compat
+    compat.install()
+    if ref_loader.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REF_ROOT)
+    from planners.basic.tree import Tree, Node
+    from planners.ilqr.cost import TreeCost
+    from planners.ilqr.potential import ControlPotential, PotentialField, StateConstraint, StatePotential
+    from planners.mind.trajectory_tree import TrajectoryTreeOptimizer
+    from planners.mind.configs.planning.demo_1 import TrajTreeCfg
+    from mind_b200.traj_opt import ilqr_solve
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(6, 30))
+    parent = [-1] + [int(rng.integers(max(0, i - 4), i)) for i in range(1, n)]
+    gx, gy, res = int(rng.integers(12, 40)), int(rng.integers(12, 40)), float(rng.choice([0.4, 1.0, 2.5]))
+    x0 = np.array([50.0, -20.0, float(rng.uniform(0, 9)), float(rng.uniform(-3, 3)), float(rng.uniform(-1, 1)), float(rng.uniform(-0.1, 0.1))])
+    off = x0[:2] - 0.5 * np.array([(gx - 1) * res, (gy - 1) * res])
+    xs_g, ys_g = np.linspace(0, (gx - 1) * res, gx) + off[0], np.linspace(0, (gy - 1) * res, gy) + off[1]
+    xx, yy = np.meshgrid(xs_g, ys_g)
+    base = ((xx - x0[0] - 3.0) ** 2 + (yy - x0[1] + 2.0) ** 2) * float(rng.uniform(0.2, 2.0))
+    fields = base[None] * rng.uniform(0.3, 1.0, size=(n, 1, 1)) + rng.uniform(0, 3.0, size=(n, gy, gx))
+    probs = rng.uniform(0.2, 1.0, size=n)
+    w_des = np.diag([0, 0, 0.1, 0, 1.0, 10.0]); w_con = np.diag([0, 0, 50.0, 0, 50.0, 500.0]); w_u = 5.0 * np.eye(2)
+    upper = np.array([1e5, 1e5, float(rng.uniform(3, 8)), 10.0, 1.0, 0.05]); lower = np.array([-1e5, -1e5, 0.5, -10.0, -1.0, -0.05])
+    des = np.array([0, 0, float(rng.uniform(2, 9)), 0.0, 0.0, 0.0])
+    tree = Tree()
+    tree.add_node(Node(-1, None, x0))
+    for i in range(n):
+        pots = [PotentialField(off, res, xx, yy, fields[i]), StatePotential(w_des * probs[i], des), StateConstraint(w_con * probs[i], lower, upper)]
+        tree.add_node(Node(i, parent[i], [pots, [ControlPotential(w_u * probs[i])]]))
+    opt = TrajectoryTreeOptimizer(TrajTreeCfg())
+    us0 = rng.normal(size=(n, 2)) * np.array([0.5, 0.02])
+    xs_r, us_r = opt.ilqr.fit(us0, TreeCost(tree, 6, 2))
+    xs, us, it, cost = ilqr_solve(parent, x0, 0.2, off, xs_g, ys_g, res, fields, probs[:, None, None] * w_des[None], np.tile(des, (n, 1)),
+                                  probs[:, None, None] * w_con[None], lower, upper, probs[:, None, None] * w_u[None], us0)
+    err = max(np.abs(xs - xs_r).max(), np.abs(us - us_r).max())
+    print("seed %d: %d nodes, grid %dx%d @ %.1f m, %d iterations, max diff %.2e" % (seed, n, gx, gy, res, it, err))
+    assert err < 1e-6
