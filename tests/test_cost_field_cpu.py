@@ -101,3 +101,59 @@ def test_product_host_tables_match_the_oracle(warm):
             assert np.array_equal(mean, o_mean) and np.array_equal(rad, o_rad)
         else:
             assert mean is None and rad is None
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_oracle_cost_fields_vs_live_reference_on_random_trees(seed):
+    """random scenario trees (1..6 actors incl. ego-only, odd and even durations, branching), random lanes and grids:
+    the unmodified TrajectoryTreeOptimizer.init_warm_start_cost_tree / init_cost_tree vs the oracle and vs the host
+    tables of mind_b200.cost_field"""
+    import sys
+    from oracle import ref_loader, cost_field_oracle as O
+    from mind_b200 import compat
+    from mind_b200.cost_field import node_tables
+    compat.install()
+    if ref_loader.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REF_ROOT)
+    from planners.basic.tree import Tree, Node
+    from planners.mind.trajectory_tree import TrajectoryTreeOptimizer
+    from planners.mind.configs.planning.demo_3 import TrajTreeCfg
+    rng = np.random.default_rng(100 + seed)
+    na = int(rng.integers(1, 7))
+    keys, parents = ["r"], {"r": None}
+    for i in range(int(rng.integers(1, 6))):
+        k = "n%d" % i
+        parents[k] = keys[int(rng.integers(0, len(keys)))]
+        keys.append(k)
+    flat = {}
+    for k in keys:
+        dur = int(rng.integers(1, 12))
+        trajs = (rng.normal(size=(na, dur, 2)) * 8 + np.array([100.0, 40.0])).astype(np.float32)
+        covs = rng.uniform(0.0, 2.0, size=(na, dur, 1)).astype(np.float32)
+        flat[k] = (parents[k], float(rng.uniform(0.05, 1.0)), trajs, covs)
+    tree = Tree()
+    for k in keys:
+        tree.add_node(Node(k, parents[k], [flat[k][1], flat[k][2], flat[k][3], None]))
+    nodes = {k: (parents[k], flat[k][1], flat[k][2], flat[k][3], list(tree.get_node(k).children_keys)) for k in keys}
+    cfgobj = TrajTreeCfg()
+    grid, res = (int(rng.integers(8, 24)), int(rng.integers(8, 24))), float(rng.choice([0.4, 1.0, 3.0]))
+    for c in (cfgobj.w_opt_cfg, cfgobj.opt_cfg):
+        c["smooth_grid_size"], c["smooth_grid_res"] = grid, res
+    lane = np.cumsum(rng.normal(size=(int(rng.integers(2, 12)), 2)) * 6, axis=0) + np.array([95.0, 35.0])
+    state, ctrl = np.array([100.0, 40.0, 5.0, 0.3]), np.array([0.1, 0.0])
+    opt = TrajectoryTreeOptimizer(cfgobj)
+    x0 = np.concatenate([state, ctrl])
+    for warm, init, cfg in ((True, opt.init_warm_start_cost_tree, cfgobj.w_opt_cfg), (False, opt.init_cost_tree, cfgobj.opt_cfg)):
+        init(tree, state, ctrl, lane, 7.0)
+        rn = opt.cost_tree.tree.nodes
+        rkeys = [k for k in rn if k != -1]
+        want = np.stack([rn[k].data[0][0].cost_field for k in rkeys])
+        off, xx, yy, got, links = O.cost_fields(nodes, "r", x0, lane, cfg, warm=warm)
+        assert links == [(k, rn[k].parent_key) for k in rkeys]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+        coef, mean, rad, plinks, _ = node_tables(tree, cfg, warm)
+        o_coef, o_mean, o_rad, _ = O.node_inputs(nodes, "r", cfg, warm)
+        assert plinks == links and np.array_equal(coef, o_coef)
+        if not warm:
+            assert np.array_equal(mean, o_mean) and np.array_equal(rad, o_rad)
