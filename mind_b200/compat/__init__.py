@@ -60,4 +60,10 @@ def install(force: bool = False) -> dict:
         used["theano"] = "lite"
     else:
         used["theano"] = "real"
+    if force or not _have("matplotlib"):
+        from . import mpl_stub
+        sys.modules.update(mpl_stub.modules())
+        used["matplotlib"] = "stub (no rendering)"
+    else:
+        used["matplotlib"] = "real"
     return used

@@ -201,3 +201,31 @@ def test_centerlines_agree_with_the_maps_own_centerline_field():
             worst = max(worst, float(dist.max()))
             n += 1
     assert n > 100 and worst < 0.6, (n, worst)          # lanes are ~3.5 m wide; the two constructions differ by centimetres
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs the reference tree (build container only)")
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode of the plugin path")
+def test_reference_plugin_mechanism_reaches_the_b200_class(tmp_path):
+    """the drop-in is configuration only: a planner JSON whose `network_config` names mind_b200.integration.net_cfg_b200
+    makes the UNMODIFIED MINDPlanner.init_network (planner.py:42-49) import ScenePredNetB200 -- which, without a CUDA
+    device, refuses loudly instead of falling back"""
+    import sys
+    from mind_b200 import compat
+    compat.install()
+    if ref_loader.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REF_ROOT)
+    from mind_b200.integration.net_cfg_b200 import NetCfg
+    cfg = NetCfg().get_net_cfg()
+    assert cfg["network"] == "mind_b200.predictor:ScenePredNetB200" and cfg["n_scene_layer"] == 6 and cfg["g_num_modes"] == 6
+    pc = json.load(open(os.path.join(ref_loader.REF_ROOT, "planners/mind/configs/demo_2.json")))
+    pc["network_config"] = "mind_b200.integration.net_cfg_b200"
+    path = tmp_path / "planner.json"
+    path.write_text(json.dumps(pc))
+    from planners.mind.planner import MINDPlanner
+    cwd = os.getcwd()
+    os.chdir(ref_loader.REF_ROOT)
+    try:
+        with pytest.raises(RuntimeError, match="CUDA"):
+            MINDPlanner(str(path))
+    finally:
+        os.chdir(cwd)
