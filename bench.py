@@ -508,6 +508,28 @@ def run_native(args):
     cpu_v, cores, sample = cpu_port_rate(sd)
     tree = bench_tree(net, dev)
     cost = bench_cost_fields(dev) if rank == 0 else None
+    sharded = None
+    if args.tree_sharded and world > 1:
+        # opt-in (never part of the driver's default run): forced-full depth-4 x branch-6 tree with every level's frontier
+        # sharded over the ranks and one all-gather of (cls, reg, vel) per level (SURVEY.md 8e tree mode); max over ranks
+        import copy
+        from mind_b200 import synth
+        from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
+        sargs = dict(x0=(100, 108, 92, 120, 112, 96, 130, 85), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0), v=(5, 9, 3, 8, 2, 10, 6, 12))
+        gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
+        gen.force_full, gen.distributed = (10, 20, 30), True
+        times = []
+        for r in range(7):
+            data, lane, info, graph = synth.scene_s3(**sargs)
+            gen.reset(); gen.set_target_lane(lane, info); gen.lane_graph = copy.deepcopy(graph)
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gen.rollout(data)
+            torch.cuda.synchronize()
+            t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        sharded = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches), "ranks": world}
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -523,7 +545,7 @@ def run_native(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "stage_ms_per_step": stage_ms,
-            "cost_fields": cost,
+            "cost_fields": cost, "tree_rollout_sharded": sharded,
             "tree_rollout": {"unit": "ms/scene", "scene": "natural / forced_full: S3 kinematic, 8 actors x 60 lane polylines; demo_2_*: the Argoverse-2 demo_2 scene of BASELINE.json configs[2]", **tree}}
     print(json.dumps(line))
     if world > 1:
@@ -539,6 +561,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default="f16tc", choices=["f16tc", "fp32"])
     ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (for ncu runs)")
+    ap.add_argument("--tree-sharded", action="store_true",
+                    help="N > 1 only, opt-in: forced-full scenario tree with the frontier of every level sharded over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
