@@ -101,6 +101,11 @@ typedef struct {
 /* bytes of caller-provided device workspace mind_forward needs for this batch shape */
 int64_t mind_workspace_bytes(MindCtx* ctx, int32_t n_scenes, int32_t sum_actors, int32_t sum_lanes,
                              int32_t max_tokens /* max_b (Na_b+Nl_b+1) */);
+/* same for one concrete batch (only n_scenes and the two offset arrays are read).  In the tensor-core mode the
+ * requirement depends on the per-scene token counts: scenes below option "tc_min_tokens" take the exact tier (3-term
+ * tcgen05 products, fp32 edge) on their own pair grid; mind_workspace_bytes() assumes every scene has max_tokens
+ * tokens, which is exact for uniform batches (tree levels, the benchmark batch). */
+int64_t mind_workspace_bytes_batch(MindCtx* ctx, const MindBatch* batch);
 
 int mind_forward(MindCtx* ctx, const MindBatch* batch, const MindOutputs* out, void* workspace,
                  int64_t workspace_bytes, void* cuda_stream);

@@ -1382,10 +1382,17 @@ void tc_build_schedule(const int* n_tokens, int B, int sm_count, std::vector<TcW
     }
 }
 
-const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, HostStage& stage, cudaStream_t st) {
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, int min_tokens, __half* edge16, HostStage& stage, cudaStream_t st) {
     if (!w.packed) return "weights not packed";
     std::vector<int> ntok((size_t)B);
-    for (int b = 0; b < B; ++b) ntok[b] = sd[b].n_actor + sd[b].n_lane + 1;
+    bool any = false;
+    for (int b = 0; b < B; ++b) {        // scenes below min_tokens belong to the exact tier: no work items
+        const int n = sd[b].n_actor + sd[b].n_lane + 1;
+        ntok[b] = n >= min_tokens ? n : 0;
+        any = any || ntok[b] > 0;
+    }
+    w.B = B; w.Nmax = Nmax;
+    if (!any) { w.grid = 0; w.n_work = 0; w.n_merge = 0; return nullptr; }
     std::vector<TcWork> work;
     std::vector<TcMerge> merges;
     int n_slots = 0, grid = 1;
@@ -1428,6 +1435,7 @@ const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* a
             return "cudaFuncSetAttribute(smem) failed";
         attr = true;
     }
+    if (w.grid <= 0) return nullptr;      // no scene takes the fused tier
     tc::LayerArgs a;
     a.work = w.d_work; a.n_work = w.n_work; a.stq = stq; a.params = w.layer[layer].params; a.attn_hi = attn_hi; a.attn_lo = attn_lo;
     a.Nmax = w.Nmax; a.has_edge = w.layer[layer].has_edge; a.err = w.d_err; a.part = w.d_part;

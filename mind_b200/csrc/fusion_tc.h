@@ -58,8 +58,9 @@ void tc_free(TcWeights& w);
 // static schedule (host only): range headers + work items, merge jobs of the key-split items
 void tc_build_schedule(const int* n_tokens, int B, int sm_count, std::vector<TcWork>& work, std::vector<TcMerge>& merges,
                        int& n_slots, int& grid);
-// per forward: work list + tensor map over edge16 [B,Nmax,Nmax,128] fp16
-const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, __half* edge16, HostStage& stage, cudaStream_t st);
+// per forward: work list + tensor map over edge16 [B,Nmax,Nmax,128] fp16; scenes with fewer than min_tokens tokens get
+// no work items (they take the exact tier, pair_x3.cu)
+const char* tc_prepare(TcWeights& w, const std::vector<SceneDesc>& sd, int B, int Nmax, int min_tokens, __half* edge16, HostStage& stage, cudaStream_t st);
 // One fused layer over the whole batch: updates edge16 in place (layers 0-4), reads STQ
 // [B*Nmax,384] (S | T | q/4), writes the attention output (before out-proj) as an fp16 (hi, lo) pair [B*Nmax,128].
 const char* tc_fusion_layer(TcWeights& w, int layer, const float* stq, __half* attn_hi, __half* attn_lo, int sm_count, cudaStream_t st);

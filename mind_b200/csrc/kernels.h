@@ -83,7 +83,7 @@ void launch_gather_tokens(const float* x, const SceneDesc* sd, float* actors, fl
 void launch_edge_init_f32(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
                           const float* g, const float* be, float* edge, int b0, int nb, int Nmax, cudaStream_t st);
 void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
-                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, cudaStream_t st);
+                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st);
 
 // exact-path pair epilogues on rows r = ((b*Nmax + i)*Nmax + j)
 // memory = ReLU(LN(tmp + S[b,j] + T[b,i]))   with STQ [B*Nmax, 384] = [S | T | q]
@@ -95,6 +95,18 @@ void launch_pair_edge_epi(const float* tmp, const float* gp, const float* bp, co
 // attn[b,j,:] = sum_i softmax_i(q[b,j,h].K[b,i,j,h]) V[b,i,j,h]   (KV [rows,256] = [K|V]; q pre-scaled)
 void launch_pair_attention(const float* kv, const float* stq, const SceneDesc* sd, float* attn, int b0, int nb,
                            int Nmax, cudaStream_t st);
+
+// ---- exact tier of the tensor-core mode (pair_x3.cu): row-wise epilogues between 3-term tcgen05 GEMMs on the compact
+// pair grid row = (s*Ns + i)*Ns + j of the small scenes sids[0..ns); every kernel emits the next GEMM's (hi, lo) operand
+void launch_x3_edge_init(const SceneDesc* sd, const int32_t* sids, const float* ctrs, const float* vecs, const float* W,
+                         const float* b, const float* g, const float* be, float* e32, __half* eh, __half* el, int ns, int Ns,
+                         cudaStream_t st);
+void launch_x3_memory_epi(const float* tmp, const float* stq, const int32_t* sids, const float* g, const float* be, __half* mh,
+                          __half* ml, int ns, int Ns, int Nmax, cudaStream_t st);
+void launch_x3_edge_epi(const float* tmp, const float* gp, const float* bp, const float* ge, const float* bee, float* e32,
+                        __half* eh, __half* el, int64_t rows, cudaStream_t st);
+void launch_x3_attention(const float* kv, const float* stq, const SceneDesc* sd, const int32_t* sids, __half* ah, __half* al,
+                         int ns, int Ns, int Nmax, cudaStream_t st);
 
 // ---- decoder pieces (reference network.py:483-556) -----------------------------------------
 // self attention over the 6 modes of each scene: qkv [B*6,384] -> out [B*6,128], 4 heads

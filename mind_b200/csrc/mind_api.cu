@@ -107,6 +107,7 @@ struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     SceneDesc* d_sd = nullptr;
     int32_t* d_actor_scene = nullptr;
+    int32_t* d_small = nullptr;
     TcForwardState tcf;
     int64_t launches = 0;
     uint64_t last_use = 0;
@@ -138,6 +139,10 @@ struct MindCtx {
     int* lane_err = nullptr;
     struct NodeW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; int N = 0, K = 0, n_tile = 128; };
     NodeW node_tc[6][4];          // per fusion layer: [S|T|q] (384x128), out-proj (128x128), linear1 (256x128), linear2 (128x256)
+    // exact tier of the tensor-core mode (scenes with fewer than tc_min_tokens tokens): W_e, W_pe, W_k|W_v as 3-term operands
+    NodeW pair_tc[6][3];
+    int tc_min_tokens = 128;
+    int32_t* d_small = nullptr; int small_cap = 0;
     // descriptor tables
     SceneDesc* d_sd = nullptr; int sd_cap = 0;
     int32_t* d_actor_scene = nullptr; int as_cap = 0;
@@ -150,6 +155,7 @@ static void graph_entry_free(GraphEntry& e) {
     if (e.exec) cudaGraphExecDestroy(e.exec);
     if (e.d_sd) cudaFree(e.d_sd);
     if (e.d_actor_scene) cudaFree(e.d_actor_scene);
+    if (e.d_small) cudaFree(e.d_small);
     tc_free_forward_state(e.tcf);
     e = GraphEntry{};
 }
@@ -189,11 +195,13 @@ extern "C" void mind_destroy(MindCtx* c) {
     if (c->arena) cudaFree(c->arena);
     if (c->d_sd) cudaFree(c->d_sd);
     if (c->d_actor_scene) cudaFree(c->d_actor_scene);
+    if (c->d_small) cudaFree(c->d_small);
     tc_free(c->tc);
     actor_tc_free(c->actor_tc);
     for (auto& blk : c->lane_tc) for (auto& lw : blk) if (lw.W) cudaFree(lw.W);
     if (c->lane_err) cudaFree(c->lane_err);
     for (auto& lay : c->node_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
+    for (auto& lay : c->pair_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
     delete c;
 }
 
@@ -216,6 +224,12 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
         if (!c->use_graph) graph_cache_clear(c);
     } else if (!strcmp(name, "profile")) {
         c->prof.on = value != 0;
+    } else if (!strcmp(name, "tc_min_tokens")) {
+        // tensor-core mode: scenes with fewer tokens than this run the exact (3-term, fp32 edge) tier instead of the
+        // fp16-operand fused kernel; 0 = fused kernel for every scene
+        if (value < 0) return fail("tc_min_tokens must be >= 0");
+        if (c->tc_min_tokens != (int)value) graph_cache_clear(c);
+        c->tc_min_tokens = (int)value;
     } else if (!strcmp(name, "chunk_scenes")) {
         if (value < 1) return fail("chunk_scenes must be >= 1");
         c->chunk_scenes = (int)value;
@@ -461,6 +475,14 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
             if ((e3 = pack(c->node_tc[l][1], *find(c, P + "multihead_attn.out_proj.weight"), 128, 128, 128))) return fail("node pack: %s", e3);
             if ((e3 = pack(c->node_tc[l][2], *find(c, P + "linear1.weight"), 256, 128, 256))) return fail("node pack: %s", e3);
             if ((e3 = pack(c->node_tc[l][3], *find(c, P + "linear2.weight"), 128, 256, 128))) return fail("node pack: %s", e3);
+            // exact tier: the N^2-row contractions W_e (proj_memory.0.weight[:, :128]), W_pe, W_k|W_v (in_proj rows 128..383)
+            std::vector<float> We((size_t)128 * 128);
+            for (int o = 0; o < 128; ++o)
+                for (int k = 0; k < 128; ++k) We[(size_t)o * 128 + k] = (*Wm)[(size_t)o * 384 + k];
+            if ((e3 = pack(c->pair_tc[l][0], We, 128, 128, 128))) return fail("pair pack: %s", e3);
+            if (l < 5 && (e3 = pack(c->pair_tc[l][1], *find(c, P + "proj_edge.0.weight"), 128, 128, 128))) return fail("pair pack: %s", e3);
+            std::vector<float> Wkv(Win->begin() + 128 * 128, Win->end());
+            if ((e3 = pack(c->pair_tc[l][2], Wkv, 256, 128, 256))) return fail("pair pack: %s", e3);
         }
     }
     c->finalized = true;
@@ -498,6 +520,9 @@ struct Ws {
     __half *lh[3], *ll[3];     // lane-net fp16 hi/lo operand buffers [R,128]
     float* lt32;
     __half *xh, *xl, *ah, *al, *fh, *fl;   // token state / attention output / FFN hidden as fp16 hi/lo operands
+    // exact tier (compact pair grid of the small scenes): fp32 edge + operands of the 3-term GEMMs
+    float *xe32, *xtmp, *xkv;
+    __half *xeh, *xel, *xmh, *xml;
     // decoder
     float *actors_f, *cls_tok, *tr, *tg1, *tgt, *c1, *ce, *qkv, *att, *co, *f1, *f2, *a1, *ae, *embed, *h1, *h2, *param;
     float *k1, *k2, *logit;
@@ -505,7 +530,8 @@ struct Ws {
 
 int chunk_for(const MindCtx* c, int B) { return std::max(1, std::min(B, c->chunk_scenes)); }
 
-int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w) {
+// n_small scenes (each on an Ns x Ns compact pair grid) take the exact tier of the tensor-core mode, n_big the fused kernel
+int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, int n_small, int Ns, int n_big, Ws& w) {
     Carver cv(base);
     const int64_t Lp = (int64_t)L + B, R = Lp * 10, TOK = (int64_t)B * Nmax;
     w.actor_feat = cv.take<float>((int64_t)A * 128);
@@ -537,7 +563,14 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w
         w.xh = w.xl = w.ah = w.al = w.fh = w.fl = nullptr;
     } else {
         w.edge = w.tmp = w.memory = w.kv = nullptr;
-        w.edge16 = cv.take<__half>((int64_t)B * pairs * 128);
+        w.edge16 = n_big > 0 ? cv.take<__half>((int64_t)B * pairs * 128) : nullptr;
+        const int64_t xr = (int64_t)n_small * Ns * Ns;
+        w.xe32 = w.xtmp = w.xkv = nullptr; w.xeh = w.xel = w.xmh = w.xml = nullptr;
+        if (xr > 0) {
+            w.xe32 = cv.take<float>(xr * 128); w.xtmp = cv.take<float>(xr * 128); w.xkv = cv.take<float>(xr * 256);
+            w.xeh = cv.take<__half>(xr * 128 + 512); w.xel = cv.take<__half>(xr * 128 + 512);
+            w.xmh = cv.take<__half>(xr * 128 + 512); w.xml = cv.take<__half>(xr * 128 + 512);
+        }
         w.actor_ws = cv.take<char>(actor_tc_ws_bytes(A));
         for (int i = 0; i < 3; ++i) { w.lh[i] = cv.take<__half>(R * 128 + 512); w.ll[i] = cv.take<__half>(R * 128 + 512); }
         w.lt32 = cv.take<float>(R * 128);
@@ -572,8 +605,28 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, Ws& w
 
 extern "C" int64_t mind_workspace_bytes(MindCtx* c, int32_t B, int32_t A, int32_t L, int32_t Nmax) {
     if (!c || B <= 0 || A < 0 || L < 0 || Nmax <= 0) { fail("mind_workspace_bytes: bad argument"); return -1; }
+    Ws w;      // uniform batch: every scene has Nmax tokens (exact for tree levels and the benchmark batch)
+    const bool small = c->precision == MIND_PREC_F16TC && Nmax < c->tc_min_tokens;
+    return carve(c, nullptr, B, A, L, Nmax, small ? B : 0, small ? Nmax : 0, small ? 0 : B, w);
+}
+
+// exact requirement of one batch (ragged scenes: how many take which tier follows from the offsets)
+static void tier_split(const MindCtx* c, const MindBatch* bt, int& Nmax, int& n_small, int& Ns, int& n_big) {
+    Nmax = n_small = Ns = n_big = 0;
+    for (int b = 0; b < bt->n_scenes; ++b) {
+        const int n = (bt->actor_off[b + 1] - bt->actor_off[b]) + (bt->lane_off[b + 1] - bt->lane_off[b]) + 1;
+        Nmax = std::max(Nmax, n);
+        if (c->precision == MIND_PREC_F16TC && n < c->tc_min_tokens) { ++n_small; Ns = std::max(Ns, n); }
+        else ++n_big;
+    }
+}
+extern "C" int64_t mind_workspace_bytes_batch(MindCtx* c, const MindBatch* bt) {
+    if (!c || !bt || bt->n_scenes <= 0 || !bt->actor_off || !bt->lane_off) { fail("mind_workspace_bytes_batch: bad argument"); return -1; }
+    int Nmax, n_small, Ns, n_big;
+    tier_split(c, bt, Nmax, n_small, Ns, n_big);
     Ws w;
-    return carve(c, nullptr, B, A, L, Nmax, w);
+    const int B = bt->n_scenes;
+    return carve(c, nullptr, B, bt->actor_off[B] - bt->actor_off[0], bt->lane_off[B] - bt->lane_off[0], Nmax, n_small, Ns, n_big, w);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -771,6 +824,8 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     int Nmax = 0;
     std::vector<SceneDesc> sd(B);
     std::vector<int32_t> actor_scene((size_t)std::max(A, 1));
+    std::vector<int32_t> small_ids;      // tensor-core mode: scenes that take the exact tier
+    int Ns = 0;
     for (int b = 0; b < B; ++b) {
         const int na = bt->actor_off[b + 1] - bt->actor_off[b], nl = bt->lane_off[b + 1] - bt->lane_off[b];
         if (na <= 0 || nl < 0) return fail("mind_forward: scene %d has %d actors / %d lanes", b, na, nl);
@@ -781,10 +836,12 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         sd[b].rpe = bt->rpe ? bt->rpe[b] : nullptr;
         if (bt->rpe && !bt->rpe[b]) return fail("mind_forward: rpe[%d] is null", b);
         Nmax = std::max(Nmax, na + nl + 1);
+        if (c->precision == MIND_PREC_F16TC && na + nl + 1 < c->tc_min_tokens) { small_ids.push_back(b); Ns = std::max(Ns, na + nl + 1); }
         for (int a = 0; a < na; ++a) actor_scene[(size_t)bt->actor_off[b] + a] = b;
     }
+    const int n_small = (int)small_ids.size(), n_big = B - n_small;
     Ws w;
-    const int64_t needb = carve(c, workspace, B, A, Ltot, Nmax, w);
+    const int64_t needb = carve(c, workspace, B, A, Ltot, Nmax, n_small, Ns, n_big, w);
     if (needb > workspace_bytes) return fail("mind_forward: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)needb);
     if ((((uintptr_t)workspace) & 255) != 0) return fail("mind_forward: workspace must be 256-byte aligned");
 
@@ -796,7 +853,8 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         std::vector<uint64_t> key;
         key.reserve(16 + 3 * (size_t)B);
         auto kp = [&](const void* p) { key.push_back((uint64_t)(uintptr_t)p); };
-        key.push_back((uint64_t)B); key.push_back((uint64_t)A); key.push_back((uint64_t)Ltot); key.push_back((uint64_t)c->precision);
+        key.push_back((uint64_t)B); key.push_back((uint64_t)A); key.push_back((uint64_t)Ltot);
+        key.push_back((uint64_t)c->precision | ((uint64_t)c->tc_min_tokens << 8));
         kp(bt->actors); kp(bt->lanes); kp(bt->ctrs); kp(bt->vecs); kp(bt->tgt_nodes); kp(bt->tgt_rpe);
         kp(out->cls); kp(out->reg); kp(out->vel); kp(out->cov_vel); kp(out->param); kp(workspace); kp(cuda_stream);
         for (int b = 0; b <= B; ++b) key.push_back(((uint64_t)(uint32_t)bt->actor_off[b] << 32) | (uint32_t)bt->lane_off[b]);
@@ -834,21 +892,24 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     // the context's own tables are set aside while a capture builds the entry's private ones
     SceneDesc* keep_sd = c->d_sd; const int keep_sd_cap = c->sd_cap;
     int32_t* keep_as = c->d_actor_scene; const int keep_as_cap = c->as_cap;
+    int32_t* keep_small = c->d_small; const int keep_small_cap = c->small_cap;
     const TcForwardState keep_tcf = c->tc;
     if (capture) {
-        c->d_sd = nullptr; c->sd_cap = 0; c->d_actor_scene = nullptr; c->as_cap = 0;
+        c->d_sd = nullptr; c->sd_cap = 0; c->d_actor_scene = nullptr; c->as_cap = 0; c->d_small = nullptr; c->small_cap = 0;
         (TcForwardState&)c->tc = TcForwardState{};
     }
     auto restore_tables = [&](bool adopt) {
         if (!capture) return;
         if (adopt) {
-            ge->d_sd = c->d_sd; ge->d_actor_scene = c->d_actor_scene; ge->tcf = c->tc;
+            ge->d_sd = c->d_sd; ge->d_actor_scene = c->d_actor_scene; ge->d_small = c->d_small; ge->tcf = c->tc;
         } else {
             if (c->d_sd) cudaFree(c->d_sd);
             if (c->d_actor_scene) cudaFree(c->d_actor_scene);
+            if (c->d_small) cudaFree(c->d_small);
             tc_free_forward_state(c->tc);
         }
         c->d_sd = keep_sd; c->sd_cap = keep_sd_cap; c->d_actor_scene = keep_as; c->as_cap = keep_as_cap;
+        c->d_small = keep_small; c->small_cap = keep_small_cap;
         (TcForwardState&)c->tc = keep_tcf;
     };
 
@@ -869,8 +930,17 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         if (const char* e = c->stage.begin()) return fail("mind_forward: %s", e);
         if (const char* e = c->stage.upload(c->d_sd, sd.data(), sizeof(SceneDesc) * (size_t)B, st)) return fail("mind_forward: %s", e);
         if (const char* e = c->stage.upload(c->d_actor_scene, actor_scene.data(), sizeof(int32_t) * (size_t)A, st)) return fail("mind_forward: %s", e);
+        if (n_small > 0) {
+            if (c->small_cap < n_small) {
+                if (c->d_small) cudaFree(c->d_small);
+                c->d_small = nullptr; c->small_cap = 0;
+                CUDA_OK(cudaMalloc(&c->d_small, sizeof(int32_t) * (size_t)n_small));
+                c->small_cap = n_small;
+            }
+            if (const char* e = c->stage.upload(c->d_small, small_ids.data(), sizeof(int32_t) * (size_t)n_small, st)) return fail("mind_forward: %s", e);
+        }
         if (c->precision == MIND_PREC_F16TC)
-            if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, w.edge16, c->stage, st)) return fail("tc_prepare: %s", perr);
+            if (const char* perr = tc_prepare(c->tc, sd, B, Nmax, c->tc_min_tokens, w.edge16, c->stage, st)) return fail("tc_prepare: %s", perr);
         c->stage.end(st);
         return 0;
     };
@@ -932,7 +1002,9 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
             }
         }
     } else {
-        launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, st);
+        if (n_big > 0) launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, c->tc_min_tokens, st);
+        const int64_t xrows = (int64_t)n_small * Ns * Ns;
+        launch_x3_edge_init(c->d_sd, c->d_small, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.xe32, w.xeh, w.xel, n_small, Ns, st);
         const int64_t TOKR = (int64_t)B * Nmax;
         launch_split_hl(w.x, w.xh, w.xl, TOKR * 128, st);                      // token state as fp16 hi/lo operand
         CUDA_OK(cudaMemsetAsync(w.ah, 0, sizeof(__half) * (size_t)TOKR * 128, st));   // padded token rows are never written by the fused kernel
@@ -941,9 +1013,27 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         for (int l = 0; l < 6; ++l) {
             if (const char* e = run_node_pre_tc(c, l, w, TOKR, st)) return fail("node_pre_tc(%d): %s", l, e);
             PROF_NEXT("node_pre");
-            const char* err = tc_fusion_layer(c->tc, l, w.stq, w.ah, w.al, c->sm_count, st);
-            if (err) return fail("tc_fusion_layer(%d): %s", l, err);
-            PROF_NEXT(l < 5 ? "fusion_tc" : "fusion_tc_last");
+            if (n_big > 0) {
+                const char* err = tc_fusion_layer(c->tc, l, w.stq, w.ah, w.al, c->sm_count, st);
+                if (err) return fail("tc_fusion_layer(%d): %s", l, err);
+                PROF_NEXT(l < 5 ? "fusion_tc" : "fusion_tc_last");
+            }
+            if (n_small > 0) {      // exact tier: un-fused pair pipeline, 3-term GEMMs, fp32 edge (network.py:197-226)
+                const FusionLayerW& f = c->fl[l];
+                const char* e;
+                if ((e = node_tc_gemm(c, c->pair_tc[l][0], w.xeh, w.xel, xrows, nullptr, 0, w.xtmp, 128, nullptr, nullptr, 0, st)))
+                    return fail("x3 W_e(%d): %s", l, e);
+                launch_x3_memory_epi(w.xtmp, w.stq, c->d_small, f.mem_g, f.mem_b, w.xmh, w.xml, n_small, Ns, Nmax, st);
+                if (f.Wpe) {
+                    if ((e = node_tc_gemm(c, c->pair_tc[l][1], w.xmh, w.xml, xrows, f.bpe, 0, w.xtmp, 128, nullptr, nullptr, 0, st)))
+                        return fail("x3 W_pe(%d): %s", l, e);
+                    launch_x3_edge_epi(w.xtmp, f.pe_g, f.pe_b, f.ne_g, f.ne_b, w.xe32, w.xeh, w.xel, xrows, st);
+                }
+                if ((e = node_tc_gemm(c, c->pair_tc[l][2], w.xmh, w.xml, xrows, f.bkv, 0, w.xkv, 256, nullptr, nullptr, 0, st)))
+                    return fail("x3 W_kv(%d): %s", l, e);
+                launch_x3_attention(w.xkv, w.stq, c->d_sd, c->d_small, w.ah, w.al, n_small, Ns, Nmax, st);
+                PROF_NEXT("fusion_x3");
+            }
             if (const char* e = run_node_post_tc(c, l, w, TOKR, st)) return fail("node_post_tc(%d): %s", l, e);
             PROF_NEXT("node_post");
         }

@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(256) k_edge_init_h8(const SceneDesc* __restric
                                                       const float* __restrict__ vecs, const float* __restrict__ W,
                                                       const float* __restrict__ bias, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, __half* __restrict__ edge, int nb,
-                                                      int Nmax) {
+                                                      int Nmax, int min_tokens) {
     const int lane = threadIdx.x & 31;
     const int units_per_row = (Nmax + 7) >> 3;
     const int64_t n_units = (int64_t)nb * Nmax * units_per_row;
@@ -722,6 +722,7 @@ __global__ void __launch_bounds__(256) k_edge_init_h8(const SceneDesc* __restric
         const int i = (int)(bi_ % Nmax), b = (int)(bi_ / Nmax);
         const SceneDesc d = sd[b];
         const int M = d.n_actor + d.n_lane;
+        if (M + 1 < min_tokens) continue;        // exact-tier scene: its edge lives in the fp32 pair grid
         const int j0 = j8 * 8;
         // slot s = k*8 + jj (k < 4) in lanes 0..31, slots 32..39 (k = 4) in lanes 0..7
         float va = 0.f, vb = 0.f;
@@ -775,11 +776,11 @@ __global__ void __launch_bounds__(256) k_edge_init_h8(const SceneDesc* __restric
 }
 
 void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
-                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, cudaStream_t st) {
+                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st) {
     const int64_t units = (int64_t)nb * Nmax * ((Nmax + 7) / 8);
     if (units <= 0) return;
     const int64_t blocks = std::min<int64_t>((units + 7) / 8, 148 * 16);
-    k_edge_init_h8<<<(unsigned)blocks, 256, 0, st>>>(sd + b0, ctrs, vecs, W, b, g, be, edge, nb, Nmax);
+    k_edge_init_h8<<<(unsigned)blocks, 256, 0, st>>>(sd + b0, ctrs, vecs, W, b, g, be, edge, nb, Nmax, min_tokens);
     ++g_launches;
 }
 

@@ -65,7 +65,7 @@ class MindTreeUpdate(C.Structure):
 
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
-           "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_forward",
+           "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_workspace_bytes_batch", "mind_forward",
            "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_sync_check", "mind_profile_read",
            "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error", "mind_ilqr_tree_solve", "mind_ilqr_last_error", "mind_debug_field_eval"]
 
@@ -96,6 +96,8 @@ def load(build_if_missing: bool = True):
     lib.mind_set_option.restype = C.c_int
     lib.mind_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.mind_workspace_bytes.restype = C.c_int64
+    lib.mind_workspace_bytes_batch.argtypes = [C.c_void_p, C.POINTER(MindBatch)]
+    lib.mind_workspace_bytes_batch.restype = C.c_int64
     lib.mind_forward.argtypes = [C.c_void_p, C.POINTER(MindBatch), C.POINTER(MindOutputs), C.c_void_p,
                                  C.c_int64, C.c_void_p]
     lib.mind_forward.restype = C.c_int

@@ -269,9 +269,9 @@ class ScenePredNetB200:
                 self._out_cache[(B, A)] = outs
         cls, reg, vel, cov_vel, param = outs
         out = _lib.MindOutputs(cls.data_ptr(), reg.data_ptr(), vel.data_ptr(), cov_vel.data_ptr(), param.data_ptr())
-        need = self._lib.mind_workspace_bytes(self._h, B, A, L, nmax)
+        need = self._lib.mind_workspace_bytes_batch(self._h, C.byref(bt))
         if need < 0:
-            _lib.check(1, "mind_workspace_bytes")
+            _lib.check(1, "mind_workspace_bytes_batch")
         ws = self._workspace(need)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
