@@ -22,8 +22,14 @@ def _have(name: str) -> bool:
         return False
 
 
+_installed = None      # decision of the first install(): later calls return it instead of re-probing / re-registering
+
+
 def install(force: bool = False) -> dict:
-    """Register the stand-ins in sys.modules.  Returns {package: 'real' | 'lite'}."""
+    """Register the stand-ins in sys.modules (once).  Returns {package: 'real' | 'lite'}."""
+    global _installed
+    if _installed is not None and not force:
+        return dict(_installed)
     used = {}
     if force or not _have("av2"):
         from . import av2_lite
@@ -66,4 +72,5 @@ def install(force: bool = False) -> dict:
         used["matplotlib"] = "stub (no rendering)"
     else:
         used["matplotlib"] = "real"
+    _installed = dict(used)
     return used

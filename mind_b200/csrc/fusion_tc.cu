@@ -285,9 +285,6 @@ __device__ __forceinline__ uint32_t cvt_rn_h2(f2 v) {
 }
 __device__ __forceinline__ f2 h2_to_f2(uint32_t u) { const float2 f = unpack_h2(u); return pk2(f.x, f.y); }
 __device__ __forceinline__ void lds_2f2(const float* p, f2& a, f2& b) {     // 4 consecutive floats as two pairs
-#ifdef MIND_EXP_NOLDS      // timing experiment only (wrong results): how much do the epilogue's LDS cost / slow the MMAs?
-    a = b = 0x3f8000003f800000ull; return;
-#endif
     const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
     a = v.x; b = v.y;
 }
@@ -382,11 +379,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 
     // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (TMEM
     // addresses, barrier ids, role tests) in uniform registers instead of an R2UR in front of every tcgen05.ld / st
-#ifdef MIND_EXP_NOUNI      // A/B build: plain warp index
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#else
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-#endif
     if (tid == 0) {
         mbar_init(bar_w, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2a, 1); mbar_init(bar_m2b, 1);
         mbar_init(bar_ld0, 1); mbar_init(bar_ld0 + 8, 1);
@@ -634,33 +627,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 const uint32_t tX = sbase + SM_TILE0 + (g & 1) * 32768;  // edge tile (in place -> edge')
                 TR(0, g);
                 mbar_wait(bar_t, par, a.err, E_LOAD_EDGE + 10);          // T rows staged by the issuer
-#ifdef MIND_EXP_STPRE
-                // A/B build for the next round (profiles/r01_v8_stall_analysis.md, item 1): S[j] + T[i] of this thread's 32
-                // channels is formed in the shadow of the wait for G1, so that after the TMEM load one FADD2 per channel pair
-                // remains and no shared-memory load sits on the critical path of epilogue 1; a single-query item's T row
-                // (global memory: E1 pass 1 of such a tile takes ~8,000 cycles today) is fetched there as well.
-                // Not yet run on hardware.
-                f2 st2[16];
-                if (!mode) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        f2 sa, sb, ta, tb;
-                        lds_2f2(sS + (j_l * 132 + col0 + k4 * 4), sa, sb);
-                        lds_2f2(sT + (i_l * 128 + col0 + k4 * 4), ta, tb);
-                        st2[2 * k4] = add2(sa, ta); st2[2 * k4 + 1] = add2(sb, tb);
-                    }
-                } else {     // single-query item: the T row comes from global memory; eight independent loads in flight during the wait
-                    ulonglong2 tv[8];
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) tv[k4] = __ldg(reinterpret_cast<const ulonglong2*>(Tg + col0 + k4 * 4));
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        f2 sa, sb;
-                        lds_2f2(sS + (j_l * 132 + col0 + k4 * 4), sa, sb);
-                        st2[2 * k4] = add2(sa, tv[k4].x); st2[2 * k4 + 1] = add2(sb, tv[k4].y);
-                    }
-                }
-#endif
                 mbar_wait(bar_m1, par, a.err, E_MMA1);
                 TR(1, g);
                 tc_fence_after();
@@ -669,11 +635,9 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 // streaming 16-column passes; x = D1 + S + T is parked in this thread's own Dpe cells
                 // (free until G2 of this tile is issued) so nothing has to live in registers across the barrier
                 const uint32_t scr_t = tmem + lane_base + 128 + col0;
-#ifdef MIND_EXP_XREG
                 // A/B build for the next round: x stays in 32 registers across the row-group barrier instead of a round trip
                 // through the TMEM scratch cells (2 tcgen05.st + wait::st + 2 tcgen05.ld per thread-tile).  Not yet run on hardware.
                 uint32_t xr[32];
-#endif
                 auto e1_pass1 = [&](auto qtag) {                   // two straight-line copies: no branch inside the unrolled loops
                     constexpr bool kQ = decltype(qtag)::value;
                     f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
@@ -688,11 +652,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
-#ifdef MIND_EXP_STPRE
-                            (void)c;
-                            const f2 x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), st2[2 * (hf * 4 + k4)]);
-                            const f2 x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), st2[2 * (hf * 4 + k4) + 1]);
-#else
                             f2 sa, sb, ta, tb;
                             lds_2f2(sS + (j_l * 132 + c), sa, sb);
                             if constexpr (kQ) {
@@ -703,38 +662,20 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                             }
                             const f2 x0 = add2(add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), sa), ta);
                             const f2 x1 = add2(add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), sb), tb);
-#endif
                             upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
                             upk2u(x1, r[k4 * 4 + 2], r[k4 * 4 + 3]);
                             s1a = add2(s1a, x0); s1b = add2(s1b, x1);
                             s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                         }
-#ifdef MIND_EXP_XREG
 #pragma unroll
                         for (int e = 0; e < 16; ++e) xr[hf * 16 + e] = r[e];
-#else
-                        TMEM_ST_X16(scr_t + hf * 16, r);
-#endif
                     }
                     sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
-#ifndef MIND_EXP_XREG
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-#endif
                 };
                 if (mode) e1_pass1(std::true_type{});
                 else e1_pass1(std::false_type{});
                 tc_fence_before();
                 TR(2, g);
-#ifdef MIND_EXP_P2PRE
-                // A/B build for the next round (profiles/r01_v8_stall_analysis.md, item 2): LN_mem gamma / beta of the first 16
-                // channels are loaded in front of the row-group barrier instead of behind it.  Not yet run on hardware.
-                f2 pg2[8], pb2[8];
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    lds_2f2(sP + (P_MEM_G * 128 + col0 + k4 * 4), pg2[2 * k4], pg2[2 * k4 + 1]);
-                    lds_2f2(sP + (P_MEM_B * 128 + col0 + k4 * 4), pb2[2 * k4], pb2[2 * k4 + 1]);
-                }
-#endif
                 row_group_sync(lg);                                // statistics exchanged, D1 reads of these lanes retired
                 TR(3, g);
                 tc_fence_after();
@@ -745,32 +686,15 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
                     const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
-#ifdef MIND_EXP_XREG
                     uint32_t (&rr)[32] = xr;
-#else
-                    uint32_t rr[2][16];
-                    TMEM_LD_X16_NM(scr_t, rr[0]);
-                    TMEM_LD_X16_NM(scr_t + 16, rr[1]);
-                    TMEM_WAIT_LD_R16(rr[0]);
-                    TMEM_PIN_R16(rr[1]);
-#endif
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-#ifdef MIND_EXP_XREG
                         uint32_t* r = rr + hf * 16;
-#else
-                        uint32_t (&r)[16] = rr[hf];
-#endif
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const int c = col0 + hf * 16 + k4 * 4;
                             f2 ga, gb, ba, bb;
-#ifdef MIND_EXP_P2PRE
-                            if (hf == 0) {
-                                ga = pg2[2 * k4]; gb = pg2[2 * k4 + 1]; ba = pb2[2 * k4]; bb = pb2[2 * k4 + 1];
-                            } else
-#endif
                             {
                                 lds_2f2(sP + (P_MEM_G * 128 + c), ga, gb);
                                 lds_2f2(sP + (P_MEM_B * 128 + c), ba, bb);
@@ -803,18 +727,12 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                     mbar_wait(bar_m2a, par, a.err, E_MMA2);
                     TR(7, g);
                     tc_fence_after();
-#ifdef MIND_EXP_XREG2
                     // A/B build for the next round: Dpe + b stays in 32 registers from pass A to pass C (no TMEM scratch round
                     // trips, b_pe loaded and added once instead of twice).  Not yet run on hardware.
                     uint32_t er[2][16];
-#endif
                     {   // pass A: statistics of Dpe + b
                         f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
-#ifdef MIND_EXP_XREG2
                         uint32_t (&rr)[2][16] = er;
-#else
-                        uint32_t rr[2][16];
-#endif
                         TMEM_LD_X16_NM(scr_t, rr[0]);
                         TMEM_LD_X16_NM(scr_t + 16, rr[1]);
                         TMEM_WAIT_LD_R16(rr[0]);
@@ -828,10 +746,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                 lds_2f2(sP + (P_BPE * 128 + col0 + hf * 16 + k4 * 4), ba, bb);
                                 const f2 x0 = add2(pk2u(r[k4 * 4 + 0], r[k4 * 4 + 1]), ba);
                                 const f2 x1 = add2(pk2u(r[k4 * 4 + 2], r[k4 * 4 + 3]), bb);
-#ifdef MIND_EXP_XREG2
                                 upk2u(x0, r[k4 * 4 + 0], r[k4 * 4 + 1]);
                                 upk2u(x1, r[k4 * 4 + 2], r[k4 * 4 + 3]);
-#endif
                                 s1a = add2(s1a, x0); s1b = add2(s1b, x1);
                                 s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                             }
@@ -849,15 +765,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float rstd = rsqrtf(var + kEps);
                         const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
                         f2 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;
-#ifdef MIND_EXP_XREG2
                         uint32_t (&rr)[2][16] = er;
-#else
-                        uint32_t rr[2][16];
-                        TMEM_LD_X16_NM(scr_t, rr[0]);
-                        TMEM_LD_X16_NM(scr_t + 16, rr[1]);
-                        TMEM_WAIT_LD_R16(rr[0]);
-                        TMEM_PIN_R16(rr[1]);
-#endif
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t (&r)[16] = rr[hf];
@@ -873,15 +781,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                     lds_2f2(sP + (P_PE_B * 128 + c + h4 * 4), a0, a1);
                                     const int k = c8 * 8 + h4 * 4;
                                     float u0, u1, u2, u3;
-#ifdef MIND_EXP_XREG2
                                     upk2(fma2(fma2(pk2u(r[k + 0], r[k + 1]), r2, n2), g0, a0), u0, u1);
                                     upk2(fma2(fma2(pk2u(r[k + 2], r[k + 3]), r2, n2), g1, a1), u2, u3);
-#else
-                                    f2 b0, b1;
-                                    lds_2f2(sP + (P_BPE * 128 + c + h4 * 4), b0, b1);
-                                    upk2(fma2(fma2(add2(pk2u(r[k + 0], r[k + 1]), b0), r2, n2), g0, a0), u0, u1);
-                                    upk2(fma2(fma2(add2(pk2u(r[k + 2], r[k + 3]), b1), r2, n2), g1, a1), u2, u3);
-#endif
                                     const f2 x0 = add2(h2_to_f2(ev[h4 * 2 + 0]), pk2(fmaxf(u0, 0.f), fmaxf(u1, 0.f)));
                                     const f2 x1 = add2(h2_to_f2(ev[h4 * 2 + 1]), pk2(fmaxf(u2, 0.f), fmaxf(u3, 0.f)));
                                     upk2u(x0, r[k + 0], r[k + 1]);
@@ -890,14 +791,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                     s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                                 }
                             }
-#ifndef MIND_EXP_XREG2
-                            TMEM_ST_X16(scr_t + hf * 16, r);
-#endif
                         }
                         sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
-#ifndef MIND_EXP_XREG2
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-#endif
                     }
                     TR(10, g);
                     row_group_sync(lg);
@@ -909,15 +804,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
                         const f2 r2 = pk2(rstd, rstd), n2 = pk2(-mean * rstd, -mean * rstd);
-#ifdef MIND_EXP_XREG2
                         uint32_t (&rr)[2][16] = er;
-#else
-                        uint32_t rr[2][16];
-                        TMEM_LD_X16_NM(scr_t, rr[0]);
-                        TMEM_LD_X16_NM(scr_t + 16, rr[1]);
-                        TMEM_WAIT_LD_R16(rr[0]);
-                        TMEM_PIN_R16(rr[1]);
-#endif
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t (&r)[16] = rr[hf];
@@ -1299,11 +1186,7 @@ const char* tc_pack_weights(TcWeights& w, const TcHostLayer (&hl)[6]) {
 // ceil(n / 8) tiles that are 15/16 padding.  Every CTA gets a contiguous run of the tile sequence, equal to within one
 // tile: an item that straddles a boundary is split along the key axis and the partial softmax states of its parts are
 // merged by k_merge_parts.  work[0 .. grid) are the per-CTA range headers.
-#ifdef MIND_EXP_NOQ      // timing experiment: schedule without single-query items
-static const bool kSingleQueryItems = false;
-#else
 static const bool kSingleQueryItems = true;
-#endif
 // Default: every CTA gets one contiguous run of the scene-ordered tile sequence.  MIND_TC_SCHED=deal (development) deals
 // whole items round by round first and balances only the remainder; measured slower (single-query items pile up on the
 // last CTAs: 9.99 vs 9.84 ms per 5 launches).

@@ -309,6 +309,11 @@ extern "C" const char* mind_tree_last_error(void) { return g_terr; }
 extern "C" int mind_tree_level(const MindTreeLevel* a, void* cuda_stream) {
     using namespace mind;
     if (!a || a->n_frontier <= 0 || a->n_actor <= 0 || a->n_actor > 256) { snprintf(g_terr, sizeof g_terr, "mind_tree_level: bad argument"); return 1; }
+    // child histories are 100-step rows (50 observed + 50 predicted, planners/mind/planner.py:20-21,53): the kernels index them so
+    if (a->obs_len != 50 || a->pred_len != 50) {
+        snprintf(g_terr, sizeof g_terr, "mind_tree_level: obs_len / pred_len must be 50 / 50 (got %d / %d)", a->obs_len, a->pred_len);
+        return 1;
+    }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     k_tree_expand<<<a->n_frontier * 6 * a->n_actor, 128, 0, st>>>(*a);
     k_tree_select<<<a->n_frontier, 128, sizeof(float) * 6 * (size_t)std::max(a->n_actor - 1, 1), st>>>(*a);

@@ -184,7 +184,12 @@ class ScenePredNetB200:
             views = [base[offs[i]:offs[i] + sizes[i]].view(torch.float32).view(out.shapes[i]) for i in range(n)]
         for r, v in zip(rpe, views):
             out.append({"scene": v, "scene_mask": r.get("scene_mask") if isinstance(r, dict) else None})
-        self._keep_host = scenes                              # pinned sources must outlive the asynchronous copies
+        # pinned sources must outlive the asynchronous copies (torch's caching host allocator does not know about the
+        # library's cudaMemcpyAsync): hold them until an event recorded behind the upload has completed
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pending_host = [(e, src) for e, src in getattr(self, "_pending_host", []) if not e.query()]
+        self._pending_host.append((ev, scenes))
         return out
 
     # ---- reference network.py:582-595 ----

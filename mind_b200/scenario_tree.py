@@ -104,12 +104,14 @@ class _Level:
 
 
 class ScenarioTreeGeneratorB200:
-    def __init__(self, device, network, obs_len=50, pred_len=60, config=None):
+    def __init__(self, device, network, obs_len=50, pred_len=50, config=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ScenarioTreeGeneratorB200 needs a CUDA device (no CPU fallback)")
-        if obs_len != 50:
-            raise ValueError("obs_len must be 50 (the network's history length)")
+        if obs_len != 50 or pred_len != 50:
+            # the tree-step kernels lay child histories out as 100-step rows (50 observed + 50 predicted), which is what
+            # MINDPlanner passes (planners/mind/planner.py:20-21,53); anything else would read past a row
+            raise ValueError("obs_len / pred_len must be 50 / 50 (got %r / %r)" % (obs_len, pred_len))
         self.network, self.obs_len, self.pred_len = network, obs_len, pred_len
         self.seq_len = obs_len + pred_len
         self.config = config

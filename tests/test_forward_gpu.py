@@ -1,6 +1,7 @@
 """GPU parity tests: CUDA path (through the C ABI) vs golden vectors from the reference and vs
-the oracle on seeded inputs.  Tolerances: exact fp32 path 2e-5; tensor-core (fp16-operand) path
-1e-3 relative (north_star), mode order bit-exact."""
+the oracle on seeded inputs.  Tolerances: exact fp32 path 5e-5; tensor-core mode 5e-4 relative -- half of the 1e-3
+north_star allows (scenes of 128 tokens and more: fp16-operand fused kernel, measured <= 3.9e-4; smaller scenes: exact
+tier, ~1e-5) -- mode order bit-exact."""
 import ctypes as C
 
 import numpy as np
@@ -12,7 +13,7 @@ from conftest import load_golden, rel_err
 pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 5e-5
-TOL_TC = 1e-3
+TOL_TC = 5e-4
 
 
 @pytest.fixture(scope="module")

@@ -32,7 +32,7 @@ def make_net(sd, dev, prec):
     return net.to(dev).eval()
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("f16tc", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("f16tc", 5e-4)])
 @pytest.mark.parametrize("name", DEMOS)
 def test_forward_on_real_scene(ckpt_sd, name, prec, tol):
     dev = torch.device("cuda", 0)
@@ -77,15 +77,9 @@ def test_tree_on_real_scene(ckpt_sd, name, prec):
     frag, closest = fragile_depths(ckpt_sd, gold)
     print("%s %s: %d nodes, levels %s, closest merge decision %.4f rad from the threshold, fragile depths %s" %
           (name, prec, len(flat), gen.net_batches, closest, frag))
-    if prec == "f16tc" and frag and sorted(flat) != sorted(gold["tree"]):
-        # a merge decision inside the noise band flipped: everything decided above that depth must still be identical
-        d0 = min(frag)
-        keep = lambda keys: sorted(k for k in keys if int(k.split("_")[0]) < d0)
-        assert keep(flat) == keep(gold["tree"]) and list(gen.net_batches[:d0 + 1]) == list(gold["levels"][:d0 + 1])
-        sub = dict(gold, tree={k: v for k, v in gold["tree"].items() if int(k.split("_")[0]) < d0 and k in flat},
-                   levels=gen.net_batches)
-        compare_tree({k: v for k, v in flat.items() if k in sub["tree"]}, gen.net_batches, sub, 1e-3)
-        pytest.xfail("merge decision %.4f rad from its threshold flipped under fp16 operands (depth %d)" % (closest, d0))
+    # every real scene has fewer than 128 tokens: in the tensor-core mode they take the exact tier, so both precisions
+    # must reproduce the reference's branch / merge decisions node for node (north_star: bit-exact branch selection),
+    # including demo_3's decision 0.0176 rad from its threshold
     compare_tree(flat, gen.net_batches, gold, 1e-3)
 
 
@@ -115,7 +109,7 @@ def test_tree_level_inputs_on_real_scene(ckpt_sd, name):
         compare_level_inputs(got, want, coord_ulp(gold))
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("f16tc", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("f16tc", 5e-4)])
 @pytest.mark.parametrize("name", DEMOS)
 def test_forward_on_recorded_level_inputs(ckpt_sd, name, prec, tol):
     """the network on the level >= 1 batches exactly as the reference built them (3-4 scenes, lanes ~3-7 km away in the
