@@ -50,6 +50,19 @@ def make_batch(batch, seed0):
     return synth.batch_s2(batch=batch, n_actor=NA, n_lane=NL, seed0=seed0)
 
 
+def make_batch_dict(batch, seed0):
+    """The collated dict network.pre_process receives (scenario_tree.py:69-70): the 7 network inputs plus the per-scene
+    anchors the dense RPE was built from (TRAJS[b]['TRAJS_CTRS'/'TRAJS_VECS'], LANE_GRAPH[b]['lane_ctrs'/'lane_vecs'],
+    scenario_tree.py:160-186, utils.py:468-483), as collate_fn leaves them (lists over scenes)."""
+    from mind_b200 import synth
+    scenes = [synth.scene_s1(seed0 + b, NA, NL, with_geom=True) for b in range(batch)]
+    keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+    d = dict(zip(keys, synth.batch_from_scenes(scenes)))
+    d["TRAJS"] = [{"TRAJS_CTRS": s["ctrs"][:NA].contiguous(), "TRAJS_VECS": s["vecs"][:NA].contiguous()} for s in scenes]
+    d["LANE_GRAPH"] = [{"lane_ctrs": s["ctrs"][NA:].contiguous(), "lane_vecs": s["vecs"][NA:].contiguous()} for s in scenes]
+    return d
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -110,30 +123,84 @@ def fusion_bytes_per_scene(update_edge=True):
     return N_TOK * N_TOK * D * 2.0 * (2 if update_edge else 1)
 
 
-def cpu_threads():
-    """Threads for the CPU port.  torch's intra-op pool degrades badly past ~16 threads on this
-    workload (measured on the 128-core GPU-box host: 128 threads -> 0.03 scenes/s, 32 s/scene),
-    so the port uses min(host cores, 16) and reports that number as `cores`."""
-    return max(1, min(os.cpu_count() or 1, int(os.environ.get("MIND_CPU_THREADS", "16"))))
+def cpu_layout():
+    """(processes, threads per process) for the CPU port.  torch's intra-op pool degrades badly past ~16 threads on this
+    workload (measured on the 128-core GPU-box host: 128 threads -> 0.03 scenes/s, 32 s/scene), so the host cores are
+    used as several 16-thread processes, each predicting its own scenes."""
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, int(os.environ.get("MIND_CPU_THREADS", "16"))))
+    procs = max(1, min(cores // threads, int(os.environ.get("MIND_CPU_PROCS", "8"))))
+    return procs, threads
 
 
-def cpu_port_rate(sd, seconds_target=10.0, chunk=2, seed0=5000):
-    """Reference algorithm on the host cores: the oracle port (torch CPU, all threads), bounded
-    sample of the same workload (S2 scenes 32x128)."""
+def _cpu_worker(idx, threads, chunk, seed0, seconds, warm, q, go):
+    torch.set_num_threads(threads)
     from oracle.scene_pred_oracle import ScenePredOracle
-    cores = cpu_threads()
-    torch.set_num_threads(cores)
-    orc = ScenePredOracle(sd)
-    data = make_batch(chunk, seed0)
-    orc(data)   # warm-up
+    orc = ScenePredOracle(load_weights())
+    data = make_batch(chunk, seed0 + 100 * idx)
+    for _ in range(warm):
+        orc(data)
+    q.put(("ready", idx))
+    go.wait()
     n, t0 = 0, time.perf_counter()
     while True:
         orc(data)
         n += chunk
         el = time.perf_counter() - t0
-        if el >= seconds_target:
+        if el >= seconds:
             break
-    return n / el, cores, "%d S2 scenes (32 actors x 128 lanes) in %.1f s, batches of %d" % (n, el, chunk)
+    q.put(("done", idx, n, el))
+
+
+def cpu_port_rate(sd, seconds_target=10.0, chunk=2, seed0=5000):
+    """Reference algorithm on the host cores: the oracle port (torch CPU fp32) in `procs` processes of `threads` threads,
+    bounded sample of the same workload (S2 scenes 32x128).  Returns (scenes/s over all processes, cores used, sample)."""
+    import multiprocessing as mp
+    procs, threads = cpu_layout()
+    ctx = mp.get_context("spawn")
+    q, go = ctx.Queue(), ctx.Event()
+    ps = [ctx.Process(target=_cpu_worker, args=(i, threads, chunk, seed0, seconds_target, 1, q, go)) for i in range(procs)]
+    for p_ in ps:
+        p_.start()
+    for _ in ps:
+        q.get(timeout=600)
+    go.set()
+    res = [q.get(timeout=600) for _ in ps]
+    for p_ in ps:
+        p_.join(timeout=60)
+    n = sum(r[2] for r in res)
+    el = max(r[3] for r in res)
+    return n / el, procs * threads, ("%d S2 scenes (32 actors x 128 lanes) in %.1f s, %d process(es) x %d threads, batches of %d (host has %d cores)"
+                                     % (n, el, procs, threads, chunk, os.cpu_count() or 1))
+
+
+def gpu_eager_rate(sd, dev, batches=(8, 64)):
+    """Second baseline: the reference network's arithmetic under torch EAGER on this same GPU (cuBLAS /
+    ATen kernels, fp32, the reference's Python loop over scenes, network.py:318,497).  The reference module itself cannot
+    travel to the box, so this is the oracle's functional restatement of it with its tensors on the device (kind "port";
+    same op sequence as the nn.Module: Linear / LayerNorm / softmax / einsum per scene).  Never fatal."""
+    out = {"kind": "port (oracle/scene_pred_oracle.py on cuda, torch eager fp32, TF32 off)", "unit": UNIT}
+    try:
+        from oracle.scene_pred_oracle import ScenePredOracle
+        torch.backends.cuda.matmul.allow_tf32 = False
+        orc = ScenePredOracle(sd, device=dev)
+        for nb in batches:
+            data = make_batch(nb, 7000)
+            data = (data[0].to(dev), data[1], data[2].to(dev), data[3], [{"scene": r["scene"].to(dev), "scene_mask": None} for r in data[4]],
+                    data[5].to(dev), data[6].to(dev))
+            orc(data)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3 if nb <= 8 else 2
+            e0.record()
+            for _ in range(reps):
+                orc(data)
+            e1.record()
+            torch.cuda.synchronize()
+            out["scenes_per_s_B%d" % nb] = nb * reps / (e0.elapsed_time(e1) * 1e-3)
+    except Exception as e:
+        out["error"] = repr(e)[:300]
+    return out
 
 
 class _TreeCfg:      # planners/mind/configs/planning/demo_1.py:3-10
@@ -295,32 +362,84 @@ def bench_cost_fields(dev, reps=5):
         return {"error": repr(e)[:300]}
 
 
+def bench_closed_loop(net, dev):
+    """BASELINE.json configs[4]: plan calls recorded while the UNMODIFIED reference drove demo_1..4 closed loop on the CPU
+    (oracle/record_plan_calls.py) replayed on the product's planner stack on this GPU (mind_b200/integration/replay.py:
+    scenario tree on the CUDA predictor, GPU cost fields, native tree iLQR).  Wall time per plan call from the collated
+    scene dict (host) to the returned control, next to the reference's time for the same call on the CPU it was recorded
+    on, and the largest control difference.  Never fatal."""
+    import glob
+    import numpy as np
+    out = {}
+    try:
+        from mind_b200.integration.replay import replay_file
+        for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "plan_calls_demo_*.pt.xz"))):
+            rec, res = replay_file(path, dev, net)
+            tot = [r["seconds"]["total"] for r in res]
+            out[rec["demo"]] = {
+                "plan_calls_replayed": len(res), "plan_calls_in_run": rec["n_plan_calls"],
+                "ms_per_plan_call": 1e3 * statistics.median(tot),
+                "scenario_tree_ms": 1e3 * statistics.median(r["seconds"]["scenario_tree"] for r in res),
+                "optimizer_ms": 1e3 * statistics.median(r["seconds"]["optimizer"] for r in res),
+                "trees_per_call": sum(r["n_trees"] for r in res) / len(res),
+                "reference_cpu_ms_per_plan_call": 1e3 * statistics.median(r["ref_seconds"]["scenario_tree"] + r["ref_seconds"]["optimizer"] for r in res),
+                "reference_cpu_host": rec["host"],
+                "same_scenario_trees": all(r["same_trees"] for r in res),
+                "same_chosen_tree": all(r["best_idx"] in r["ref_best"] for r in res),
+                "max_abs_ctrl_diff": [float(v) for v in np.max([np.abs(r["ctrl"] - r["ref_ctrl"]) for r in res], axis=0)]}
+        out["note"] = ("replay of recorded closed-loop plan calls (inputs = what the reference's process_data produced at that call); "
+                       "the front end (process_data, host code) is not inside these times")
+    except Exception as e:
+        out["error"] = repr(e)[:300]
+    return out
+
+
 def run_reference(args):
+    """--impl reference: the reference algorithm's CPU port (oracle/) on all the host cores it can use (several 16-thread
+    processes); each "step" is a bounded sample of the workload: every process predicts 4 of the 256 scenes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sd = load_weights()
-    from oracle.scene_pred_oracle import ScenePredOracle
-    cores = cpu_threads()
-    torch.set_num_threads(cores)
-    orc = ScenePredOracle(sd)
-    per_step = 4      # bounded sample: each step predicts 4 of the 256 scenes of the workload
-    data = make_batch(per_step, 1000)
-    for _ in range(args.warmup):
-        orc(data)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc(data)
-    el = time.perf_counter() - t0
-    v = per_step * args.steps / el
+    import multiprocessing as mp
+    procs, threads = cpu_layout()
+    per_step = 4
+    ctx = mp.get_context("spawn")
+    q, go = ctx.Queue(), ctx.Event()
+    ps = [ctx.Process(target=_ref_worker, args=(i, threads, per_step, args.warmup, args.steps, q, go)) for i in range(procs)]
+    for p_ in ps:
+        p_.start()
+    for _ in ps:
+        q.get(timeout=1200)
+    go.set()
+    res = [q.get(timeout=3000) for _ in ps]
+    for p_ in ps:
+        p_.join(timeout=60)
+    el = max(r[1] for r in res)
+    v = procs * per_step * args.steps / el
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "S2: 32 actors x 128 lanes, K=6; CPU sample of %d scenes/step" % per_step},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d scenes/step x %d steps, oracle port (torch CPU fp32)" % (per_step, args.steps)},
+            "config": {"workload": "S2: 32 actors x 128 lanes, K=6; CPU sample of %d scenes/step (%d processes x %d scenes)" % (procs * per_step, procs, per_step)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs * threads, "kind": "port",
+                             "sample": "%d processes x %d threads, %d scenes/step each x %d steps, oracle port (torch CPU fp32); host has %d cores"
+                                       % (procs, threads, per_step, args.steps, os.cpu_count() or 1)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def _ref_worker(idx, threads, per_step, warmup, steps, q, go):
+    torch.set_num_threads(threads)
+    from oracle.scene_pred_oracle import ScenePredOracle
+    orc = ScenePredOracle(load_weights())
+    data = make_batch(per_step, 1000 + 10 * idx)
+    for _ in range(max(1, warmup)):
+        orc(data)
+    q.put(("ready", idx))
+    go.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc(data)
+    q.put(("done", time.perf_counter() - t0))
 
 
 def run_native(args):
@@ -339,8 +458,9 @@ def run_native(args):
     net.load_state_dict(sd)
     net.set_precision(args.precision)
     B = args.batch
-    host = make_batch(B, 1000 + rank * B)
     keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+    host_full = make_batch_dict(B, 1000 + rank * B)
+    host = tuple(host_full[k] for k in keys)
 
     def pin(x):
         if isinstance(x, torch.Tensor):
@@ -350,23 +470,35 @@ def run_native(args):
         if isinstance(x, dict):
             return {k: pin(v) for k, v in x.items()}
         return x
-    host_dict = {k: pin(v) for k, v in zip(keys, host)}
+    host_dict = {k: pin(v) for k, v in host_full.items()}
     data_dev = net.pre_process(host_dict)
     torch.cuda.synchronize()
-    gather_bufs = None
+    # the path's single collective: ONE all-gather of the buffer the decoder kernels wrote (cls | reg | vel), issued
+    # asynchronously so that it runs under the next step's encoders; two gather buffers alternate
+    from mind_b200.distributed import all_gather_packed
+    gather_bufs, pending = [None, None], [None, None]
+    step_no = [0]
 
     def step_device():
         out = net.forward_packed(data_dev)
         if world > 1:
-            nonlocal gather_bufs
-            if gather_bufs is None:
-                gather_bufs = [torch.empty((world,) + tuple(t.shape), device=dev) for t in out[:3]]
-            for g, t in zip(gather_bufs, out[:3]):   # cls, reg, vel : what prune_merge consumes
-                dist.all_gather_into_tensor(g, t)        # equal shards: mind_b200.distributed fast path, preallocated
+            k = step_no[0] & 1
+            step_no[0] += 1
+            if pending[k] is not None:
+                pending[k][0].wait()                      # the gather that last used this buffer
+            gather_bufs[k], work = all_gather_packed(out[6], B, out[1].shape[0], out=gather_bufs[k], async_op=True)
+            pending[k] = (work, out)                      # keeps the send buffer alive until the collective is done
         return out
+
+    def drain():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k][0].wait()
+                pending[k] = None
 
     for _ in range(args.warmup):
         step_device()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -381,6 +513,7 @@ def run_native(args):
     e0.record()
     for _ in range(args.steps):
         step_device()
+    drain()                                                # every step's all-gather is inside the timed region
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -447,8 +580,7 @@ def run_native(args):
             t2 = time.perf_counter()
             pk = net._last_packed
             if world > 1:
-                for g, x in zip(gather_bufs, pk[:3]):
-                    dist.all_gather_into_tensor(g, x)
+                gather_bufs[slot], _ = all_gather_packed(pk[6], B, pk[1].shape[0], out=gather_bufs[slot])
             ev_out[slot].record(comp_s)
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(ev_out[slot])
@@ -464,24 +596,39 @@ def run_native(args):
             host_ms["forward"] += (t2 - t1) * 1e3
             host_ms["download"] += (t3 - t2) * 1e3
         comp_s.wait_stream(copy_s)
-    run_e2e(max(3, args.warmup))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    for k in host_ms:
-        host_ms[k] = 0.0
-    e0.record()
-    run_e2e(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1)
-    t = torch.tensor([ms2], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms2 = float(t.item())
+    def measure_e2e(n_steps):
+        run_e2e(max(3, args.warmup))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        for k in host_ms:
+            host_ms[k] = 0.0
+        e0.record()
+        run_e2e(n_steps)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), {k: round(v / n_steps, 3) for k, v in host_ms.items()}
+
+    # (a) the plug-in as shipped: pre_process reads the anchors out of the collated dict (2.6 KB per scene) and the
+    #     device evaluates get_rpe; (b) the same call made to ship the dense RPE tensors like the reference's gpu() does
+    net.rpe_on_device = True
+    ms2, host_enq = measure_e2e(args.steps)
     e2e = world * B * args.steps / (ms2 * 1e-3)
+    common = sum(x.numel() * 4 for x in (host[0], host[2], host[5], host[6]))
+    h2d = common + sum(4 * (t["TRAJS_CTRS"].numel() + t["TRAJS_VECS"].numel()) for t in host_full["TRAJS"]) \
+        + sum(4 * (g["lane_ctrs"].numel() + g["lane_vecs"].numel()) for g in host_full["LANE_GRAPH"])
+    net.rpe_on_device = False
+    n_dense = max(3, args.steps // 2)
+    ms3, host_enq_dense = measure_e2e(n_dense)
+    e2e_dense = {"value": world * B * n_dense / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / n_dense,
+                 "h2d_bytes_per_step": common + sum(r["scene"].numel() * 4 for r in host[4]),
+                 "host_enqueue_ms_per_step": host_enq_dense,
+                 "note": "pre_process made to upload the dense [5,M,M] RPE tensors (rpe_on_device = False)"}
+    net.rpe_on_device = True
     out_host = out_host[0]
-    h2d = sum(x.numel() * 4 for x in (host[0], host[2], host[5], host[6])) + sum(r["scene"].numel() * 4 for r in host[4])
     d2h = sum(x.numel() * 4 for x in out_host)
 
     if rank != 0:
@@ -501,15 +648,21 @@ def run_native(args):
         if os.path.exists(tp) and B == 256:                     # dram bytes per launch from the committed ncu --set full capture
             traffic = json.load(open(tp))["dram_bytes_per_launch"]
         roof = {"kernel": "k_rela_fusion_tc (layers 0-4)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
-                "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": traffic, "peak_source": pk["src"] + ", sustained bf16/fp16 dense",
+                "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "frac_of_burst_peak": ach / pk["tf_burst"], "peak_burst": pk["tf_burst"],
+                "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel build (profiles/fusion_tc_traffic.json)" if traffic else None,
+                "peak_source": pk["src"] + ", sustained bf16/fp16 dense (the kernel is timed inside a long step)",
                 "ms_per_launch": f_ms / f_n, "launches_timed": f_n,
                 "hbm_algorithmic_gbs": hb, "hbm_frac_of_measured": hb / pk["hbm"],
                 "flops_per_launch": flops, "bytes_per_launch": B * fusion_bytes_per_scene(True)}
     cpu_v, cores, sample = cpu_port_rate(sd)
     tree = bench_tree(net, dev)
     cost = bench_cost_fields(dev) if rank == 0 else None
+    closed = bench_closed_loop(net, dev) if rank == 0 else None
+    eager = gpu_eager_rate(sd, dev) if rank == 0 else None
+    if eager and "scenes_per_s_B64" in eager:
+        eager["native_over_eager_device_resident"] = value / world / eager["scenes_per_s_B64"]
     sharded = None
-    if args.tree_sharded and world > 1:
+    if world > 1 and not args.no_tree_sharded:
         # opt-in (never part of the driver's default run): forced-full depth-4 x branch-6 tree with every level's frontier
         # sharded over the ranks and one all-gather of (cls, reg, vel) per level (SURVEY.md 8e tree mode); max over ranks
         import copy
@@ -537,15 +690,17 @@ def run_native(args):
             "config": {"workload": "configs[1]: batch=%d synthetic scenes per GPU, 32 actors x 128 lane polylines, K=6" % B,
                        "global_batch": world * B, "precision": args.precision,
                        "l2": "inputs larger than L2 (fp16 edge stream %.2f GB per step)" % (B * N_TOK * N_TOK * 256 / 1e9),
-                       "collective": "all_gather(cls,reg,vel) per step" if world > 1 else "none",
+                       "collective": "ONE all_gather per step of the packed cls|reg|vel buffer the decoder wrote, overlapped with the next step" if world > 1 else "none",
                        "weights": "reference checkpoint 20240121-172745"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms2 / args.steps,
-                    "host_enqueue_ms_per_step": {k: round(v / args.steps, 3) for k, v in host_ms.items()}},
+                    "ms_per_step": ms2 / args.steps, "host_enqueue_ms_per_step": host_enq,
+                    "inputs": "pinned host collated dict -> pre_process (actors, lanes, target, anchors; get_rpe on the device) -> "
+                              "net() -> cls/reg/vel in pinned host memory"},
+            "e2e_dense_rpe": e2e_dense,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "stage_ms_per_step": stage_ms,
-            "cost_fields": cost, "tree_rollout_sharded": sharded,
+            "gpu_eager_baseline": eager, "cost_fields": cost, "closed_loop": closed, "tree_rollout_sharded": sharded,
             "tree_rollout": {"unit": "ms/scene", "scene": "natural / forced_full: S3 kinematic, 8 actors x 60 lane polylines; demo_2_*: the Argoverse-2 demo_2 scene of BASELINE.json configs[2]", **tree}}
     print(json.dumps(line))
     if world > 1:
@@ -561,8 +716,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default="f16tc", choices=["f16tc", "fp32"])
     ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (for ncu runs)")
-    ap.add_argument("--tree-sharded", action="store_true",
-                    help="N > 1 only, opt-in: forced-full scenario tree with the frontier of every level sharded over the ranks")
+    ap.add_argument("--no-tree-sharded", action="store_true",
+                    help="N > 1: skip the forced-full scenario tree with every level's frontier sharded over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

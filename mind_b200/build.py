@@ -1,5 +1,6 @@
 """Build libmind_b200.so in-tree with nvcc for sm_100a (no torch extension machinery: the
 boundary is a plain C ABI loaded through ctypes)."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -16,6 +17,17 @@ def _newer(a, b):
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
+def source_hash(deps, flags) -> str:
+    """sha256 over the compile flags and the CONTENT of every source / header: what decides whether a shipped library
+    is the one these sources produce (modification times do not survive a checkout or a snapshot copy)."""
+    h = hashlib.sha256(" ".join(flags).encode())
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
     """trace=True builds libmind_b200_trace.so (-DMIND_TRACE: timeline instrumentation of the fused layer kernel,
     a development tool selected with MIND_B200_LIB; never the product library)."""
@@ -27,8 +39,12 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "mind_b200.h"))
-    if not force and os.path.exists(LIB) and not any(_newer(d, LIB) for d in deps):
+    want = source_hash(deps, flags)
+    stamp = LIB + ".srchash"
+    have = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    if not force and os.path.exists(LIB) and have == want:
         return LIB
+    force = force or have != want       # a stale or unstamped library is rebuilt from every source
     objs = []
     os.makedirs(bdir, exist_ok=True)
     procs = []
@@ -47,6 +63,8 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
             sys.stderr.write(out)
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(want + "\n")
     return LIB
 
 

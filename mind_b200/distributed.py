@@ -49,6 +49,28 @@ def all_gather_predictions(cls: torch.Tensor, reg: torch.Tensor, vel: torch.Tens
     return all_gather_rows(cls, group), all_gather_rows(reg, group), all_gather_rows(vel, group)
 
 
+def all_gather_packed(pack: torch.Tensor, B: int, A: int, group=None, out: torch.Tensor = None, async_op: bool = False):
+    """ONE collective for a batch with equal shards (every rank B scenes / A actors: the benchmark batch, a tree level):
+    `pack` is forward_packed's output buffer cls | reg | vel (predictor.pack_layout), written by the decoder kernels
+    themselves, so nothing is packed or copied before the send.  Returns (gathered [world, len(pack)], work handle);
+    `unpack_gathered` gives per-tensor views of it."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world, pack.numel()), device=pack.device, dtype=pack.dtype)
+    work = dist.all_gather_into_tensor(out.view(-1), pack, group=group, async_op=async_op)
+    return out, work
+
+
+def unpack_gathered(gathered: torch.Tensor, B: int, A: int):
+    """(cls [world, B, 6], reg [world, A, 6, 60, 5], vel [world, A, 6, 60, 2]) as strided views of the gathered buffer:
+    rank r's scenes are [r]; flattening the first two dims (scene order) costs one copy per tensor, only if needed."""
+    from .predictor import pack_layout
+    (c0, cn), (r0, rn), (v0, vn) = pack_layout(B, A)
+    w = gathered.shape[0]
+    return (gathered[:, c0:c0 + cn].view(w, B, 6), gathered[:, r0:r0 + rn].view(w, A, 6, 60, 5),
+            gathered[:, v0:v0 + vn].view(w, A, 6, 60, 2))
+
+
 # ---- tree mode (SURVEY.md 8e): the frontier of one depth level sharded over ranks ------------------------------
 def shard_level_inputs(net_in, geom, n_frontier: int, rank: int, world: int):
     """Contiguous block of frontier scenes for `rank`.  `net_in` is the level's network input tuple
@@ -80,6 +102,13 @@ def sharded_level_forward(forward, net_in, geom, n_frontier: int, group=None):
     if world == 1 or n_frontier < world:
         out = forward(net_in, geom)
         return out[0], out[1], out[2]
-    sub, g, _ = shard_level_inputs(net_in, geom, n_frontier, dist.get_rank(group), world)
+    sub, g, (s0, e0) = shard_level_inputs(net_in, geom, n_frontier, dist.get_rank(group), world)
     out = forward(sub, g)
+    pack = out[6] if len(out) > 6 else None
+    if pack is not None and n_frontier % world == 0:
+        # equal shards: one all-gather of the packed cls | reg | vel buffer the decoder wrote
+        f, a = e0 - s0, out[1].shape[0]
+        gathered, _ = all_gather_packed(pack, f, a, group)
+        c, r, v = unpack_gathered(gathered, f, a)
+        return c.reshape(-1, 6), r.reshape((-1,) + tuple(r.shape[2:])), v.reshape((-1,) + tuple(v.shape[2:]))
     return all_gather_predictions(out[0], out[1], out[2], group)

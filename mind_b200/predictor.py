@@ -33,6 +33,16 @@ def _bezier_bases(n_order=7, n_step=60):
     return np.ascontiguousarray(T, dtype=np.float32), np.ascontiguousarray(Tp, dtype=np.float32)
 
 
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def pack_layout(B: int, A: int):
+    """(offset, numel) of cls [B,6], reg [A,6,60,5], vel [A,6,60,2] inside forward_packed's output buffer `last_pack`."""
+    n_cls, n_reg = _pad64(B * 6), _pad64(A * 1800)
+    return (0, B * 6), (n_cls, A * 1800), (n_cls + n_reg, A * 720)
+
+
 def _to_device(data, device):
     """Recursive transfer, same contract as the reference's gpu() (planners/mind/utils.py:9-20)."""
     if isinstance(data, (list, tuple)):
@@ -51,6 +61,32 @@ class _PackedRPE(list):
     base = None      # the packed device buffer (uint8)
     ptrs = None      # ctypes array of per-scene device pointers
     shapes = None    # per-scene (5, M, M)
+
+
+class _LazyRPE(dict):
+    """One entry of data['RPE'] when only the anchors travelled: 'scene' is evaluated on demand (device torch ops, the
+    same formulas as get_rpe, planners/mind/utils.py:193-212).  The network itself never asks: it evaluates the
+    encoding inside its edge-init kernels from the anchors."""
+    def __init__(self, ctrs, vecs):
+        super().__init__(scene_mask=None)
+        self._c, self._v = ctrs, vecs
+
+    def __missing__(self, key):
+        if key != "scene":
+            raise KeyError(key)
+        from .synth import pairwise_rpe
+        self["scene"] = pairwise_rpe(self._c, self._v)
+        return self["scene"]
+
+
+class _GeomRPE(list):
+    """data['RPE'] after pre_process when the collated dict carries the anchors the dense encoding was built from
+    (TRAJS[b]['TRAJS_CTRS' / 'TRAJS_VECS'], LANE_GRAPH[b]['lane_ctrs' / 'lane_vecs'], scenario_tree.py:176-186):
+    only those [sum M_b, 2] arrays are uploaded (~2.6 KB per 160-token scene instead of 512 KB of dense RPE) and
+    get_rpe is evaluated on the device."""
+    ctrs = None      # [sum M_b, 2] device, per scene [actors ; lanes]
+    vecs = None
+    counts = None    # per-scene M_b
 
 
 class ScenePredNetB200:
@@ -74,6 +110,8 @@ class ScenePredNetB200:
         self._out_cache = {}
         self.training = False
         self.precision = _lib.PREC_FP32
+        self.rpe_on_device = True       # pre_process uploads anchors instead of dense RPE when the dict has them
+        self._geom_pin = {}
 
     # ---- nn.Module-like surface used by planners/mind/planner.py:46-49 ----
     def load_state_dict(self, state_dict, strict: bool = True):
@@ -149,10 +187,52 @@ class ScenePredNetB200:
         (mind_upload_packed), and the index lists (only their lengths are used by this network) stay on the host."""
         dev = self.device
         rpe = data["RPE"]
-        packed = self._upload_rpe(rpe) if isinstance(rpe, (list, tuple)) and len(rpe) > 0 else None
+        packed = self._upload_geom(data) if self.rpe_on_device else None
+        if packed is None:
+            packed = self._upload_rpe(rpe) if isinstance(rpe, (list, tuple)) and len(rpe) > 0 else None
         return (_to_device(data["ACTORS"], dev), data["ACTOR_IDCS"], _to_device(data["LANES"], dev), data["LANE_IDCS"],
                 packed if packed is not None else _to_device(rpe, dev),
                 _to_device(data["TGT_NODES"], dev), _to_device(data["TGT_RPE"], dev))
+
+    def _upload_geom(self, data):
+        """anchors of every scene -> one pinned staging buffer -> one H2D copy; None if the dict does not carry them"""
+        trajs, graphs = data.get("TRAJS"), data.get("LANE_GRAPH")
+        if not isinstance(trajs, (list, tuple)) or not isinstance(graphs, (list, tuple)) or len(trajs) != len(graphs) or not trajs:
+            return None
+        try:
+            cs, vs, counts = [], [], []
+            for t, g in zip(trajs, graphs):
+                cs += [t["TRAJS_CTRS"], g["lane_ctrs"]]
+                vs += [t["TRAJS_VECS"], g["lane_vecs"]]
+                counts.append(int(t["TRAJS_CTRS"].shape[0]) + int(g["lane_ctrs"].shape[0]))
+        except (KeyError, TypeError, AttributeError):
+            return None
+        if any((not isinstance(x, torch.Tensor)) or x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 2 for x in cs + vs):
+            return None
+        m = sum(counts)
+        if cs[0].device.type == "cpu":
+            slot = self._geom_pin.get(m)
+            if slot is None:      # two staging buffers per size: a two-deep pipeline may still be copying out of the other
+                slot = self._geom_pin[m] = [[torch.empty(2, m, 2).pin_memory() for _ in range(2)], 0, [None, None]]
+            k = slot[1] = slot[1] ^ 1
+            if slot[2][k] is not None:
+                slot[2][k].synchronize()
+            pin = slot[0][k]
+            torch.cat(cs, 0, out=pin[0])
+            torch.cat(vs, 0, out=pin[1])
+            devbuf = pin.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            slot[2][k] = ev
+        else:
+            devbuf = torch.stack([torch.cat(cs, 0), torch.cat(vs, 0)]).to(self.device)
+        out = _GeomRPE()
+        out.ctrs, out.vecs, out.counts = devbuf[0], devbuf[1], counts
+        off = 0
+        for n in counts:
+            out.append(_LazyRPE(out.ctrs[off:off + n], out.vecs[off:off + n]))
+            off += n
+        return out
 
     def _upload_rpe(self, rpe):
         scenes = []
@@ -196,7 +276,7 @@ class ScenePredNetB200:
     def forward(self, data):
         packed = self.forward_packed(data)
         self._last_packed = packed
-        cls, reg, vel, cov_vel, param, a_off = packed
+        cls, reg, vel, cov_vel, param, a_off = packed[:6]
         B = cls.shape[0]
         sizes = [a_off[b + 1] - a_off[b] for b in range(B)]  # per-scene views: one split call per output tensor
         res_cls = list(cls.split(1))
@@ -214,7 +294,8 @@ class ScenePredNetB200:
 
     def forward_packed(self, data, geom=None, persistent_out=False):
         """Runs the library; returns packed (cls [B,6], reg [A,6,60,5], vel [A,6,60,2],
-        cov_vel [A,6,60,3], param [A,6,8,5], actor_offsets list).  `geom` = (ctrs, vecs) device
+        cov_vel [A,6,60,3], param [A,6,8,5], actor_offsets list, pack) where `pack` is the one flat buffer cls, reg and
+        vel are views of (pack_layout): the send buffer of the path's single all-gather.  `geom` = (ctrs, vecs) device
         tensors [sum M_b, 2] switches RPE evaluation to the device (the 'rpe' entry is ignored).
         `persistent_out` hands out the same output tensors for every call of a given (B, A) shape (the caller must be
         done with the previous result): with option "graph" on, stable pointers let the library replay a captured
@@ -242,6 +323,12 @@ class ScenePredNetB200:
         bt.actor_off, bt.lane_off = ao, lo
         bt.actors, bt.lanes = actors.data_ptr(), lanes.data_ptr() if L > 0 else 0
         keep = []
+        if geom is None and isinstance(rpe, _GeomRPE) and len(rpe) == B:
+            for b in range(B):
+                if rpe.counts[b] != (a_off[b + 1] - a_off[b]) + (l_off[b + 1] - l_off[b]):
+                    raise ValueError("anchors of scene %d cover %d tokens, expected %d" %
+                                     (b, rpe.counts[b], (a_off[b + 1] - a_off[b]) + (l_off[b + 1] - l_off[b])))
+            geom = (rpe.ctrs, rpe.vecs)
         if geom is not None:
             ctrs, vecs = f32(geom[0]), f32(geom[1])
             keep += [ctrs, vecs]
@@ -268,11 +355,16 @@ class ScenePredNetB200:
         bt.tgt_nodes, bt.tgt_rpe = tgt_nodes.data_ptr(), tgt_rpe.data_ptr()
         outs = self._out_cache.get((B, A)) if persistent_out else None
         if outs is None:
-            outs = (torch.empty(B, 6, device=dev), torch.empty(A, 6, 60, 5, device=dev), torch.empty(A, 6, 60, 2, device=dev),
-                    torch.empty(A, 6, 60, 3, device=dev), torch.empty(A, 6, 8, 5, device=dev))
+            # cls | reg | vel live in ONE buffer: the decoder kernels write the send buffer of the path's single
+            # all-gather directly (mind_b200.distributed.all_gather_packed), no packing copy
+            n_cls, n_reg, n_vel = _pad64(B * 6), _pad64(A * 1800), A * 720
+            pack = torch.empty(n_cls + n_reg + n_vel, device=dev)
+            outs = (pack[:B * 6].view(B, 6), pack[n_cls:n_cls + A * 1800].view(A, 6, 60, 5),
+                    pack[n_cls + n_reg:].view(A, 6, 60, 2),
+                    torch.empty(A, 6, 60, 3, device=dev), torch.empty(A, 6, 8, 5, device=dev), pack)
             if persistent_out:
                 self._out_cache[(B, A)] = outs
-        cls, reg, vel, cov_vel, param = outs
+        cls, reg, vel, cov_vel, param, self.last_pack = outs
         out = _lib.MindOutputs(cls.data_ptr(), reg.data_ptr(), vel.data_ptr(), cov_vel.data_ptr(), param.data_ptr())
         need = self._lib.mind_workspace_bytes_batch(self._h, C.byref(bt))
         if need < 0:
@@ -283,7 +375,7 @@ class ScenePredNetB200:
             _lib.check(self._lib.mind_forward(self._h, C.byref(bt), C.byref(out), C.c_void_p(ws.data_ptr()),
                                               ws.numel(), C.c_void_p(stream)), "mind_forward")
         self._keep = keep   # inputs must outlive the asynchronous launches
-        return cls, reg, vel, cov_vel, param, a_off
+        return cls, reg, vel, cov_vel, param, a_off, self.last_pack
 
     def debug_tap(self, name: str, numel: int):
         buf = torch.empty(numel, device=self.device)

@@ -55,10 +55,10 @@ def conv1d(x, w, stride=1):
     k = w.shape[2]
     pad = (k - 1) // 2
     A, Cin, L = x.shape
-    xp = torch.zeros(A, Cin, L + 2 * pad, dtype=x.dtype)
+    xp = torch.zeros(A, Cin, L + 2 * pad, dtype=x.dtype, device=x.device)
     xp[:, :, pad:pad + L] = x
     Lout = (L + 2 * pad - k) // stride + 1
-    out = torch.zeros(A, w.shape[0], Lout, dtype=x.dtype)
+    out = torch.zeros(A, w.shape[0], Lout, dtype=x.dtype, device=x.device)
     for kk in range(k):
         xs = xp[:, :, kk:kk + stride * (Lout - 1) + 1:stride]  # [A, Cin, Lout]
         out += torch.einsum("oc,acl->aol", w[:, :, kk], xs)
@@ -70,7 +70,7 @@ def upsample_linear_x2(x):
     (network.py:57).  x [A, C, L] -> [A, C, 2L].
     src = (dst + 0.5)/2 - 0.5 clamped at 0; neighbours clamped to L-1."""
     A, C, L = x.shape
-    dst = torch.arange(2 * L, dtype=torch.float32)
+    dst = torch.arange(2 * L, dtype=torch.float32, device=x.device)
     src = torch.clamp((dst + 0.5) * 0.5 - 0.5, min=0.0)
     i0 = src.floor().long()
     i1 = torch.clamp(i0 + 1, max=L - 1)
@@ -201,7 +201,7 @@ def edge_init(rpe, p: Params):
     """rpe [5, M, M] -> edge0 [M+1, M+1, 128] with a zero cls row/col (:326-330)."""
     M = rpe.shape[1]
     e = _lin_ln_relu(rpe.permute(1, 2, 0), p.sub("proj_rpe_scene."), 0)
-    out = torch.zeros(M + 1, M + 1, D)
+    out = torch.zeros(M + 1, M + 1, D, device=e.device)
     out[:M, :M] = e
     return out
 
@@ -212,7 +212,7 @@ def fusion_net(actors, actor_idcs, lanes, lane_idcs, rpes, p: Params, emu=None,
     l = _lin_ln_relu(lanes, p.sub("proj_lane."), 0)
     a_new, l_new, c_new, edges = [], [], [], []
     for ai, li, rp in zip(actor_idcs, lane_idcs, rpes):
-        x = torch.cat([a[ai], l[li], torch.zeros(1, D)], dim=0)
+        x = torch.cat([a[ai], l[li], torch.zeros(1, D, device=a.device)], dim=0)
         edge = edge_init(rp["scene"], p)
         for i in range(n_layer):
             x, edge = rela_fusion_layer(x, edge, p.sub("fuse_scene.fusion.%d." % i),
@@ -265,7 +265,7 @@ def _mlp2(x, p: Params):
 
 
 def scene_decoder(ctx, actors, actor_idcs, tgt_feat, tgt_rpes, p: Params):
-    T, Tp = bezier_T(), bezier_Tp()
+    T, Tp = bezier_T().to(ctx.device), bezier_Tp().to(ctx.device)
     tr = _lin_ln_relu(tgt_rpes, p.sub("proj_rpe."), 0)
     if tgt_feat.dim() == 1:
         tgt_feat = tgt_feat[None]
@@ -302,8 +302,11 @@ def scene_decoder(ctx, actors, actor_idcs, tgt_feat, tgt_rpes, p: Params):
 # full forward  (network.py:582-595)
 # --------------------------------------------------------------------------- #
 class ScenePredOracle:
-    def __init__(self, state_dict, emu=None):
-        self.p = Params({k: v.detach().cpu().float() for k, v in state_dict.items()})
+    def __init__(self, state_dict, emu=None, device="cpu"):
+        """device != "cpu": the same torch-eager restatement with its tensors on that device (bench.py's
+        gpu_eager_baseline: what the reference's nn.Module forward amounts to under torch eager on a GPU)."""
+        self.device = torch.device(device)
+        self.p = Params({k: v.detach().to(self.device).float() for k, v in state_dict.items()})
         self.emu = emu
 
     @torch.no_grad()
