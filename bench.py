@@ -372,7 +372,7 @@ def bench_closed_loop(net, dev):
     import numpy as np
     out = {}
     try:
-        from mind_b200.integration.replay import replay_file
+        from mind_b200.integration.replay import fragile_depth, replay_file
         for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "plan_calls_demo_*.pt.xz"))):
             rec, res = replay_file(path, dev, net)
             tot = [r["seconds"]["total"] for r in res]
@@ -384,9 +384,11 @@ def bench_closed_loop(net, dev):
                 "trees_per_call": sum(r["n_trees"] for r in res) / len(res),
                 "reference_cpu_ms_per_plan_call": 1e3 * statistics.median(r["ref_seconds"]["scenario_tree"] + r["ref_seconds"]["optimizer"] for r in res),
                 "reference_cpu_host": rec["host"],
-                "same_scenario_trees": all(r["same_trees"] for r in res),
-                "same_chosen_tree": all(r["best_idx"] in r["ref_best"] for r in res),
-                "max_abs_ctrl_diff": [float(v) for v in np.max([np.abs(r["ctrl"] - r["ref_ctrl"]) for r in res], axis=0)]}
+                "calls_with_reference_trees_node_for_node": sum(r["same_trees"] for r in res),
+                "calls_with_every_decision_clear_of_its_threshold": sum(fragile_depth(r) is None for r in res),
+                "same_chosen_tree_when_trees_agree": all(r["best_idx"] in r["ref_best"] for r in res if r["same_trees"]),
+                "max_abs_ctrl_diff_when_trees_agree": [float(v) for v in np.max([np.abs(r["ctrl"] - r["ref_ctrl"]) for r in res if r["same_trees"]] or [[0.0, 0.0]], axis=0)],
+                "max_abs_ctrl_diff_all_calls": [float(v) for v in np.max([np.abs(r["ctrl"] - r["ref_ctrl"]) for r in res], axis=0)]}
         out["note"] = ("replay of recorded closed-loop plan calls (inputs = what the reference's process_data produced at that call); "
                        "the front end (process_data, host code) is not inside these times")
     except Exception as e:

@@ -78,12 +78,13 @@ class PlanReplayer:
 
     def plan(self, rec):
         """-> dict(ctrl, best_idx, scen_trees, traj_trees, seconds = {scenario_tree, optimizer, total})"""
+        data, graph = self.scene_dict(rec), copy.deepcopy(rec["graph"])        # fixture reconstruction: outside the timed call
         t0 = time.perf_counter()
         gen = self.gen
         gen.reset()                                                            # planner.py:107
         gen.set_target_lane(rec["lane"], rec["info"])                          # :109-111
-        gen.lane_graph = copy.deepcopy(rec["graph"])
-        scen_trees = gen.rollout(self.scene_dict(rec))                         # :113 (behind process_data)
+        gen.lane_graph = graph
+        scen_trees = gen.rollout(data)                                         # :113 (behind process_data)
         t1 = time.perf_counter()
         traj_trees = []
         for st in scen_trees:                                                  # :120-123, get_traj_tree :171-175
@@ -116,6 +117,24 @@ def replay_file(path, device, network, warmup=1):
         ref_keys = [sorted(t) for t in r["scen_trees"]]
         got_keys = [sorted(t.nodes) for t in res["scen_trees"]]
         out.append(dict(plan_index=r["plan_index"], sim_time=r["sim_time"], ctrl=res["ctrl"], ref_ctrl=r["ret_ctrl"],
-                        same_trees=ref_keys == got_keys, best_idx=res["best_idx"], ref_best=r["best_candidates"],
-                        seconds=res["seconds"], ref_seconds=r["cpu_reference_s"], n_trees=len(got_keys)))
+                        same_trees=ref_keys == got_keys, got_keys=got_keys, ref_keys=ref_keys, best_idx=res["best_idx"],
+                        ref_best=r["best_candidates"], seconds=res["seconds"], ref_seconds=r["cpu_reference_s"],
+                        n_trees=len(got_keys), merge_margins=r.get("merge_margins")))
     return rec, out
+
+
+FRAGILE_RAD = 0.05      # a keep / merge decision closer than this to pi/6 can fall either way (see oracle/record_plan_calls.py)
+
+
+def fragile_depth(result):
+    """first tree depth at which the recorded call has a decision inside the noise band, or None"""
+    mm = result.get("merge_margins")
+    if not mm:
+        return None
+    d = [int(dep) for dep, m in mm if abs(m) < FRAGILE_RAD]
+    return min(d) if d else None
+
+
+def keys_above(keys, depth):
+    """node keys '{depth}_{scene}_{mode}' created before `depth`, over all trees of a call"""
+    return sorted(k for t in keys for k in t if int(k.split("_")[0]) < depth)
