@@ -217,12 +217,15 @@ def bench_tree(net, dev, reps=5):
     from mind_b200 import synth
     from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
     args = dict(x0=(100, 108, 92, 120, 112, 96, 130, 85), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0), v=(5, 9, 3, 8, 2, 10, 6, 12))
-    out = {}
-    for name, ff in (("natural", None), ("forced_full", (10, 20, 30))):
+    out = {"tiers": "natural trees: tensor-core mode as shipped (these scenes have < 128 tokens -> exact tier, bit-exact branch selection); "
+                    "forced_full: every keep / branch decision is forced, so nothing depends on the predictions' last bits -> fused "
+                    "fp16-operand tier (tc_min_tokens = 0); forced_full_exact_tier: the same tree in the exact tier"}
+    for name, ff in (("natural", None), ("forced_full", (10, 20, 30)), ("forced_full_exact_tier", (10, 20, 30))):
         gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
         gen.force_full = ff
+        net.set_option("tc_min_tokens", 0 if name == "forced_full" else 128)
         times = []
-        for r in range(reps + 2):
+        for r in range((reps if name != "forced_full_exact_tier" else 1) + 2):
             data, lane, info, graph = synth.scene_s3(**args)
             gen.reset(); gen.set_target_lane(lane, info); gen.lane_graph = copy.deepcopy(graph)
             torch.cuda.synchronize()
@@ -241,6 +244,7 @@ def bench_tree(net, dev, reps=5):
         for name, ff in (("demo_2_natural", None), ("demo_2_forced_full", (10, 20, 30))):
             gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
             gen.force_full = ff
+            net.set_option("tc_min_tokens", 0 if ff else 128)
             times = []
             try:
                 for r in range(reps + 2):
@@ -258,6 +262,7 @@ def bench_tree(net, dev, reps=5):
                          "nodes": gen.tree.size(), "trees": len(trees), "actors": int(gold["data"]["ACTORS"].shape[0]),
                          "lane_polylines": int(gold["data"]["LANES"].shape[0]), "input": "host tensors (collated scene dict on the CPU)",
                          "host_phase_ms_last": {k: round(v * 1e3, 3) for k, v in gen.timing.items()}}
+    net.set_option("tc_min_tokens", 128)
     return out
 
 
@@ -673,6 +678,7 @@ def run_native(args):
         sargs = dict(x0=(100, 108, 92, 120, 112, 96, 130, 85), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0), v=(5, 9, 3, 8, 2, 10, 6, 12))
         gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
         gen.force_full, gen.distributed = (10, 20, 30), True
+        net.set_option("tc_min_tokens", 0)              # forced decisions: fused tier, as in tree_rollout.forced_full
         times = []
         for r in range(7):
             data, lane, info, graph = synth.scene_s3(**sargs)
@@ -684,7 +690,9 @@ def run_native(args):
             t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             times.append(float(t.item()))
-        sharded = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches), "ranks": world}
+        net.set_option("tc_min_tokens", 128)
+        sharded = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches), "ranks": world,
+                   "single_gpu_ms_per_tree": tree.get("forced_full", {}).get("ms_per_tree")}
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -172,7 +172,19 @@ class ScenarioTreeGeneratorB200:
         return time.perf_counter()
 
     def rollout(self, data):
-        """AIME iteration from a collated one-scene dict (what process_data returns)."""
+        """AIME iteration from a collated one-scene dict (what process_data returns).  The cyclic garbage collector is held
+        off for the duration of the call: a rollout allocates thousands of small container objects (none of them cyclic),
+        and a generation-2 collection triggered in the middle of one costs ~100 ms on a process that has torch loaded."""
+        import gc
+        was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return self._rollout(data)
+        finally:
+            if was_on:
+                gc.enable()
+
+    def _rollout(self, data):
         import time
         self.timing = {}
         t = time.perf_counter()
@@ -312,12 +324,14 @@ class ScenarioTreeGeneratorB200:
     def prune_merge(self, level: _Level, nodes):
         dev, F, Na = self.device, level.F, level.Na
         f32 = dict(device=dev, dtype=torch.float32)
-        level.cpos = torch.empty(F, 6, Na, 100, 2, **f32)
-        level.cvel = torch.empty(F, 6, Na, 100, 2, **f32)
-        level.cang = torch.empty(F, 6, Na, 100, **f32)
-        level.ccov = torch.empty(F, 6, Na, 100, **f32)
-        level.gpos = torch.empty(F, 6, Na, 60, 2, **f32)
-        ibuf = torch.empty(4, F, 6, device=dev, dtype=torch.int32)      # order, keep, tb | cprob (fp32 bits): one D2H
+        lv_index = next(i for i, L in enumerate(self._levels) if L is level)
+        ckey = ("children", lv_index, F, Na)                            # child histories: device buffers kept across rollouts
+        level.cpos = self._buf(ckey, "cpos", (F, 6, Na, 100, 2))
+        level.cvel = self._buf(ckey, "cvel", (F, 6, Na, 100, 2))
+        level.cang = self._buf(ckey, "cang", (F, 6, Na, 100))
+        level.ccov = self._buf(ckey, "ccov", (F, 6, Na, 100))
+        level.gpos = self._buf(ckey, "gpos", (F, 6, Na, 60, 2))
+        ibuf = self._buf(ckey, "ibuf", (4, F, 6), torch.int32)          # order, keep, tb | cprob (fp32 bits): one D2H
         cprob = ibuf[3].view(torch.float32)
         a = _lib.MindTreeLevel()
         a.n_frontier, a.n_actor, a.obs_len, a.pred_len = F, Na, self.obs_len, self.pred_len
@@ -334,22 +348,19 @@ class ScenarioTreeGeneratorB200:
         stream = torch.cuda.current_stream(dev).cuda_stream
         if self._lib.mind_tree_level(C.byref(a), C.c_void_p(stream)) != 0:
             raise RuntimeError(self._lib.mind_tree_last_error().decode())
-        lv_index = next(i for i, L in enumerate(self._levels) if L is level)
         ih = ibuf.cpu().numpy()                                           # the level's only D2H: decisions
         ph = ih[3].view(np.float32)
         if self.force_full is not None:
             ih[1] = 1
             ih[2] = self.force_full[lv_index] if lv_index < len(self.force_full) else self.pred_len
-        out = []
-        for f in range(F):
-            for k in range(6):
-                if not ih[1, f, k]:
-                    continue
-                mode = int(ih[0, f, k])
-                out.append(dict(SCEN_ID="{}_{}_{}".format(self.branch_depth, f, mode), PARENT_ID=nodes[f].key,
-                                level=lv_index, row=f * 6 + k, f=f, prob=np.float32(ph[f, k]), cur_t=level.cur_t_host[f],
-                                end_t=self.pred_len, tb0=int(ih[2, f, k]), examined=False))
-        return out
+        # kept children in (scene, slot) order; the bookkeeping below is plain Python on ~F*6 small records
+        fs, ks = np.nonzero(ih[1])
+        modes, tbs, probs = ih[0][fs, ks].tolist(), ih[2][fs, ks].tolist(), ph[fs, ks]
+        depth, end_t, cur = self.branch_depth, self.pred_len, level.cur_t_host
+        keys = [n.key for n in nodes]
+        return [dict(SCEN_ID="%d_%d_%d" % (depth, f, m), PARENT_ID=keys[f], level=lv_index, row=f * 6 + k, f=f, prob=p,
+                     cur_t=cur[f], end_t=end_t, tb0=tb, examined=False)
+                for f, k, m, tb, p in zip(fs.tolist(), ks.tolist(), modes, tbs, probs)]
 
     def create_nodes(self, preds):                                                # :73-80
         for p in preds:
@@ -451,40 +462,52 @@ class ScenarioTreeGeneratorB200:
 
     # ---- output packing (:208-272) -------------------------------------------------------------
     def get_scenario_tree(self):
-        data_tree = Tree()
-        root = self.tree.get_root()
-        data_tree.add_node(Node(root.key, None, [1.0]))
+        """One pass over the finished tree: label the branches that reached an end node, renormalise sibling
+        probabilities, and build the reference's output directly -- one Tree per labelled child of the root with
+        node.data = [prob, trajs (Na,dur,2), covs (Na,dur,1), tgt_pts (11,2)] -- while the payloads of all contributing
+        levels travel in one asynchronous D2H per level into pinned buffers.  The numpy payloads are views of those
+        buffers; two sets alternate, so a result stays valid until the rollout after the next one."""
+        tree = self.tree
+        get = tree.nodes.__getitem__
+        root = tree.get_root()
         for n in self.get_end_set():                                   # label the branches that finished
-            n = self.tree.get_node(n.parent_key) if n.parent_key is not None else n
+            n = get(n.parent_key) if n.parent_key is not None else n
             while n.parent_key is not None and not n.data.end_flag:   # ancestors already labelled: stop early
                 n.data.end_flag = True
-                n = self.tree.get_node(n.parent_key)
+                n = get(n.parent_key)
+        trees, todo, levels = [], [], set()
         for key in root.children_keys:
-            n = self.tree.get_node(key)
+            n = get(key)
             if not n.data.end_flag:
                 continue
-            data_tree.add_node(Node(n.key, root.key, [1.0]))
-            queue = [n]
+            st = Tree()
+            dn = Node(n.key, None, [1.0])
+            st.add_node(dn)
+            todo.append((dn, n.data.rec))
+            levels.add(n.data.rec["level"])
+            queue = [(n, 1.0)]
             while queue:
-                c = queue.pop(0)
-                pp = data_tree.get_node(c.key).data[0]
-                kids = [self.tree.get_node(k) for k in c.children_keys if self.tree.get_node(k).data.end_flag]
+                c, pp = queue.pop(0)
+                kids = [k for k in map(get, c.children_keys) if k.data.end_flag]
                 total = 0.0
                 for k in kids:
                     total += np.asarray(k.data.rec["prob"])
                 for k in kids:
-                    data_tree.add_node(Node(k.key, c.key, [np.asarray(k.data.rec["prob"]) / total * pp]))
-                    queue.append(k)
-        # one asynchronous D2H per contributing level (predicted half of the child histories only) into pinned
-        # buffers kept across rollouts, a single synchronisation, then numpy views per node
-        todo = [(key, dn, self.tree.get_node(key).data.rec) for key, dn in data_tree.nodes.items()
-                if key != root.key and len(dn.data) == 1]
+                    pk = np.asarray(k.data.rec["prob"]) / total * pp
+                    dn = Node(k.key, c.key, [pk])
+                    st.add_node(dn)
+                    todo.append((dn, k.data.rec))
+                    levels.add(k.data.rec["level"])
+                    queue.append((k, pk))
+            trees.append(st)
+        # one asynchronous D2H per contributing level (predicted half of the child histories only), a single synchronisation
+        self._host_flip = getattr(self, "_host_flip", 0) ^ 1
         host = {}
-        for lv in sorted({rec["level"] for _, _, rec in todo}):
+        for lv in sorted(levels):
             L = self._levels[lv]
             ent = []
             for name, t in (("cpos", L.cpos[:, :, :, self.obs_len:]), ("ccov", L.ccov[:, :, :, self.obs_len:]), ("tgt", L.tgt_pts)):
-                hk = ("host", lv, name)
+                hk = ("host", self._host_flip, lv, name)
                 h = self._pool.get(hk)
                 if h is None or tuple(h.shape) != tuple(t.shape):
                     h = self._pool[hk] = torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory()
@@ -492,23 +515,10 @@ class ScenarioTreeGeneratorB200:
                 ent.append(h)
             host[lv] = ent
         torch.cuda.current_stream(self.device).synchronize()
-        host = {lv: tuple(h.numpy().copy() for h in ent) for lv, ent in host.items()}   # own the data: the pinned buffers are reused
-        for key, dn, rec in todo:                                      # every labelled node gets its payload once
+        host = {lv: tuple(h.numpy() for h in ent) for lv, ent in host.items()}
+        for dn, rec in todo:                                           # every labelled node gets its payload once
             dur = rec["end_t"] - rec["cur_t"]
             cpos, ccov, tgt = host[rec["level"]]
-            f, k = rec["row"] // 6, rec["row"] % 6
+            f, k = divmod(rec["row"], 6)
             dn.data += [cpos[f, k, :, :dur, :], ccov[f, k, :, :dur, None], tgt[f]]
-        trees = []
-        for key in data_tree.get_root().children_keys:
-            st = Tree()
-            n = data_tree.get_node(key)
-            st.add_node(Node(n.key, None, n.data))
-            queue = [n]
-            while queue:
-                c = queue.pop(0)
-                for ck in c.children_keys:
-                    cn = data_tree.get_node(ck)
-                    st.add_node(Node(cn.key, c.key, cn.data))
-                    queue.append(cn)
-            trees.append(st)
         return trees
