@@ -695,92 +695,133 @@ void launch_edge_init_f32(const SceneDesc* sd, const float* ctrs, const float* v
     k_edge_init<float><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sd, ctrs, vecs, W, b, g, be, edge, b0, nb, Nmax);
     ++g_launches;
 }
-// fp16 edge stream for the tensor-core path: a warp keeps its 4-channel weight slice in registers and
-// walks units of 8 consecutive queries j of one key row i; rpe values are loaded once per unit by the
-// first 40 "slots" of the warp and broadcast by shuffle.  Write-bound (256 B per pair row).
-__global__ void __launch_bounds__(256) k_edge_init_h8(const SceneDesc* __restrict__ sd, const float* __restrict__ ctrs,
-                                                      const float* __restrict__ vecs, const float* __restrict__ W,
-                                                      const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, __half* __restrict__ edge, int nb,
-                                                      int Nmax, int min_tokens) {
-    const int lane = threadIdx.x & 31;
-    const int units_per_row = (Nmax + 7) >> 3;
-    const int64_t n_units = (int64_t)nb * Nmax * units_per_row;
-    float w[4][5], bi[4], gm[4], bt[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int c = lane * 4 + e;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) w[e][k] = __ldg(W + c * 5 + k);
-        bi[e] = __ldg(bias + c); gm[e] = __ldg(gamma + c); bt[e] = __ldg(beta + c);
+// fp16 edge stream for the tensor-core path.  One THREAD per pair row: the 5 -> 128 projection, the LayerNorm statistics
+// and the normalisation run on packed fp32 pairs in the thread's own registers (no cross-lane reduction), the per-channel
+// parameters are broadcast shared-memory loads, and the 256-byte fp16 rows leave through a padded shared-memory tile so
+// that the global stores are full 256-byte segments.  (The warp-per-row version before it was issue-bound: 124 warp
+// instructions per pair row, 77 % issue-slot utilisation at 1.7 TB/s of a pure write stream, profiles/r02_v1_other_kernels_ncu_full.md;
+// this one needs ~30.)
+namespace {
+typedef unsigned long long ef2;
+__device__ __forceinline__ ef2 e_pk2(float a, float b) { ef2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void e_upk2(ef2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ ef2 e_fma2(ef2 a, ef2 b, ef2 c) { ef2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ ef2 e_add2(ef2 a, ef2 b) { ef2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ ef2 e_sub2(ef2 a, ef2 b) { ef2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ ef2 e_mul2(ef2 a, ef2 b) { ef2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint32_t e_cvt_relu_h2(ef2 v) {      // (lo, hi) fp32 -> fp16 pair, ReLU folded into the conversion
+    float a, b; e_upk2(v, a, b); uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a)); return d;
+}
+constexpr int kEiRows = 128;            // pair rows (= threads) per tile
+constexpr int kEiStride = 272;          // bytes per staged row: 256 + 16 keeps the 16-byte stores of 32 lanes conflict-free
+}  // namespace
+
+__global__ void __launch_bounds__(kEiRows, 3) k_edge_init_rows(const SceneDesc* __restrict__ sd, const float* __restrict__ ctrs,
+                                                               const float* __restrict__ vecs, const float* __restrict__ W,
+                                                               const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, __half* __restrict__ edge, int nb,
+                                                               int Nmax, int min_tokens) {
+    // per channel pair p: [b | w0 | w1 | w2] [w3 | w4 | gamma | beta], each entry a (channel 2p, channel 2p+1) pair
+    __shared__ __align__(16) float sw[64 * 16];
+    __shared__ __align__(16) unsigned char stile[kEiRows * kEiStride];
+    for (int e = threadIdx.x; e < 64 * 16; e += kEiRows) {
+        const int p = e >> 4, f = (e >> 1) & 7, c = 2 * p + (e & 1);
+        sw[e] = f == 0 ? bias[c] : f <= 5 ? W[c * 5 + (f - 1)] : f == 6 ? gamma[c] : beta[c];
     }
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t u = warp0; u < n_units; u += nwarps) {
-        const int j8 = (int)(u % units_per_row);
-        const int64_t bi_ = u / units_per_row;
-        const int i = (int)(bi_ % Nmax), b = (int)(bi_ / Nmax);
+    __syncthreads();
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int64_t per = (int64_t)Nmax * Nmax;
+    const int tiles_per_scene = (int)((per + kEiRows - 1) / kEiRows);
+    const int64_t n_tiles = (int64_t)nb * tiles_per_scene;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_scene);
+        const int64_t r0 = (int64_t)(tile - (int64_t)b * tiles_per_scene) * kEiRows;
         const SceneDesc d = sd[b];
         const int M = d.n_actor + d.n_lane;
-        if (M + 1 < min_tokens) continue;        // exact-tier scene: its edge lives in the fp32 pair grid
-        const int j0 = j8 * 8;
-        // slot s = k*8 + jj (k < 4) in lanes 0..31, slots 32..39 (k = 4) in lanes 0..7
-        float va = 0.f, vb = 0.f;
-        if (i < M) {
-            const int jj = lane & 7, k = lane >> 3, j = j0 + jj;
-            if (j < M) {
-                if (d.rpe) {
-                    va = __ldg(d.rpe + ((int64_t)k * M + i) * M + j);
-                    if (lane < 8) vb = __ldg(d.rpe + ((int64_t)4 * M + i) * M + j);
-                } else {
-                    const float2 ci = reinterpret_cast<const float2*>(ctrs)[d.geom_off + i];
-                    const float2 cj = reinterpret_cast<const float2*>(ctrs)[d.geom_off + j];
-                    const float2 vi = reinterpret_cast<const float2*>(vecs)[d.geom_off + i];
-                    const float2 vj = reinterpret_cast<const float2*>(vecs)[d.geom_off + j];
-                    const float dx = cj.x - ci.x, dy = cj.y - ci.y;
-                    const float dist = sqrtf(dx * dx + dy * dy);
-                    const float nj = sqrtf(vj.x * vj.x + vj.y * vj.y), ni = sqrtf(vi.x * vi.x + vi.y * vi.y);
-                    const float den1 = nj * ni + 1e-10f, den2 = nj * dist + 1e-10f;
-                    va = k == 0 ? (vj.x * vi.x + vj.y * vi.y) / den1
-                       : k == 1 ? (vj.x * vi.y - vj.y * vi.x) / den1
-                       : k == 2 ? (vj.x * dx + vj.y * dy) / den2
-                                : (vj.x * dy - vj.y * dx) / den2;
-                    vb = dist * 2.f / 100.f;
+        if (M + 1 < min_tokens) continue;            // exact-tier scene: its edge lives in the fp32 pair grid (uniform per tile)
+        const int64_t r = r0 + t;
+        const int i = (int)(r / Nmax), j = (int)(r - (int64_t)i * Nmax);
+        uint4* srow = reinterpret_cast<uint4*>(stile + t * kEiStride);
+        if (r < per && i < M && j < M) {
+            float rk[5];
+            if (d.rpe) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) rk[k] = __ldg(d.rpe + ((int64_t)k * M + i) * M + j);
+            } else {      // entry [i, j]: v1 = vecs[j], v2 = vecs[i], dpos = ctrs[j] - ctrs[i]   (utils.py:195-209)
+                const float2 ci = reinterpret_cast<const float2*>(ctrs)[d.geom_off + i];
+                const float2 cj = reinterpret_cast<const float2*>(ctrs)[d.geom_off + j];
+                const float2 vi = reinterpret_cast<const float2*>(vecs)[d.geom_off + i];
+                const float2 vj = reinterpret_cast<const float2*>(vecs)[d.geom_off + j];
+                const float dx = cj.x - ci.x, dy = cj.y - ci.y;
+                const float dist = sqrtf(dx * dx + dy * dy);
+                const float nj = sqrtf(vj.x * vj.x + vj.y * vj.y), ni = sqrtf(vi.x * vi.x + vi.y * vi.y);
+                const float den1 = nj * ni + 1e-10f, den2 = nj * dist + 1e-10f;
+                rk[0] = (vj.x * vi.x + vj.y * vi.y) / den1;
+                rk[1] = (vj.x * vi.y - vj.y * vi.x) / den1;
+                rk[2] = (vj.x * dx + vj.y * dy) / den2;
+                rk[3] = (vj.x * dy - vj.y * dx) / den2;
+                rk[4] = dist * 2.f / 100.f;
+            }
+            const ef2 q0 = e_pk2(rk[0], rk[0]), q1 = e_pk2(rk[1], rk[1]), q2 = e_pk2(rk[2], rk[2]), q3 = e_pk2(rk[3], rk[3]),
+                      q4 = e_pk2(rk[4], rk[4]);
+            ef2 y[64];
+            ef2 s1 = 0ull;
+#pragma unroll
+            for (int p = 0; p < 64; ++p) {
+                const ulonglong2 A = *reinterpret_cast<const ulonglong2*>(sw + p * 16);        // b, w0
+                const ulonglong2 Bv = *reinterpret_cast<const ulonglong2*>(sw + p * 16 + 4);   // w1, w2
+                const ulonglong2 Cv = *reinterpret_cast<const ulonglong2*>(sw + p * 16 + 8);   // w3, w4
+                const ef2 v = e_fma2(Cv.y, q4, e_fma2(Cv.x, q3, e_fma2(Bv.y, q2, e_fma2(Bv.x, q1, e_fma2(A.y, q0, A.x)))));
+                y[p] = v;
+                s1 = e_add2(s1, v);
+            }
+            float sa, sb;
+            e_upk2(s1, sa, sb);
+            const float mean = (sa + sb) * (1.f / 128.f);
+            const ef2 m2 = e_pk2(mean, mean);
+            ef2 qq = 0ull;
+#pragma unroll
+            for (int p = 0; p < 64; ++p) { y[p] = e_sub2(y[p], m2); qq = e_fma2(y[p], y[p], qq); }
+            e_upk2(qq, sa, sb);
+            const float rstd = rsqrtf((sa + sb) * (1.f / 128.f) + LN_EPS);
+            const ef2 r2 = e_pk2(rstd, rstd);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {          // 8 channels = 4 pairs per 16-byte chunk
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int p = c * 4 + e;
+                    const ulonglong2 G = *reinterpret_cast<const ulonglong2*>(sw + p * 16 + 12);   // gamma, beta
+                    o[e] = e_cvt_relu_h2(e_fma2(e_mul2(y[p], r2), G.x, G.y));
                 }
+                srow[c] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        } else if (r < per) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) srow[c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        // copy-out: a warp moves 2 staged rows (2 x 256 B) per instruction as two full segments
+        __half* dst0 = edge + ((int64_t)b * per + r0) * 128;
+#pragma unroll 4
+        for (int it = 0; it < kEiRows / 8; ++it) {
+            const int rr = it * 8 + warp * 2 + (lane >> 4);
+            if (r0 + rr < per) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stile + rr * kEiStride + (lane & 15) * 16);
+                *reinterpret_cast<uint4*>(dst0 + (int64_t)rr * 128 + (lane & 15) * 8) = v;
             }
         }
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = j0 + jj;
-            if (j >= Nmax) break;
-            const float r0 = __shfl_sync(0xffffffffu, va, jj), r1 = __shfl_sync(0xffffffffu, va, 8 + jj);
-            const float r2 = __shfl_sync(0xffffffffu, va, 16 + jj), r3 = __shfl_sync(0xffffffffu, va, 24 + jj);
-            const float r4 = __shfl_sync(0xffffffffu, vb, jj);
-            __half* dst = edge + (((int64_t)b * Nmax + i) * Nmax + j) * 128 + lane * 4;
-            if (i >= M || j >= M) { store4(dst, make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
-            float y[4], s = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                y[e] = fmaf(w[e][4], r4, fmaf(w[e][3], r3, fmaf(w[e][2], r2, fmaf(w[e][1], r1, fmaf(w[e][0], r0, bi[e])))));
-                s += y[e];
-            }
-            const float mean = warp_sum(s) * (1.f / 128.f);
-            float q = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { const float t = y[e] - mean; q += t * t; }
-            const float rstd = rsqrtf(warp_sum(q) * (1.f / 128.f) + LN_EPS);
-            store4(dst, make_float4(fmaxf((y[0] - mean) * rstd * gm[0] + bt[0], 0.f), fmaxf((y[1] - mean) * rstd * gm[1] + bt[1], 0.f),
-                                    fmaxf((y[2] - mean) * rstd * gm[2] + bt[2], 0.f), fmaxf((y[3] - mean) * rstd * gm[3] + bt[3], 0.f)));
-        }
+        __syncthreads();
     }
 }
 
 void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
                           const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st) {
-    const int64_t units = (int64_t)nb * Nmax * ((Nmax + 7) / 8);
-    if (units <= 0) return;
-    const int64_t blocks = std::min<int64_t>((units + 7) / 8, 148 * 16);
-    k_edge_init_h8<<<(unsigned)blocks, 256, 0, st>>>(sd + b0, ctrs, vecs, W, b, g, be, edge, nb, Nmax, min_tokens);
+    const int64_t tiles = (int64_t)nb * (((int64_t)Nmax * Nmax + kEiRows - 1) / kEiRows);
+    if (tiles <= 0) return;
+    const int64_t blocks = std::min<int64_t>(tiles, 148 * 3 * 4);
+    k_edge_init_rows<<<(unsigned)blocks, kEiRows, 0, st>>>(sd + b0, ctrs, vecs, W, b, g, be, edge, nb, Nmax, min_tokens);
     ++g_launches;
 }
 

@@ -212,10 +212,12 @@ class ScenarioTreeGeneratorB200:
         return out
 
     # ---- level construction -----------------------------------------------------------------
-    def _root_level(self, data) -> _Level:
+    def _root_level(self, data, L: "_Level") -> "_Level":
         """prepare_root_data (:414-465): observations (actor-local) -> global-frame histories.  One scene of a few
         actors: the frame arithmetic runs on the host (same torch fp32 ops as the reference) and everything the device
-        needs travels in ONE pinned buffer / one H2D copy instead of ~30 small copies and ~25 small launches."""
+        needs travels in ONE pinned buffer / one H2D copy instead of ~30 small copies and ~25 small launches.  Called
+        AFTER the root scene's network forward has been enqueued (the forward needs none of this), so the ~1 ms of host
+        arithmetic runs under the GPU's work instead of in front of it."""
         dev = self.device
         cpu = lambda t: t.detach().to("cpu", torch.float32)
         tj = data["TRAJS"][0]
@@ -258,8 +260,6 @@ class ScenarioTreeGeneratorB200:
             view[name] = dbuf[off:off + f.numel()].view(shape if shape is not None else tuple(t.shape))
             off += n
         dbuf[:total].copy_(pin[:total], non_blocking=True)
-        L = _Level()
-        L.F, L.Na = 1, Na
         L.hpos, L.hvel, L.hang, L.hcov = view["hpos"], view["hvel"], view["hang"], view["hcov"]
         L.orig, L.rot, L.ctrs, L.vecs = view["orig"], view["rot"], view["ctrs"], view["vecs"]
         L.pprob = view["pprob"]
@@ -269,14 +269,10 @@ class ScenarioTreeGeneratorB200:
             pool["cur_t0_set"] = True
         L.cur_t_host = [0]
         L.tgt_pts = view["tgt_pts"]
-        L.net_in = self._root_inputs(data, None, Na)
-        L.geom = None
         L.parent_keys = ["root"]
         # constants of the tree
         self._ttype = view["ttype"]
         self._lane_ctrs, self._lane_vecs = view["lane_ctrs"], view["lane_vecs"]
-        self._lanes = L.net_in[2]
-        self._n_lane = self._lanes.shape[0]
         return L
 
     def _root_inputs(self, data, d, Na):
@@ -298,12 +294,18 @@ class ScenarioTreeGeneratorB200:
                 out["tgt_nodes"], out["tgt_rpe"])
 
     def init_scenario_tree(self, data):                                           # :60-67
-        root = self._root_level(data)
+        Na = int(data["TRAJS"][0]["TRAJS_POS_OBS"].shape[0])
+        root = _Level()
+        root.F, root.Na, root.geom = 1, Na, None
+        root.net_in = self._root_inputs(data, None, Na)
+        self._lanes = root.net_in[2]
+        self._n_lane = self._lanes.shape[0]
         self._levels.append(root)
         rn = Node("root", None, _Scen(None, branch_flag=True))
         rn.data.obs_slot = 0
         self.tree.add_node(rn)
-        self.predict_scenes(root)
+        self.predict_scenes(root)                 # the GPU works on the root prediction ...
+        self._root_level(data, root)              # ... while the host builds the global-frame histories (one packed upload)
         self.create_nodes(self.prune_merge(root, [rn]))
         self.decide_branch()
 
