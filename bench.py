@@ -570,6 +570,8 @@ def run_native(args):
             elif isinstance(x, dict):
                 for v in x.values():
                     mark(v)
+            elif hasattr(x, "ctrs") and hasattr(x, "vecs"):       # anchors uploaded instead of dense RPE (one device buffer)
+                x.ctrs.record_stream(comp_s)
         mark(staged[slot])
 
     host_ms = {"upload": 0.0, "forward": 0.0, "download": 0.0}   # host wall time spent enqueueing each phase
@@ -638,6 +640,31 @@ def run_native(args):
     out_host = out_host[0]
     d2h = sum(x.numel() * 4 for x in out_host)
 
+    sharded = None
+    if world > 1 and not args.no_tree_sharded:
+        # tree mode of SURVEY.md 8e on ALL ranks: forced-full depth-4 x branch-6 tree, every level's frontier sharded over the
+        # ranks, one all-gather of the packed (cls | reg | vel) buffer per level; wall time, max over ranks
+        import copy
+        from mind_b200 import synth
+        from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
+        sargs = dict(x0=(100, 108, 92, 120, 112, 96, 130, 85), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0), v=(5, 9, 3, 8, 2, 10, 6, 12))
+        gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
+        gen.force_full, gen.distributed = (10, 20, 30), True
+        net.set_option("tc_min_tokens", 0)              # forced decisions: fused tier, as in tree_rollout.forced_full
+        times = []
+        for r in range(7):
+            data, lane, info, graph = synth.scene_s3(**sargs)
+            gen.reset(); gen.set_target_lane(lane, info); gen.lane_graph = copy.deepcopy(graph)
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gen.rollout(data)
+            torch.cuda.synchronize()
+            t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        net.set_option("tc_min_tokens", 128)
+        sharded = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches), "ranks": world,
+                   "single_gpu_ms_per_tree": None}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -663,36 +690,13 @@ def run_native(args):
                 "flops_per_launch": flops, "bytes_per_launch": B * fusion_bytes_per_scene(True)}
     cpu_v, cores, sample = cpu_port_rate(sd)
     tree = bench_tree(net, dev)
+    if sharded is not None:
+        sharded["single_gpu_ms_per_tree"] = tree.get("forced_full", {}).get("ms_per_tree")
     cost = bench_cost_fields(dev) if rank == 0 else None
     closed = bench_closed_loop(net, dev) if rank == 0 else None
     eager = gpu_eager_rate(sd, dev) if rank == 0 else None
     if eager and "scenes_per_s_B64" in eager:
         eager["native_over_eager_device_resident"] = value / world / eager["scenes_per_s_B64"]
-    sharded = None
-    if world > 1 and not args.no_tree_sharded:
-        # opt-in (never part of the driver's default run): forced-full depth-4 x branch-6 tree with every level's frontier
-        # sharded over the ranks and one all-gather of (cls, reg, vel) per level (SURVEY.md 8e tree mode); max over ranks
-        import copy
-        from mind_b200 import synth
-        from mind_b200.scenario_tree import ScenarioTreeGeneratorB200
-        sargs = dict(x0=(100, 108, 92, 120, 112, 96, 130, 85), y0=(0, 3.5, -3.5, 0, 3.5, 3.5, -3.5, 0), v=(5, 9, 3, 8, 2, 10, 6, 12))
-        gen = ScenarioTreeGeneratorB200(dev, net, 50, 50, _TreeCfg())
-        gen.force_full, gen.distributed = (10, 20, 30), True
-        net.set_option("tc_min_tokens", 0)              # forced decisions: fused tier, as in tree_rollout.forced_full
-        times = []
-        for r in range(7):
-            data, lane, info, graph = synth.scene_s3(**sargs)
-            gen.reset(); gen.set_target_lane(lane, info); gen.lane_graph = copy.deepcopy(graph)
-            dist.barrier(); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            gen.rollout(data)
-            torch.cuda.synchronize()
-            t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            times.append(float(t.item()))
-        net.set_option("tc_min_tokens", 128)
-        sharded = {"ms_per_tree": statistics.median(times[2:]), "level_batches": list(gen.net_batches), "ranks": world,
-                   "single_gpu_ms_per_tree": tree.get("forced_full", {}).get("ms_per_tree")}
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

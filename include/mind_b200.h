@@ -63,7 +63,11 @@ const char* mind_build_info(void);
 int mind_set_weight(MindCtx* ctx, const char* key, const float* host, int64_t numel);
 int mind_finalize_weights(MindCtx* ctx);
 
-/* options: "precision" (MIND_PREC_*), "chunk_scenes" (exact path workspace bound), "profile" (0/1) */
+/* options: "precision" (MIND_PREC_*), "chunk_scenes" (exact path workspace bound), "profile" (0/1), "graph" (0/1: replay a
+ * captured CUDA graph when batch shape + pointers repeat), "tc_min_tokens" (MIND_PREC_F16TC only, default 128: scenes with
+ * fewer tokens than this run the exact tier -- every N^2 contraction as a 3-term fp16 hi/lo tcgen05 product, fp32 edge --
+ * instead of the fp16-operand fused kernel, whose operand rounding is not averaged out over a small scene's few keys;
+ * 0 = fused kernel for every scene) */
 int mind_set_option(MindCtx* ctx, const char* name, int64_t value);
 
 /* ---- one batched forward:  network(data_in)   planners/mind/networks/network.py:582-595 ----

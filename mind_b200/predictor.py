@@ -79,14 +79,33 @@ class _LazyRPE(dict):
         return self["scene"]
 
 
-class _GeomRPE(list):
+class _GeomRPE:
     """data['RPE'] after pre_process when the collated dict carries the anchors the dense encoding was built from
     (TRAJS[b]['TRAJS_CTRS' / 'TRAJS_VECS'], LANE_GRAPH[b]['lane_ctrs' / 'lane_vecs'], scenario_tree.py:176-186):
     only those [sum M_b, 2] arrays are uploaded (~2.6 KB per 160-token scene instead of 512 KB of dense RPE) and
-    get_rpe is evaluated on the device."""
-    ctrs = None      # [sum M_b, 2] device, per scene [actors ; lanes]
-    vecs = None
-    counts = None    # per-scene M_b
+    get_rpe is evaluated on the device.  Behaves like the reference's list of {'scene', 'scene_mask'} dicts; the entries
+    are created when somebody indexes or iterates it (the network itself only reads ctrs / vecs / counts)."""
+
+    def __init__(self, ctrs, vecs, counts):
+        self.ctrs, self.vecs, self.counts = ctrs, vecs, counts      # [sum M_b, 2] device, per scene [actors ; lanes]
+        self._items = None
+
+    def _make(self):
+        if self._items is None:
+            self._items, off = [], 0
+            for n in self.counts:
+                self._items.append(_LazyRPE(self.ctrs[off:off + n], self.vecs[off:off + n]))
+                off += n
+        return self._items
+
+    def __len__(self):
+        return len(self.counts)
+
+    def __getitem__(self, i):
+        return self._make()[i]
+
+    def __iter__(self):
+        return iter(self._make())
 
 
 class ScenePredNetB200:
@@ -207,32 +226,30 @@ class ScenePredNetB200:
                 counts.append(int(t["TRAJS_CTRS"].shape[0]) + int(g["lane_ctrs"].shape[0]))
         except (KeyError, TypeError, AttributeError):
             return None
-        if any((not isinstance(x, torch.Tensor)) or x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 2 for x in cs + vs):
+        first = cs[0]
+        if not isinstance(first, torch.Tensor) or first.dtype != torch.float32 or first.dim() != 2 or first.shape[1] != 2:
             return None
         m = sum(counts)
         if cs[0].device.type == "cpu":
             slot = self._geom_pin.get(m)
-            if slot is None:      # two staging buffers per size: a two-deep pipeline may still be copying out of the other
-                slot = self._geom_pin[m] = [[torch.empty(2, m, 2).pin_memory() for _ in range(2)], 0, [None, None]]
-            k = slot[1] = slot[1] ^ 1
-            if slot[2][k] is not None:
-                slot[2][k].synchronize()
+            if slot is None:      # ring of pinned staging buffers: the host may run up to 7 uploads ahead of the copies
+                slot = self._geom_pin[m] = [[torch.empty(2, m, 2).pin_memory() for _ in range(8)], 0, [None] * 8]
+            k = slot[1] = (slot[1] + 1) % 8
+            if slot[2][k] is not None and not slot[2][k].query():
+                slot[2][k].synchronize()           # only when the host is 8 uploads ahead of the device
             pin = slot[0][k]
-            torch.cat(cs, 0, out=pin[0])
-            torch.cat(vs, 0, out=pin[1])
+            try:                                  # a tensor of another dtype / shape among the anchors: per-tensor path
+                torch.cat(cs, 0, out=pin[0])
+                torch.cat(vs, 0, out=pin[1])
+            except (RuntimeError, TypeError):
+                return None
             devbuf = pin.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             slot[2][k] = ev
         else:
             devbuf = torch.stack([torch.cat(cs, 0), torch.cat(vs, 0)]).to(self.device)
-        out = _GeomRPE()
-        out.ctrs, out.vecs, out.counts = devbuf[0], devbuf[1], counts
-        off = 0
-        for n in counts:
-            out.append(_LazyRPE(out.ctrs[off:off + n], out.vecs[off:off + n]))
-            off += n
-        return out
+        return _GeomRPE(devbuf[0], devbuf[1], counts)
 
     def _upload_rpe(self, rpe):
         scenes = []

@@ -66,6 +66,17 @@ def _fake_forward(net_in, geom):
     return cls, reg, vel, None, None
 
 
+def _fake_forward_packed(net_in, geom):
+    """same outputs laid out like ScenePredNetB200.forward_packed: (cls, reg, vel, cov_vel, param, a_off, pack)"""
+    from mind_b200.predictor import pack_layout
+    cls, reg, vel, _, _ = _fake_forward(net_in, geom)
+    B, A = cls.shape[0], reg.shape[0]
+    (c0, cn), (r0, rn), (v0, vn) = pack_layout(B, A)
+    pack = torch.zeros(v0 + vn)
+    pack[c0:c0 + cn] = cls.reshape(-1); pack[r0:r0 + rn] = reg.reshape(-1); pack[v0:v0 + vn] = vel.reshape(-1)
+    return (pack[c0:c0 + cn].view(B, 6), pack[r0:r0 + rn].view(A, 6, 60, 5), pack[v0:v0 + vn].view(A, 6, 60, 2), None, None, None, pack)
+
+
 def _level(F, na, nl, seed):
     g = torch.Generator().manual_seed(seed)
     net_in = (torch.rand(F * na, 14, 48, generator=g), [range(i * na, (i + 1) * na) for i in range(F)],
@@ -84,6 +95,9 @@ def _tree_worker(rank, world, port, q):
         net_in, geom = _level(F, na, nl, 100 + F)
         want = _fake_forward(net_in, geom)
         got = sharded_level_forward(_fake_forward, net_in, geom, F)
+        ok = ok and all(torch.equal(a, b) for a, b in zip(got, want[:3]))
+        # the predictor's output form: cls | reg | vel as views of ONE buffer -> equal shards take the single packed all-gather
+        got = sharded_level_forward(_fake_forward_packed, net_in, geom, F)
         ok = ok and all(torch.equal(a, b) for a, b in zip(got, want[:3]))
     q.put((rank, ok))
     dist.destroy_process_group()

@@ -233,3 +233,39 @@ def test_repeated_forwards_keep_the_protocol_clean(ckpt_sd, dev):
         if ref is None:
             ref = reg
         assert torch.equal(reg, ref), it
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", TOL_FP32), ("f16tc", TOL_TC)])
+def test_pre_process_uploads_anchors_when_the_dict_has_them(ckpt_sd, dev, prec, tol):
+    """pre_process on the collated dict as the tree generator hands it over (scenario_tree.py:69-70): when TRAJS / LANE_GRAPH
+    carry the anchors the dense RPE was built from, only those travel and get_rpe (utils.py:193-212) is evaluated on the
+    device; outputs vs the oracle on the dense RPE, ragged batch, and the staged 'RPE' entry still indexes like the
+    reference's list of dicts."""
+    from mind_b200 import synth
+    from mind_b200.predictor import _GeomRPE
+    from oracle.scene_pred_oracle import ScenePredOracle
+    sizes = [(5, 20), (17, 40), (32, 128), (8, 33)]
+    scenes = [synth.scene_s1(400 + i, na, nl, with_geom=True) for i, (na, nl) in enumerate(sizes)]
+    keys = ["ACTORS", "ACTOR_IDCS", "LANES", "LANE_IDCS", "RPE", "TGT_NODES", "TGT_RPE"]
+    data = synth.batch_from_scenes(scenes)
+    d = dict(zip(keys, data))
+    d["TRAJS"] = [{"TRAJS_CTRS": s["ctrs"][:na].contiguous(), "TRAJS_VECS": s["vecs"][:na].contiguous()} for s, (na, nl) in zip(scenes, sizes)]
+    d["LANE_GRAPH"] = [{"lane_ctrs": s["ctrs"][na:].contiguous(), "lane_vecs": s["vecs"][na:].contiguous()} for s, (na, nl) in zip(scenes, sizes)]
+    oc, orr, oa = ScenePredOracle(ckpt_sd)(data)
+    net = make_net(ckpt_sd, dev, prec)
+    staged = net.pre_process(d)
+    assert isinstance(staged[4], _GeomRPE) and len(staged[4]) == 4
+    cls, reg, aux = net(staged)
+    torch.cuda.synchronize()
+    for b in range(4):
+        assert (cls[b].cpu() - oc[b]).abs().max() < max(tol, 1e-5)
+        assert rel_err(reg[b], orr[b]) < tol and rel_err(aux[b][0], oa[b][0]) < tol
+    r2 = staged[4][2]["scene"]                       # on demand: the dense tensor, evaluated on the device
+    assert r2.is_cuda and tuple(r2.shape) == (5, 160, 160) and rel_err(r2, data[4][2]["scene"]) < 1e-5
+    net.rpe_on_device = False                        # the same dict through the dense-RPE upload
+    staged2 = net.pre_process(d)
+    assert not isinstance(staged2[4], _GeomRPE)
+    cls2, reg2, _ = net(staged2)
+    torch.cuda.synchronize()
+    for b in range(4):
+        assert rel_err(reg2[b], reg[b]) < max(tol, 1e-5)
