@@ -16,15 +16,21 @@
 namespace mind {
 namespace tcg {
 
-constexpr int kStages = 4;
 constexpr int kThreads = 320;      // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
-constexpr uint32_t STAGE_A = 16384, STAGE_W = 32768, STAGE = STAGE_A + STAGE_W;
-constexpr uint32_t RES_W_MAX = 98304;          // resident-W mode: W region (96 KB) + 6 A stages of 16 KB
-constexpr int RES_STAGES = 6;
-static_assert(RES_W_MAX + RES_STAGES * STAGE_A <= kStages * STAGE, "resident layout must fit the ring region");
-constexpr uint32_t SM_BAR = kStages * STAGE;
+// operand ring: stages of (16 KB A + n_tile x 128 B W) -- 3 stages at n_tile = 256, 4 at 128, up to 8 below; in resident-W mode
+// the W k-blocks sit at the front of the region and the rest is a ring of 16 KB A stages
+constexpr uint32_t RING_BYTES = 147456;
+constexpr uint32_t STAGE_A = 16384;
+constexpr uint32_t RES_W_MAX = 98304;          // resident-W mode: W region <= 96 KB, leaving >= 3 A stages
+// epilogue staging: each epilogue warp transposes its [32 rows x 32 columns] fp32 chunk through shared memory so that global
+// stores leave as full 128-byte row segments (one row per thread straight out of TMEM is 32 sectors per store instruction)
+constexpr uint32_t STG_STRIDE = 36;            // floats per staged row: 16-byte stores of 32 lanes and the transposed reads are conflict-free
+constexpr uint32_t STG_WARP = 32 * STG_STRIDE * 4;
+constexpr uint32_t SM_STG = RING_BYTES;
+constexpr uint32_t SM_BAR = SM_STG + 8 * STG_WARP;
 constexpr uint32_t SM_TMEM = SM_BAR + 192;
 constexpr uint32_t SMEM_BYTES = SM_TMEM + 16 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -113,6 +119,9 @@ struct Args {
     float* stats;
     int* err;
     int w_resident;            // all W k-blocks fit in smem: loaded once per CTA, A ring of 16 KB stages
+    int n_stages; uint32_t stage_bytes;      // streaming mode ring
+    int res_stages; uint32_t res_w_bytes;    // resident mode: A stages behind the W region
+    int r_in_shift;                          // r_in is a power of two: tile row -> (outer, inner) by shift / mask
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -143,11 +152,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
     const int total_tiles = g.tiles_outer * g.tiles_inner * g.tiles_n;
     const int nq = g.n_terms * g.k_blocks;
 
-    // resident mode: smem = [W: all k-blocks, <= RES_W_MAX][A ring: RES_STAGES x 16 KB]; bar_wres = bars + 96
+    // resident mode: smem = [W: all k-blocks, <= RES_W_MAX][A ring: res_stages x 16 KB]; bar_wres = bars + 160
     const uint32_t bar_wres = bars + 160;
     const int nkb_w = g.n_terms == 3 ? 2 * g.k_blocks : g.k_blocks;          // W k-blocks (hi | lo)
     const uint32_t wblk = (uint32_t)g.n_tile * 128u;                          // bytes of one W k-block
-    const uint32_t res_a0 = sbase + RES_W_MAX;                                // A ring base in resident mode
+    const uint32_t res_a0 = sbase + g.res_w_bytes;                            // A ring base in resident mode
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -162,7 +171,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                             const uint32_t full = bars + 8 * stage;
                             mbar_expect_tx(full, STAGE_A);
                             tma_load_3d(res_a0 + stage * STAGE_A, part ? &amap1 : &amap0, full, kb * 64, c * g.r_in, o * g.r_out);
-                            if (++stage == RES_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == g.res_stages) { stage = 0; phase ^= 1; }
                         }
                 }
             } else {
@@ -174,10 +183,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                         mbar_wait(bars + 64 + 8 * stage, phase ^ 1, g.err, 11);
                         const uint32_t full = bars + 8 * stage;
                         mbar_expect_tx(full, STAGE_A + (uint32_t)g.n_tile * 128u);
-                        const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+                        const uint32_t sA = sbase + stage * g.stage_bytes, sW = sA + STAGE_A;
                         tma_load_3d(sA, g.a_sel[term] ? &amap1 : &amap0, full, kb * 64, c * g.r_in, o * g.r_out);
                         tma_load_2d(sW, &wmap, full, g.w_k_off[term] + kb * 64, nt * g.n_tile);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -209,7 +218,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                                     umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sWlo + kk * 32), idesc, 1u);
                             }
                             umma_commit(bars + 64 + 8 * stage);
-                            if (++stage == RES_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == g.res_stages) { stage = 0; phase ^= 1; }
                         }
                     umma_commit(bars + 128 + 8 * acc);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -221,13 +230,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                     for (int q = 0; q < nq; ++q) {
                         mbar_wait(bars + 8 * stage, phase, g.err, 13);
                         tc_fence_after();
-                        const uint32_t sA = sbase + stage * STAGE, sW = sA + STAGE_A;
+                        const uint32_t sA = sbase + stage * g.stage_bytes, sW = sA + STAGE_A;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             umma_f16(tmem + acc * 256, umma_desc_sw128(sA + kk * 32), umma_desc_sw128(sW + kk * 32), idesc,
                                      (q | kk) != 0);
                         umma_commit(bars + 64 + 8 * stage);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(bars + 128 + 8 * acc);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -246,10 +255,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
         for (int tile = blockIdx.x; tile < total_tiles && (split_cols || chalf == 0); tile += gridDim.x) {
             const int nt = tile % g.tiles_n; const int rest = tile / g.tiles_n;
             const int c = rest % g.tiles_inner, o = rest / g.tiles_inner;
-            const int outer = o * g.r_out + row / g.r_in, inner = c * g.r_in + row % g.r_in;
+            const int outer = o * g.r_out + (row >> g.r_in_shift), inner = c * g.r_in + (row & (g.r_in - 1));
             const bool valid = outer < g.n_outer && inner < g.L_inner;
             const int64_t orow = (int64_t)outer * g.L_inner + inner;
-            float* crow = g.C + orow * g.ldc;
             const float* grow = (g.gbias && valid) ? g.gbias + (orow / g.gsize) * g.ldg : nullptr;
             mbar_wait(bars + 128 + 8 * acc, acc_phase, g.err, 14);
             tc_fence_after();
@@ -278,6 +286,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                     }
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float* stg = reinterpret_cast<float*>(sgen + SM_STG + (uint32_t)(warp - 2) * STG_WARP);
 #pragma unroll
                 for (int k4 = 0; k4 < 8; ++k4) {
                     const float bb[4] = {bz[k4].x, bz[k4].y, bz[k4].z, bz[k4].w};
@@ -290,28 +299,41 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                         if (n < g.N) { s1 += x; s2 += x * x; }
                         v[e] = x;
                     }
-                    if (valid) {
-                        const int n = nb + k4 * 4;
-                        if (g.C) {
-                            if (n + 3 < g.N && ((g.ldc & 3) == 0)) {
-                                *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-                            } else {
+                    *reinterpret_cast<float4*>(stg + lane * STG_STRIDE + k4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                __syncwarp();
+                // transposed write-out: 8 lanes cover the 32 columns of one row, 4 rows per instruction
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) if (n + e < g.N) crow[n + e] = v[e];
-                            }
-                        }
-                        if (g.Chi && n + 3 < g.N) {
-                            const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
-                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
-                            uint2 uh, ul;
-                            uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
-                            ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-                            *reinterpret_cast<uint2*>(g.Chi + orow * g.ldh + n) = uh;
-                            *reinterpret_cast<uint2*>(g.Clo + orow * g.ldh + n) = ul;
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3), c4 = lane & 7;
+                    const int trow = lg * 32 + rr;
+                    const int outer_r = o * g.r_out + (trow >> g.r_in_shift), inner_r = c * g.r_in + (trow & (g.r_in - 1));
+                    if (outer_r >= g.n_outer || inner_r >= g.L_inner) continue;
+                    const float4 x = *reinterpret_cast<const float4*>(stg + rr * STG_STRIDE + c4 * 4);
+                    const int64_t orow_r = (int64_t)outer_r * g.L_inner + inner_r;
+                    const int n = nb + c4 * 4;
+                    if (g.C) {
+                        float* cr = g.C + orow_r * g.ldc;
+                        if (n + 3 < g.N && ((g.ldc & 3) == 0)) {
+                            *reinterpret_cast<float4*>(cr + n) = x;
+                        } else {
+                            const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (n + e < g.N) cr[n + e] = xv[e];
                         }
                     }
+                    if (g.Chi && n + 3 < g.N) {
+                        const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+                        uint2 uh, ul;
+                        uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+                        *reinterpret_cast<uint2*>(g.Chi + orow_r * g.ldh + n) = uh;
+                        *reinterpret_cast<uint2*>(g.Clo + orow_r * g.ldh + n) = ul;
+                    }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -535,7 +557,7 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
             return "cudaFuncSetAttribute(tc_gemm) failed";
         attr = true;
     }
-    if (p.r_in * p.r_out != 128) return "tc_gemm: r_in * r_out must be 128";
+    if (p.r_in * p.r_out != 128 || (p.r_in & (p.r_in - 1))) return "tc_gemm: r_in * r_out must be 128, r_in a power of two";
     if (p.n_tile % 32 || p.n_tile > 256 || p.n_tile < 32) return "tc_gemm: n_tile must be a multiple of 32 in [32,256]";
     tcg::Args g;
     g.n_terms = p.split ? 3 : 1;
@@ -549,7 +571,13 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.C = p.C; g.ldc = p.ldc; g.Chi = p.Chi; g.Clo = p.Clo; g.ldh = p.ldh; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
     g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
     const int nkb_w = (p.split ? 2 : 1) * p.k_blocks;
+    g.res_w_bytes = (uint32_t)nkb_w * (uint32_t)p.n_tile * 128u;
     g.w_resident = (g.tiles_n == 1 && (int64_t)nkb_w * p.n_tile * 128 <= (int64_t)tcg::RES_W_MAX) ? 1 : 0;
+    g.res_stages = g.w_resident ? std::min<int>(8, (int)((tcg::RING_BYTES - g.res_w_bytes) / tcg::STAGE_A)) : 0;
+    g.r_in_shift = 0;
+    while ((1 << g.r_in_shift) < p.r_in) ++g.r_in_shift;
+    g.stage_bytes = tcg::STAGE_A + (uint32_t)p.n_tile * 128u;
+    g.n_stages = std::min<int>(8, (int)(tcg::RING_BYTES / g.stage_bytes));
     const int total = g.tiles_inner * g.tiles_outer * g.tiles_n;
     if (total <= 0) return nullptr;
     CUtensorMap a0, a1, w;
