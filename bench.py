@@ -588,8 +588,11 @@ def run_native(args):
             cls, reg, aux = net(staged[slot])                   # the call scenario_tree.py:71 makes
             t2 = time.perf_counter()
             pk = net._last_packed
-            if world > 1:
-                gather_bufs[slot], _ = all_gather_packed(pk[6], B, pk[1].shape[0], out=gather_bufs[slot])
+            if world > 1:                                       # same overlapped collective as in the device-timed loop
+                if pending[slot] is not None:
+                    pending[slot][0].wait()
+                gather_bufs[slot], work = all_gather_packed(pk[6], B, pk[1].shape[0], out=gather_bufs[slot], async_op=True)
+                pending[slot] = (work, pk)
             ev_out[slot].record(comp_s)
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(ev_out[slot])
@@ -604,6 +607,7 @@ def run_native(args):
             host_ms["upload"] += (t1 - t0) * 1e3
             host_ms["forward"] += (t2 - t1) * 1e3
             host_ms["download"] += (t3 - t2) * 1e3
+        drain()
         comp_s.wait_stream(copy_s)
     def measure_e2e(n_steps):
         run_e2e(max(3, args.warmup))

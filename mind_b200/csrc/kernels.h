@@ -32,6 +32,9 @@ struct GemmArgs {
     float* C = nullptr; int ldc = 0;            // [M,N]
     int M = 0, N = 0, K = 0;
     int relu = 0;
+    // set by launch_gemm for skinny outputs with a long K (few CTAs, serial K loop): grid.z slices of K write raw partial
+    // sums to `part` [ksplit][M][N]; a second kernel adds them in slice order (deterministic) and applies bias / ReLU
+    int ksplit = 1; float* part = nullptr;
 };
 void launch_gemm(const GemmArgs& g, cudaStream_t st);
 

@@ -48,18 +48,20 @@ __global__ void __launch_bounds__(256) k_gemm_tn(GemmArgs g) {
     const bool a_vec = ((g.lda & 3) == 0) && ((((uintptr_t)g.A) & 15) == 0);
     const bool w_vec = ((g.ldw & 3) == 0) && ((((uintptr_t)g.W) & 15) == 0);
 
-    for (int k0 = 0; k0 < g.K; k0 += GBK) {
+    const int kslice = g.ksplit > 1 ? ((g.K / g.ksplit + GBK - 1) / GBK) * GBK : g.K;
+    const int k_begin = g.ksplit > 1 ? (int)blockIdx.z * kslice : 0, k_end = min(g.K, k_begin + kslice);
+    for (int k0 = k_begin; k0 < k_end; k0 += GBK) {
         {   // A tile
             const int64_t m = m0 + lrow;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (m < g.M) {
                 const float* p = g.A + m * (int64_t)g.lda + k0 + lcol;
-                if (a_vec && k0 + lcol + 3 < g.K) {
+                if (a_vec && k0 + lcol + 3 < k_end) {
                     float4 t = *reinterpret_cast<const float4*>(p);
                     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) if (k0 + lcol + e < g.K) v[e] = p[e];
+                    for (int e = 0; e < 4; ++e) if (k0 + lcol + e < k_end) v[e] = p[e];
                 }
             }
 #pragma unroll
@@ -70,12 +72,12 @@ __global__ void __launch_bounds__(256) k_gemm_tn(GemmArgs g) {
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (n < g.N) {
                 const float* p = g.W + (int64_t)n * g.ldw + k0 + lcol;
-                if (w_vec && k0 + lcol + 3 < g.K) {
+                if (w_vec && k0 + lcol + 3 < k_end) {
                     float4 t = *reinterpret_cast<const float4*>(p);
                     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) if (k0 + lcol + e < g.K) v[e] = p[e];
+                    for (int e = 0; e < 4; ++e) if (k0 + lcol + e < k_end) v[e] = p[e];
                 }
             }
 #pragma unroll
@@ -104,12 +106,27 @@ __global__ void __launch_bounds__(256) k_gemm_tn(GemmArgs g) {
             const int n = n0 + tx * 4 + j;
             if (n >= g.N) continue;
             float v = acc[i][j];
+            if (g.ksplit > 1) { g.part[((int64_t)blockIdx.z * g.M + m) * g.N + n] = v; continue; }
             if (g.bias) v += g.bias[n];
             if (g.gbias) v += g.gbias[(m / g.gsize) * (int64_t)g.ldg + n];
             if (g.relu) v = fmaxf(v, 0.f);
             g.C[m * (int64_t)g.ldc + n] = v;
         }
     }
+}
+
+// second half of a split-K product: partial sums added in slice order, then bias / group bias / ReLU
+__global__ void __launch_bounds__(256) k_splitk_reduce(GemmArgs g) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)g.M * g.N) return;
+    const int64_t m = idx / g.N;
+    const int n = (int)(idx - m * g.N);
+    float v = 0.f;
+    for (int z = 0; z < g.ksplit; ++z) v += g.part[(int64_t)z * g.M * g.N + idx];
+    if (g.bias) v += g.bias[n];
+    if (g.gbias) v += g.gbias[(m / g.gsize) * (int64_t)g.ldg + n];
+    if (g.relu) v = fmaxf(v, 0.f);
+    g.C[m * (int64_t)g.ldc + n] = v;
 }
 
 // large aligned case (K % 16 == 0, N % 128 == 0, 16-byte aligned rows): 128x128x16 tiles, 8x8 per
@@ -246,7 +263,33 @@ void launch_gemm(const GemmArgs& g, cudaStream_t st) {
         k_gemm_tn_big<<<grid, 256, 0, st>>>(g);
     } else {
         dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
-        k_gemm_tn<<<grid, 256, 0, st>>>(g);
+        // skinny output, long K (e.g. the decoder's 1536 -> 128 linear on B*6 rows: 48 CTAs walking K = 1536 serially):
+        // split K over grid.z so that the chip is covered, reduce deterministically
+        // scratch per device, grow-only and never freed: a captured CUDA graph may hold the pointer of an earlier, smaller one
+        static float* s_part[16] = {nullptr};
+        static size_t s_part_floats[16] = {0};
+        const int ctas = (int)(grid.x * grid.y);
+        int ks = 1, dev = 0;
+        if (ctas < 96 && g.K >= 512) ks = std::min(std::min(8, g.K / 128), std::max(1, 296 / ctas));
+        if (ks > 1 && (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16)) ks = 1;
+        if (ks > 1) {
+            const size_t need = (size_t)ks * (size_t)g.M * (size_t)g.N;
+            if (need > s_part_floats[dev]) {     // first use of a shape is never inside a graph capture (mind_forward runs it plainly first)
+                float* nb = nullptr;
+                const size_t cap = std::max(need, 2 * s_part_floats[dev]);
+                if (cudaMalloc(&nb, cap * sizeof(float)) == cudaSuccess) { s_part[dev] = nb; s_part_floats[dev] = cap; } else { cudaGetLastError(); ks = 1; }
+            }
+        }
+        if (ks > 1) {
+            GemmArgs h = g;
+            h.ksplit = ks; h.part = s_part[dev];
+            grid.z = (unsigned)ks;
+            k_gemm_tn<<<grid, 256, 0, st>>>(h);
+            k_splitk_reduce<<<(unsigned)(((int64_t)g.M * g.N + 255) / 256), 256, 0, st>>>(h);
+            ++g_launches;
+        } else {
+            k_gemm_tn<<<grid, 256, 0, st>>>(g);
+        }
     }
     ++g_launches;
 }

@@ -387,71 +387,72 @@ struct ApplyArgs {
     const __half* res_hi; const __half* res_lo;     // identity shortcut, padded [A][L+2][C]
     __half* out_hi; __half* out_lo; float* out_f32;
     int A, L, C, relu;
+    int c_shift;            // log2(C) when C is a power of two, else -1
 };
 __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
-    const int a = blockIdx.x;
-    __shared__ float sm[4];
-    if (threadIdx.x == 0) {
-        const float n = (float)(p.L * p.C);
+    // one WARP per actor: every lane forms the statistics from the 12 (+12) partial sums itself (broadcast loads), so there is
+    // no single-thread phase and no block barrier in front of a few hundred elements of work
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int n = p.L * p.C, n4 = n >> 2;
+    const float fn = (float)n;
+    for (int a = blockIdx.x * wpb + (threadIdx.x >> 5); a < p.A; a += gridDim.x * wpb) {
         const float* s = p.stats + (int64_t)a * 12;     // 3 inner tiles x 2 column halves x (sum, sum^2), fixed order
-        const float mean = (((s[0] + s[2]) + (s[4] + s[6])) + (s[8] + s[10])) / n;
-        const float var = fmaxf((((s[1] + s[3]) + (s[5] + s[7])) + (s[9] + s[11])) / n - mean * mean, 0.f);
-        sm[0] = mean; sm[1] = rsqrtf(var + 1e-5f);
+        const float mean = (((s[0] + s[2]) + (s[4] + s[6])) + (s[8] + s[10])) / fn;
+        const float var = fmaxf((((s[1] + s[3]) + (s[5] + s[7])) + (s[9] + s[11])) / fn - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        float m2 = 0.f, rstd2 = 0.f;
         if (p.res_raw) {
             const float* r = p.res_stats + (int64_t)a * 12;
-            const float m2 = (((r[0] + r[2]) + (r[4] + r[6])) + (r[8] + r[10])) / n;
-            const float v2 = fmaxf((((r[1] + r[3]) + (r[5] + r[7])) + (r[9] + r[11])) / n - m2 * m2, 0.f);
-            sm[2] = m2; sm[3] = rsqrtf(v2 + 1e-5f);
+            m2 = (((r[0] + r[2]) + (r[4] + r[6])) + (r[8] + r[10])) / fn;
+            const float v2 = fmaxf((((r[1] + r[3]) + (r[5] + r[7])) + (r[9] + r[11])) / fn - m2 * m2, 0.f);
+            rstd2 = rsqrtf(v2 + 1e-5f);
         }
-    }
-    __syncthreads();
-    const float mean = sm[0], rstd = sm[1];
-    const int n = p.L * p.C;
-    for (int i4 = threadIdx.x; i4 < (n >> 2); i4 += blockDim.x) {      // C % 4 == 0: 4 channels per iteration
-        const int i = i4 << 2;
-        const int t = i / p.C, c = i - t * p.C;
-        const float4 x = *reinterpret_cast<const float4*>(p.raw + (int64_t)a * n + i);
-        const float4 gm = *reinterpret_cast<const float4*>(p.gamma + c), bt = *reinterpret_cast<const float4*>(p.beta + c);
-        float y[4] = {(x.x - mean) * rstd * gm.x + bt.x, (x.y - mean) * rstd * gm.y + bt.y,
-                      (x.z - mean) * rstd * gm.z + bt.z, (x.w - mean) * rstd * gm.w + bt.w};
-        const int64_t pidx = ((int64_t)a * (p.L + 2) + t + 1) * p.C + c;
-        if (p.res_raw) {
-            const float4 r = *reinterpret_cast<const float4*>(p.res_raw + (int64_t)a * n + i);
-            const float4 g2 = *reinterpret_cast<const float4*>(p.res_gamma + c), b2 = *reinterpret_cast<const float4*>(p.res_beta + c);
-            y[0] += (r.x - sm[2]) * sm[3] * g2.x + b2.x; y[1] += (r.y - sm[2]) * sm[3] * g2.y + b2.y;
-            y[2] += (r.z - sm[2]) * sm[3] * g2.z + b2.z; y[3] += (r.w - sm[2]) * sm[3] * g2.w + b2.w;
-        } else if (p.res_hi) {
-            const uint2 h = *reinterpret_cast<const uint2*>(p.res_hi + pidx), l = *reinterpret_cast<const uint2*>(p.res_lo + pidx);
-            const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-            const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
-            y[0] += h0.x + l0.x; y[1] += h0.y + l0.y; y[2] += h1.x + l1.x; y[3] += h1.y + l1.y;
+        for (int i4 = lane; i4 < n4; i4 += 32) {      // C % 4 == 0: 4 channels per iteration
+            const int i = i4 << 2;
+            const int t = p.c_shift >= 0 ? (i >> p.c_shift) : i / p.C, c = i - t * p.C;
+            const float4 x = *reinterpret_cast<const float4*>(p.raw + (int64_t)a * n + i);
+            const float4 gm = *reinterpret_cast<const float4*>(p.gamma + c), bt = *reinterpret_cast<const float4*>(p.beta + c);
+            float y[4] = {(x.x - mean) * rstd * gm.x + bt.x, (x.y - mean) * rstd * gm.y + bt.y,
+                          (x.z - mean) * rstd * gm.z + bt.z, (x.w - mean) * rstd * gm.w + bt.w};
+            const int64_t pidx = ((int64_t)a * (p.L + 2) + t + 1) * p.C + c;
+            if (p.res_raw) {
+                const float4 r = *reinterpret_cast<const float4*>(p.res_raw + (int64_t)a * n + i);
+                const float4 g2 = *reinterpret_cast<const float4*>(p.res_gamma + c), b2 = *reinterpret_cast<const float4*>(p.res_beta + c);
+                y[0] += (r.x - m2) * rstd2 * g2.x + b2.x; y[1] += (r.y - m2) * rstd2 * g2.y + b2.y;
+                y[2] += (r.z - m2) * rstd2 * g2.z + b2.z; y[3] += (r.w - m2) * rstd2 * g2.w + b2.w;
+            } else if (p.res_hi) {
+                const uint2 h = *reinterpret_cast<const uint2*>(p.res_hi + pidx), l = *reinterpret_cast<const uint2*>(p.res_lo + pidx);
+                const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+                y[0] += h0.x + l0.x; y[1] += h0.y + l0.y; y[2] += h1.x + l1.x; y[3] += h1.y + l1.y;
+            }
+            if (p.relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
+            if (p.out_hi) {
+                const __half2 a01 = __floats2half2_rn(y[0], y[1]), a23 = __floats2half2_rn(y[2], y[3]);
+                const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
+                const __half2 b01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), b23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
+                uint2 uh, ul;
+                uh.x = *reinterpret_cast<const uint32_t*>(&a01); uh.y = *reinterpret_cast<const uint32_t*>(&a23);
+                ul.x = *reinterpret_cast<const uint32_t*>(&b01); ul.y = *reinterpret_cast<const uint32_t*>(&b23);
+                *reinterpret_cast<uint2*>(p.out_hi + pidx) = uh;
+                *reinterpret_cast<uint2*>(p.out_lo + pidx) = ul;
+            }
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)a * n + i) = make_float4(y[0], y[1], y[2], y[3]);
         }
-        if (p.relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
-        if (p.out_hi) {
-            const __half2 a01 = __floats2half2_rn(y[0], y[1]), a23 = __floats2half2_rn(y[2], y[3]);
-            const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
-            const __half2 b01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), b23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
-            uint2 uh, ul;
-            uh.x = *reinterpret_cast<const uint32_t*>(&a01); uh.y = *reinterpret_cast<const uint32_t*>(&a23);
-            ul.x = *reinterpret_cast<const uint32_t*>(&b01); ul.y = *reinterpret_cast<const uint32_t*>(&b23);
-            *reinterpret_cast<uint2*>(p.out_hi + pidx) = uh;
-            *reinterpret_cast<uint2*>(p.out_lo + pidx) = ul;
-        }
-        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)a * n + i) = make_float4(y[0], y[1], y[2], y[3]);
-    }
-    if (p.out_hi) {   // zero pad rows t = 0 and t = L+1
-        for (int c = threadIdx.x; c < 2 * p.C; c += blockDim.x) {
-            const int64_t pidx = ((int64_t)a * (p.L + 2) + (c < p.C ? 0 : p.L + 1)) * p.C + (c % p.C);
-            p.out_hi[pidx] = __float2half(0.f);
-            p.out_lo[pidx] = __float2half(0.f);
-        }
-        // K-padded conv windows of the LAST actor read up to 4 rows past the logical end of this
-        // (possibly re-used, larger) buffer: keep them finite (they meet zero weights)
-        if (a == p.A - 1) {
-            const int64_t end = (int64_t)p.A * (p.L + 2) * p.C;
-            for (int c = threadIdx.x; c < 4 * p.C; c += blockDim.x) {
-                p.out_hi[end + c] = __float2half(0.f);
-                p.out_lo[end + c] = __float2half(0.f);
+        if (p.out_hi) {   // zero pad rows t = 0 and t = L+1
+            for (int c = lane; c < 2 * p.C; c += 32) {
+                const int64_t pidx = ((int64_t)a * (p.L + 2) + (c < p.C ? 0 : p.L + 1)) * p.C + (c < p.C ? c : c - p.C);
+                p.out_hi[pidx] = __float2half(0.f);
+                p.out_lo[pidx] = __float2half(0.f);
+            }
+            // K-padded conv windows of the LAST actor read up to 4 rows past the logical end of this
+            // (possibly re-used, larger) buffer: keep them finite (they meet zero weights)
+            if (a == p.A - 1) {
+                const int64_t end = (int64_t)p.A * (p.L + 2) * p.C;
+                for (int c = lane; c < 4 * p.C; c += 32) {
+                    p.out_hi[end + c] = __float2half(0.f);
+                    p.out_lo[end + c] = __float2half(0.f);
+                }
             }
         }
     }
@@ -601,8 +602,10 @@ void tcg_gn_apply(const TcApply& q, cudaStream_t st) {
     p.res_raw = q.res_raw; p.res_stats = q.res_stats; p.res_gamma = q.res_gamma; p.res_beta = q.res_beta;
     p.res_hi = q.res_hi; p.res_lo = q.res_lo; p.out_hi = q.out_hi; p.out_lo = q.out_lo; p.out_f32 = q.out_f32;
     p.A = q.A; p.L = q.L; p.C = q.C; p.relu = q.relu;
+    p.c_shift = -1;
+    for (int sft = 0; sft < 12; ++sft) if ((1 << sft) == q.C) p.c_shift = sft;
     if (q.A <= 0) return;
-    tcg::k_gn_apply<<<q.A, 256, 0, st>>>(p);
+    tcg::k_gn_apply<<<(unsigned)std::min((q.A + 7) / 8, 148 * 8), 256, 0, st>>>(p);
     ++g_launches;
 }
 void tcg_fpn_up_add(const float* prev, const float* lat, float* out, __half* hi, __half* lo, int A, int L, int C, cudaStream_t st) {
