@@ -136,6 +136,8 @@ struct MindCtx {
     ActorTc actor_tc{};           // ActorNet on the tensor-core GEMM engine
     struct LaneW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; const float* bias = nullptr; };
     LaneW lane_tc[2][4];          // per aggregate block: fc1.0, fc1.3, fc2.0[:, :128], fc2.3 as [128][hi 128 | lo 128] fp16
+    LaneTc lane_fused{};          // the whole LaneNet as one persistent tcgen05 kernel (lane_tc.cu)
+    int lane_unfused = 0;         // diagnostics: layer-by-layer LaneNet on the GEMM engine instead
     int* lane_err = nullptr;
     struct NodeW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; int N = 0, K = 0, n_tile = 128; };
     NodeW node_tc[6][4];          // per fusion layer: [S|T|q] (384x128), out-proj (128x128), linear1 (256x128), linear2 (128x256)
@@ -198,6 +200,7 @@ extern "C" void mind_destroy(MindCtx* c) {
     if (c->d_small) cudaFree(c->d_small);
     tc_free(c->tc);
     actor_tc_free(c->actor_tc);
+    lane_tc_free(c->lane_fused);
     for (auto& blk : c->lane_tc) for (auto& lw : blk) if (lw.W) cudaFree(lw.W);
     if (c->lane_err) cudaFree(c->lane_err);
     for (auto& lay : c->node_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
@@ -219,6 +222,9 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
         c->precision = (int)value;
     } else if (!strcmp(name, "actor_simt")) {
         c->actor_simt = value != 0;
+    } else if (!strcmp(name, "lane_unfused")) {
+        if (c->lane_unfused != (value != 0)) graph_cache_clear(c);
+        c->lane_unfused = value != 0;
     } else if (!strcmp(name, "graph")) {
         c->use_graph = value ? 1 : 0;
         if (!c->use_graph) graph_cache_clear(c);
@@ -417,6 +423,8 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
         if (err) return fail("tc_pack_weights: %s", err);
         err = actor_tc_pack(c->actor_tc, c->host_w, c->dev_w);
         if (err) return fail("actor_tc_pack: %s", err);
+        err = lane_tc_pack(c->lane_fused, c->host_w);
+        if (err) return fail("%s", err);
         // LaneNet linears as [N=128][hi K=128 | lo K=128] fp16 operands of the GEMM engine
         const char* lnames[4] = {"fc1.0", "fc1.3", "fc2.0", "fc2.3"};
         for (int blk = 0; blk < 2; ++blk)
@@ -964,7 +972,9 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         CUDA_OK(cudaMemcpyAsync(w.lane_in, bt->lanes, sizeof(float) * (size_t)Ltot * 160, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemcpyAsync(w.lane_in + (int64_t)Ltot * 160, bt->tgt_nodes, sizeof(float) * (size_t)B * 160,
                             cudaMemcpyDeviceToDevice, st));
-    if (c->precision == MIND_PREC_F16TC && !c->actor_simt) {                                // :587,589
+    if (c->precision == MIND_PREC_F16TC && !c->actor_simt && !c->lane_unfused) {            // :587,589
+        if (const char* e = lane_tc_run(c->lane_fused, w.lane_in, (int)Lp, w.lane_feat, c->sm_count, st)) return fail("lane_tc_run: %s", e);
+    } else if (c->precision == MIND_PREC_F16TC && !c->actor_simt) {
         if (const char* e = run_lane_net_tc(c, w, Lp, st)) return fail("run_lane_net_tc: %s", e);
     } else {
         run_lane_net(c, w, Lp, st);

@@ -60,4 +60,17 @@ int64_t actor_tc_ws_bytes(int A);
 // actors [A,14,48] fp32 -> out [A,128]
 const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float* out, int sm_count, cudaStream_t st);
 
+// ---- LaneNet (reference network.py:64-121) as one persistent tcgen05 kernel (lane_tc.cu) --------------------
+struct LaneTc {
+    __half* W = nullptr;       // 22 matrices [128][128] fp16: per block fc1.0, fc1.3, fc2.0 (h half), fc2.0 (max half), fc2.3 as (hi, lo); proj (hi, lo)
+    float* params = nullptr;   // [31][128] biases / LayerNorm parameters in the order the kernel consumes them
+    int* d_err = nullptr;
+    alignas(64) unsigned char wmap[128];
+    bool ready = false;
+};
+const char* lane_tc_pack(LaneTc& l, const std::map<std::string, std::vector<float>>& host);
+void lane_tc_free(LaneTc& l);
+// lanes [Lp * 10, 16] fp32 node features -> out [Lp, 128]
+const char* lane_tc_run(LaneTc& l, const float* lanes, int Lp, float* out, int sm_count, cudaStream_t st);
+
 }  // namespace mind

@@ -269,3 +269,24 @@ def test_pre_process_uploads_anchors_when_the_dict_has_them(ckpt_sd, dev, prec, 
     torch.cuda.synchronize()
     for b in range(4):
         assert rel_err(reg2[b], reg[b]) < max(tol, 1e-5)
+
+
+@pytest.mark.parametrize("n_lane", [1, 11, 12, 13, 119, 131])
+def test_fused_lane_net_matches_the_layer_by_layer_path(ckpt_sd, dev, n_lane):
+    """k_lane_net_tc (the whole LaneNet chain on chip, 12 polylines per tile) vs the layer-by-layer GEMM-engine path it
+    replaces and vs the oracle, for polyline counts around the tile size (Lp = lanes + one target polyline per scene)."""
+    from mind_b200 import synth
+    from oracle import scene_pred_oracle as O
+    data = synth.batch_from_scenes([synth.scene_s1(900 + n_lane, 3, n_lane), synth.scene_s1(901 + n_lane, 2, 5)])
+    want = O.lane_net(torch.cat([data[2], data[5]]).float(), O.Params({k: v.float() for k, v in ckpt_sd.items()}).sub("lane_net."))
+    taps = []
+    for unfused in (0, 1):
+        net = make_net(ckpt_sd, dev, "f16tc")
+        net.set_option("lane_unfused", unfused)
+        net(to_dev(data, dev))
+        n = n_lane + 5 + 2
+        taps.append(net.debug_tap("lane_feat", n * 128).view(n, 128).clone())
+        net.sync_check()
+    torch.cuda.synchronize()
+    assert rel_err(taps[0], want) < 2e-5 and rel_err(taps[1], want) < 2e-5
+    assert rel_err(taps[0], taps[1]) < 1e-5
