@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmind_b200.so")
-SOURCES = ["mind_api.cu", "simt_kernels.cu", "fusion_tc.cu", "pair_x3.cu", "lane_tc.cu", "tc_gemm.cu", "actor_tc.cu", "tree_step.cu", "cost_field.cu", "ilqr_tree.cpp"]
+SOURCES = ["mind_api.cu", "simt_kernels.cu", "fusion_tc.cu", "pair_x3.cu", "lane_tc.cu", "node_tc.cu", "tc_gemm.cu", "actor_tc.cu", "tree_step.cu", "cost_field.cu", "ilqr_tree.cpp"]
 NVCC_FLAGS = (["-D" + d for d in os.environ.get("MIND_DEFS", "").split()] if os.environ.get("MIND_DEFS") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

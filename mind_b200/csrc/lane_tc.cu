@@ -26,18 +26,18 @@ using namespace mind::tcp;
 constexpr int kThreads = 544;
 constexpr int kPolyPerTile = 12;
 constexpr uint32_t kStage = 32768;                       // one 128 x 128 fp16 matrix: 2 k-blocks of [128 rows][128 B]
-constexpr uint32_t SM_RING = 0;                          // 3 weight stages
-constexpr uint32_t SM_WPROJ = 3 * kStage;                // proj weights, k-block 0 of (hi | lo): 2 x 16 KB
-constexpr uint32_t SM_H = SM_WPROJ + 32768;              // fp32 [128 rows][128 ch], 16-byte chunks XOR-swizzled by row
+constexpr int kRing = 4;                                 // weight stages in flight: the stream out of L2 is latency-bound
+constexpr uint32_t SM_RING = 0;
+constexpr uint32_t SM_H = kRing * kStage;                // fp32 [128 rows][128 ch], 16-byte chunks XOR-swizzled by row
 constexpr uint32_t SM_P = SM_H + 65536;                  // float [31][128] biases / LN parameters
 constexpr uint32_t SM_M = SM_P + 31 * 512;               // float [12][128] per-polyline max
 constexpr uint32_t SM_STAT = SM_M + 12 * 512;            // float2 [2 buffers][4 quarters][128 rows]
-constexpr uint32_t SM_BAR = SM_STAT + 8192;              // w_full[3] w_empty[3] d_full wproj
-constexpr uint32_t SM_TMEM = SM_BAR + 64;
+constexpr uint32_t SM_BAR = SM_STAT + 8192;              // w_full[kRing] w_empty[kRing] d_full
+constexpr uint32_t SM_TMEM = SM_BAR + 16 * kRing + 16;
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SM_TOTAL + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
-constexpr int kMatsPerTile = 20;                         // streamed matrices per tile (10 per block, hi then lo)
+constexpr int kMatsPerTile = 21;                         // weight stages per tile: proj (k-block 0 of hi | lo in one stage), then 10 per block (hi, lo)
 constexpr int kBarHand = 6;                              // epilogue -> issuer hand-off (named barrier, 544 threads)
 // TMEM columns: A operand [0,128) (hi [0,64) | lo [64,128)), accumulator [128,256), parked block input x [256,384) fp32,
 // second A operand (per-polyline max, broadcast to its rows) [384,512)
@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_lane_net_tc(const __grid_consta
     float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
     const uint32_t bar0 = sbase + SM_BAR;
-    const uint32_t bar_d = bar0 + 48, bar_wp = bar0 + 56;          // w_full[s] = bar0 + 8 s, w_empty[s] = bar0 + 24 + 8 s
+    const uint32_t bar_e = bar0 + 8 * kRing, bar_d = bar0 + 16 * kRing;          // w_full[s] = bar0 + 8 s, w_empty[s] = bar_e + 8 s
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < 3; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 24 + 8 * s, 1); }
-        mbar_init(bar_d, 1); mbar_init(bar_wp, 1);
+        for (int s = 0; s < kRing; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_e + 8 * s, 1); }
+        mbar_init(bar_d, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -92,36 +92,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_lane_net_tc(const __grid_consta
         uint32_t ld = 0, use = 0;                     // weight stages loaded / consumed so far (elected lane only)
         const uint32_t id128 = umma_idesc_f16(128);
         auto load_stage = [&](uint32_t s) {
-            const uint32_t slot = s % 3u, dst = sbase + SM_RING + slot * kStage, full = bar0 + 8 * slot;
-            if (s >= 3) mbar_wait(bar0 + 24 + 8 * slot, ((s / 3u) - 1u) & 1u, a.err, E_WEMPTY);
+            const uint32_t slot = s % kRing, dst = sbase + SM_RING + slot * kStage, full = bar0 + 8 * slot;
+            if (s >= kRing) mbar_wait(bar_e + 8 * slot, ((s / kRing) - 1u) & 1u, a.err, E_WEMPTY);
             mbar_expect_tx(full, kStage);
-            const int mrow = (int)(s % kMatsPerTile) * 128;
-            tma_load_2d(dst, &wmap, full, 0, mrow);
-            tma_load_2d(dst + 16384, &wmap, full, 64, mrow);
+            const int m = (int)(s % kMatsPerTile);
+            if (m == 0) {          // proj: K = 16 lives in k-block 0 of matrices 20 (hi) and 21 (lo)
+                tma_load_2d(dst, &wmap, full, 0, 20 * 128);
+                tma_load_2d(dst + 16384, &wmap, full, 0, 21 * 128);
+            } else {
+                tma_load_2d(dst, &wmap, full, 0, (m - 1) * 128);
+                tma_load_2d(dst + 16384, &wmap, full, 64, (m - 1) * 128);
+            }
         };
         auto take_stage = [&]() -> uint32_t {         // shared-memory address of the next weight stage, loads kept 2 ahead
-            while (ld < total && ld <= use + 2) load_stage(ld++);
-            mbar_wait(bar0 + 8 * (use % 3u), (use / 3u) & 1u, a.err, E_WFULL);
+            while (ld < total && ld < use + kRing) load_stage(ld++);
+            mbar_wait(bar0 + 8 * (use % kRing), (use / kRing) & 1u, a.err, E_WFULL);
             tc_fence_after();
-            return sbase + SM_RING + (use % 3u) * kStage;
+            return sbase + SM_RING + (use % kRing) * kStage;
         };
-        if (my_tiles > 0 && elect_one()) {
-            mbar_expect_tx(bar_wp, 32768u);
-            tma_load_2d(sbase + SM_WPROJ, &wmap, bar_wp, 0, 20 * 128);
-            tma_load_2d(sbase + SM_WPROJ + 16384, &wmap, bar_wp, 0, 21 * 128);
-            while (ld < total && ld < 2) load_stage(ld++);
-            mbar_wait(bar_wp, 0, a.err, E_WPROJ);
-        }
+        if (my_tiles > 0 && elect_one())
+            while (ld < total && ld < kRing) load_stage(ld++);
         __syncwarp();
         for (int t = 0; t < my_tiles; ++t) {
             // ---- proj: K = 16, one k-step, 3 terms ----
             hand_sync();
             if (elect_one()) {
                 tc_fence_after();
-                const uint64_t bh = umma_desc_sw128(sbase + SM_WPROJ), bl = umma_desc_sw128(sbase + SM_WPROJ + 16384);
+                const uint32_t sp = take_stage();
+                const uint64_t bh = umma_desc_sw128(sp), bl = umma_desc_sw128(sp + 16384);
                 umma_f16_ts(tmem + TM_D, tmem + TM_A, bh, id128, 0);
                 umma_f16_ts(tmem + TM_D, tmem + TM_A + 64, bh, id128, 1);
                 umma_f16_ts(tmem + TM_D, tmem + TM_A, bl, id128, 1);
+                umma_commit(bar_e + 8 * (use % kRing));
+                ++use;
                 umma_commit(bar_d);
             }
             __syncwarp();
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lane_net_tc(const __grid_consta
                             const uint32_t kw = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
                             umma_f16_ts(tmem + TM_D, ab + 64 + kk * 8, umma_desc_sw128(sh + kw), id128, 1);
                         }
-                        umma_commit(bar0 + 24 + 8 * (use % 3u));
+                        umma_commit(bar_e + 8 * (use % kRing));
                         ++use;
                         const uint32_t sl = take_stage();
 #pragma unroll
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lane_net_tc(const __grid_consta
                             const uint32_t kw = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
                             umma_f16_ts(tmem + TM_D, ab + kk * 8, umma_desc_sw128(sl + kw), id128, 1);
                         }
-                        umma_commit(bar0 + 24 + 8 * (use % 3u));
+                        umma_commit(bar_e + 8 * (use % kRing));
                         ++use;
                     }
                     umma_commit(bar_d);
@@ -172,8 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_lane_net_tc(const __grid_consta
         uint32_t rounds = 0, lns = 0;
         float v[32];
 
-        auto wait_d = [&]() {
-            mbar_wait(bar_d, rounds & 1u, a.err, E_DFULL);
+        auto wait_d = [&]() {           // one polling lane per warp: 512 threads spinning on the mbarrier compete with the MMAs' operand reads
+            if (lane == 0) mbar_wait(bar_d, rounds & 1u, a.err, E_DFULL);
+            __syncwarp();
             ++rounds;
             tc_fence_after();
         };

@@ -138,6 +138,8 @@ struct MindCtx {
     LaneW lane_tc[2][4];          // per aggregate block: fc1.0, fc1.3, fc2.0[:, :128], fc2.3 as [128][hi 128 | lo 128] fp16
     LaneTc lane_fused{};          // the whole LaneNet as one persistent tcgen05 kernel (lane_tc.cu)
     int lane_unfused = 0;         // diagnostics: layer-by-layer LaneNet on the GEMM engine instead
+    NodeChain node_chain{};       // per layer: out-proj + LN2 + FFN + LN3 + next layer's S|T|q as one kernel (node_tc.cu)
+    int node_unfused = 0;         // diagnostics: the same as 4 GEMM-engine launches + 2 LayerNorm launches
     int* lane_err = nullptr;
     struct NodeW { __half* W = nullptr; alignas(64) unsigned char wmap[128]; int N = 0, K = 0, n_tile = 128; };
     NodeW node_tc[6][4];          // per fusion layer: [S|T|q] (384x128), out-proj (128x128), linear1 (256x128), linear2 (128x256)
@@ -201,6 +203,7 @@ extern "C" void mind_destroy(MindCtx* c) {
     tc_free(c->tc);
     actor_tc_free(c->actor_tc);
     lane_tc_free(c->lane_fused);
+    node_chain_free(c->node_chain);
     for (auto& blk : c->lane_tc) for (auto& lw : blk) if (lw.W) cudaFree(lw.W);
     if (c->lane_err) cudaFree(c->lane_err);
     for (auto& lay : c->node_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
@@ -222,6 +225,9 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
         c->precision = (int)value;
     } else if (!strcmp(name, "actor_simt")) {
         c->actor_simt = value != 0;
+    } else if (!strcmp(name, "node_unfused")) {
+        if (c->node_unfused != (value != 0)) graph_cache_clear(c);
+        c->node_unfused = value != 0;
     } else if (!strcmp(name, "lane_unfused")) {
         if (c->lane_unfused != (value != 0)) graph_cache_clear(c);
         c->lane_unfused = value != 0;
@@ -491,6 +497,23 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
             if (l < 5 && (e3 = pack(c->pair_tc[l][1], *find(c, P + "proj_edge.0.weight"), 128, 128, 128))) return fail("pair pack: %s", e3);
             std::vector<float> Wkv(Win->begin() + 128 * 128, Win->end());
             if ((e3 = pack(c->pair_tc[l][2], Wkv, 256, 128, 256))) return fail("pair pack: %s", e3);
+        }
+        // token-side chain kernel: layer l's out-proj / FFN / norms + layer l+1's fused [S | T | q/4] projection
+        for (int l = 0; l < 6; ++l) {
+            char pfx[96];
+            snprintf(pfx, sizeof pfx, "fusion_net.fuse_scene.fusion.%d.", l);
+            const std::string P(pfx);
+            auto H = [&](const std::string& k) { return find(c, P + k)->data(); };
+            const float *Wn = nullptr, *bn = nullptr;
+            if (l < 5) {
+                snprintf(pfx, sizeof pfx, "fusion_net.fuse_scene.fusion.%d.", l + 1);
+                Wn = b.flat.data() + b.off.at(std::string(pfx) + "#Wstq");
+                bn = b.flat.data() + b.off.at(std::string(pfx) + "#bstq");
+            }
+            if (const char* e4 = node_chain_pack(c->node_chain, l, H("multihead_attn.out_proj.weight"), H("multihead_attn.out_proj.bias"),
+                                                 H("norm2.weight"), H("norm2.bias"), H("linear1.weight"), H("linear1.bias"), H("linear2.weight"),
+                                                 H("linear2.bias"), H("norm3.weight"), H("norm3.bias"), Wn, bn))
+                return fail("%s", e4);
         }
     }
     c->finalized = true;
@@ -1021,8 +1044,10 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
         CUDA_OK(cudaMemsetAsync(w.al, 0, sizeof(__half) * (size_t)TOKR * 128, st));
         PROF_NEXT("edge_init");
         for (int l = 0; l < 6; ++l) {
-            if (const char* e = run_node_pre_tc(c, l, w, TOKR, st)) return fail("node_pre_tc(%d): %s", l, e);
-            PROF_NEXT("node_pre");
+            if (l == 0 || c->node_unfused) {       // later layers: S | T | q come out of the previous layer's chain kernel
+                if (const char* e = run_node_pre_tc(c, l, w, TOKR, st)) return fail("node_pre_tc(%d): %s", l, e);
+                PROF_NEXT("node_pre");
+            }
             if (n_big > 0) {
                 const char* err = tc_fusion_layer(c->tc, l, w.stq, w.ah, w.al, c->sm_count, st);
                 if (err) return fail("tc_fusion_layer(%d): %s", l, err);
@@ -1044,7 +1069,12 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
                 launch_x3_attention(w.xkv, w.stq, c->d_sd, c->d_small, w.ah, w.al, n_small, Ns, Nmax, st);
                 PROF_NEXT("fusion_x3");
             }
-            if (const char* e = run_node_post_tc(c, l, w, TOKR, st)) return fail("node_post_tc(%d): %s", l, e);
+            if (c->node_unfused) {
+                if (const char* e = run_node_post_tc(c, l, w, TOKR, st)) return fail("node_post_tc(%d): %s", l, e);
+            } else {
+                if (const char* e = node_chain_run(c->node_chain, l, w.ah, w.al, w.x, l < 5 ? w.stq : nullptr, TOKR, c->sm_count, st))
+                    return fail("node_chain_run(%d): %s", l, e);
+            }
             PROF_NEXT("node_post");
         }
     }

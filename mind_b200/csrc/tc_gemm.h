@@ -73,4 +73,24 @@ void lane_tc_free(LaneTc& l);
 // lanes [Lp * 10, 16] fp32 node features -> out [Lp, 128]
 const char* lane_tc_run(LaneTc& l, const float* lanes, int Lp, float* out, int sm_count, cudaStream_t st);
 
+// ---- token-side tail of a rela-fusion layer + head of the next one as one persistent tcgen05 kernel (node_tc.cu) ----
+struct NodeChainLayer {
+    __half* W = nullptr;       // 10 or 16 matrices [128][128] fp16, (hi, lo) in the order the kernel streams them
+    float* params = nullptr;   // [11][128]
+    int n_mats = 0;
+    alignas(64) unsigned char wmap[128];
+};
+struct NodeChain {
+    NodeChainLayer layer[6];
+    int* d_err = nullptr;
+    bool ready = false;
+};
+const char* node_chain_pack(NodeChain& n, int l, const float* Wo, const float* bo, const float* n2g, const float* n2b, const float* W1,
+                            const float* b1, const float* W2, const float* b2, const float* n3g, const float* n3b,
+                            const float* Wstq_next, const float* bstq_next);
+void node_chain_free(NodeChain& n);
+// x [rows,128] <- LN3(x1 + FFN(x1)), x1 = LN2(x + out_proj(attn)); stq_next [rows,384] = next layer's S | T | q (or null)
+const char* node_chain_run(NodeChain& n, int l, const __half* ah, const __half* al, float* x, float* stq_next, int64_t rows,
+                           int sm_count, cudaStream_t st);
+
 }  // namespace mind

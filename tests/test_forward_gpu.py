@@ -290,3 +290,21 @@ def test_fused_lane_net_matches_the_layer_by_layer_path(ckpt_sd, dev, n_lane):
     torch.cuda.synchronize()
     assert rel_err(taps[0], want) < 2e-5 and rel_err(taps[1], want) < 2e-5
     assert rel_err(taps[0], taps[1]) < 1e-5
+
+
+def test_token_side_chain_kernel_matches_the_launch_by_launch_path(ckpt_sd, dev):
+    """k_node_chain_tc (out-proj + LN2 + FFN + LN3 + the next layer's S | T | q in one kernel per layer) vs the 4 GEMM +
+    2 LayerNorm launches it replaces: both are fp32-equivalent, so the final outputs agree far below the mode's tolerance;
+    ragged batch with both tiers of the pair pipeline present."""
+    from mind_b200 import synth
+    data = synth.batch_from_scenes([synth.scene_s1(950 + i, na, nl) for i, (na, nl) in enumerate([(5, 20), (32, 128), (17, 40), (1, 3)])])
+    outs = []
+    for unfused in (0, 1):
+        net = make_net(ckpt_sd, dev, "f16tc")
+        net.set_option("node_unfused", unfused)
+        p = net.forward_packed(to_dev(data, dev))
+        net.sync_check()
+        outs.append([t.clone() for t in p[:3]])
+    torch.cuda.synchronize()
+    for x, y in zip(*outs):
+        assert rel_err(x, y) < 2e-5
