@@ -235,18 +235,21 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                         }
                     }
                     umma_commit(bar_m2a);
+                    if (!a.has_edge && has_next) {                 // [B'] layer without edge update: next tile's T rows and G1 right here
+                        // (its D1 region is the other one, free since the previous tile's K|V products were issued; every epilogue
+                        // warp is past epilogue 1 of this tile, so the T buffer is free): epilogue 1 of the next tile then never
+                        // waits for G1, and it runs under this tile's K|V products
+                        load_T(nxt);
+                        mbar_wait(bar_ld0 + 8 * (buf ^ 1), ((g + 1) >> 1) & 1, a.err, E_LOAD_EDGE);
+                        tc_fence_after();
+                        issue_g1(buf ^ 1, ncol);
+                    }
                 }
                 TR(17, g);
                 handoff_sync(kBarK);                               // Dk/Dv of the previous tile have been consumed
                 TR(18, g);
                 if (elect_one()) {
                     tc_fence_after();
-                    if (!a.has_edge && has_next) {                 // [B'] next tile's T rows and G1 ahead of this tile's K|V products
-                        load_T(nxt);
-                        mbar_wait(bar_ld0 + 8 * (buf ^ 1), ((g + 1) >> 1) & 1, a.err, E_LOAD_EDGE);
-                        tc_fence_after();
-                        issue_g1(buf ^ 1, ncol);
-                    }
                     // K and V as two N=128 groups: with the A operand in TMEM an N=256 MMA measured ~170 cycles against
                     // ~60 for N=128 (timeline trace), so 32 narrow MMAs finish well before 16 wide ones
                     const uint32_t id128 = umma_idesc_f16(128);
