@@ -175,9 +175,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_lane_net_tc(const __grid_consta
         uint32_t rounds = 0, lns = 0;
         float v[32];
 
-        auto wait_d = [&]() {           // one polling lane per warp: 512 threads spinning on the mbarrier compete with the MMAs' operand reads
-            if (lane == 0) mbar_wait(bar_d, rounds & 1u, a.err, E_DFULL);
-            __syncwarp();
+        auto wait_d = [&]() {
+            mbar_wait(bar_d, rounds & 1u, a.err, E_DFULL);
             ++rounds;
             tc_fence_after();
         };

@@ -25,7 +25,7 @@ constexpr uint32_t SM_X = kRing * kStage;                    // fp32 [128 rows][
 constexpr uint32_t SM_P = SM_X + 65536;                  // float [11][128]: bo n2g n2b | b1 (2) | b2 n3g n3b | bstq (3)
 constexpr uint32_t SM_STAT = SM_P + 11 * 512;            // float2 [2][4][128]
 constexpr uint32_t SM_BAR = SM_STAT + 8192;              // w_full[kRing] w_empty[kRing] d_full
-constexpr uint32_t SM_TMEM = SM_BAR + 16 * kRing + 16;
+constexpr uint32_t SM_TMEM = SM_BAR + 16 * kRing + 32;     // + d_full, d_stq[2]
 constexpr uint32_t SMEM_BYTES = SM_TMEM + 16 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 constexpr int kBarHand = 6;
@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_node_chain_tc(const __grid_cons
     float* sP = reinterpret_cast<float*>(sgen + SM_P);
     float2* sStat = reinterpret_cast<float2*>(sgen + SM_STAT);
     volatile uint32_t* sTmem = reinterpret_cast<volatile uint32_t*>(sgen + SM_TMEM);
-    const uint32_t bar0 = sbase + SM_BAR, bar_e = bar0 + 8 * kRing, bar_d = bar0 + 16 * kRing;      // w_full[s] = bar0 + 8 s, w_empty[s] = bar_e + 8 s
+    const uint32_t bar0 = sbase + SM_BAR, bar_e = bar0 + 8 * kRing, bar_d = bar0 + 16 * kRing, bar_s1 = bar_d + 8, bar_s2 = bar_d + 16;      // w_full[s] = bar0 + 8 s, w_empty[s] = bar_e + 8 s
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kRing; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_e + 8 * s, 1); }
-        mbar_init(bar_d, 1);
+        mbar_init(bar_d, 1); mbar_init(bar_s1, 1); mbar_init(bar_s2, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -96,13 +96,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_node_chain_tc(const __grid_cons
         };
         auto release_stage = [&]() { umma_commit(bar_e + 8 * (use % kRing)); ++use; };
         // 8 k-steps of one 128-wide K block: D (+)= A[acol + 8 kk] . W_stage
-        auto mma_k128 = [&](uint32_t acol, uint32_t stage, bool first) {
+        auto mma_k128d = [&](uint32_t dcol, uint32_t acol, uint32_t stage, bool first) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const uint32_t kw = (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
-                umma_f16_ts(tmem + TM_D, tmem + acol + kk * 8, umma_desc_sw128(stage + kw), id128, (first && kk == 0) ? 0u : 1u);
+                umma_f16_ts(tmem + dcol, tmem + acol + kk * 8, umma_desc_sw128(stage + kw), id128, (first && kk == 0) ? 0u : 1u);
             }
         };
+        auto mma_k128 = [&](uint32_t acol, uint32_t stage, bool first) { mma_k128d(TM_D, acol, stage, first); };
         // 3-term product of the 128-wide operand at TM_A with the next (hi, lo) stage pair
         auto round_k128 = [&]() {
             const uint32_t sh = take_stage();
@@ -144,11 +145,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_node_chain_tc(const __grid_cons
             }
             __syncwarp();
             if (with_stq) {
-                for (int r = 0; r < 3; ++r) {      // S, T, q blocks of the next layer
-                    hand_sync();
-                    if (elect_one()) { tc_fence_after(); round_k128(); }
-                    __syncwarp();
+                // S, T, q blocks of the next layer: one hand-off, three accumulators (the FFN operand columns are free once
+                // linear2 has completed), so the epilogue's global stores of one block run under the MMAs of the next
+                hand_sync();
+                if (elect_one()) {
+                    tc_fence_after();
+                    for (int blk = 0; blk < 3; ++blk) {
+                        const uint32_t dcol = blk == 0 ? TM_D : (blk == 1 ? TM_H : TM_H + 128);
+                        const uint32_t sh = take_stage();
+                        mma_k128d(dcol, TM_A, sh, true);
+                        mma_k128d(dcol, TM_A + 64, sh, false);
+                        release_stage();
+                        const uint32_t sl = take_stage();
+                        mma_k128d(dcol, TM_A, sl, false);
+                        release_stage();
+                        umma_commit(blk == 0 ? bar_d : (blk == 1 ? bar_s1 : bar_s2));
+                    }
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -162,15 +176,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_node_chain_tc(const __grid_cons
         uint32_t rounds = 0, lns = 0;
         float v[32];
 
-        auto wait_d = [&]() {           // one polling lane per warp: 512 threads spinning on the mbarrier compete with the MMAs' operand reads
-            if (lane == 0) mbar_wait(bar_d, rounds & 1u, a.err, E_DFULL);
-            __syncwarp();
+        auto wait_d = [&]() {
+            mbar_wait(bar_d, rounds & 1u, a.err, E_DFULL);
             ++rounds;
             tc_fence_after();
         };
-        auto load_d = [&](int pb) {
+        auto load_dc = [&](uint32_t dcol, int pb) {
             uint32_t r[32];
-            TMEM_LD_X32(tmem + lane_base + TM_D + col0, r);
+            TMEM_LD_X32(tmem + lane_base + dcol + col0, r);
             tmem_wait_ld();
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
@@ -179,6 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_node_chain_tc(const __grid_cons
                 v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + b.z; v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + b.w;
             }
         };
+        auto load_d = [&](int pb) { load_dc(TM_D, pb); };
+        uint32_t stq_tiles = 0;
         auto ln = [&](int pg, int pbeta) {
             float s = 0.f;
 #pragma unroll
@@ -292,16 +307,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_node_chain_tc(const __grid_cons
                 tc_fence_before();
                 hand_arrive();
                 for (int blk = 0; blk < 3; ++blk) {          // S | T(+b_mem) | q/4 of the next layer
-                    wait_d();
-                    load_d(P_BS + blk);
+                    if (blk == 0) {
+                        wait_d();
+                    } else {
+                        mbar_wait(blk == 1 ? bar_s1 : bar_s2, stq_tiles & 1u, a.err, E_DFULL);
+                        tc_fence_after();
+                    }
+                    load_dc(blk == 0 ? TM_D : (blk == 1 ? TM_H : TM_H + 128), P_BS + blk);
                     if (valid) {
 #pragma unroll
                         for (int k4 = 0; k4 < 8; ++k4)
                             *reinterpret_cast<float4*>(a.stq + grow * 384 + blk * 128 + col0 + k4 * 4) =
                                 make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
                     }
-                    if (blk < 2) { tc_fence_before(); hand_arrive(); }
                 }
+                ++stq_tiles;
             }
             tc_fence_before();
         }
