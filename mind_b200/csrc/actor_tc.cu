@@ -23,7 +23,7 @@ struct HL { __half* hi; __half* lo; };
 struct Bufs {
     HL x0, t0, t1, o[4], p;              // padded channel-last activations
     __half* slack[20]; int n_slack;      // tails that overlapping windows may read (kept finite: zeroed)
-    float *raw1, *raw2, *raw3, *st1, *st2, *st3, *pyr0, *pyr1, *lat, *outf;
+    float *raw1, *raw2, *raw3, *st1, *st2, *st3, *pyr0, *pyr1;
 };
 int64_t carve(void* ws, int A, Bufs& b) {
     Carve c{(char*)ws};
@@ -41,18 +41,11 @@ int64_t carve(void* ws, int A, Bufs& b) {
     b.p = hl(50 * 128);
     b.raw1 = c.take<float>((int64_t)A * 6144); b.raw2 = c.take<float>((int64_t)A * 6144); b.raw3 = c.take<float>((int64_t)A * 6144);
     b.st1 = c.take<float>((int64_t)A * 12); b.st2 = c.take<float>((int64_t)A * 12); b.st3 = c.take<float>((int64_t)A * 12);
-    b.pyr0 = c.take<float>((int64_t)A * 6144); b.pyr1 = c.take<float>((int64_t)A * 6144);
-    b.lat = c.take<float>((int64_t)A * 6144); b.outf = c.take<float>((int64_t)A * 6144);
+    b.pyr0 = c.take<float>((int64_t)A * 3072); b.pyr1 = c.take<float>((int64_t)A * 3072);   // FPN levels L = 6 / 24 and L = 12
     return (c.off + 255) & ~int64_t(255);
 }
 char g_aerr[256];
 
-__global__ void k_last_step(const float* __restrict__ x, float* __restrict__ out, int A, int L, int C) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)A * C) return;
-    const int a = (int)(idx / C), c = (int)(idx % C);
-    out[idx] = x[((int64_t)a * L + (L - 1)) * C + c];
-}
 }  // namespace
 
 int64_t actor_tc_ws_bytes(int A) { Bufs b; return carve(nullptr, std::max(A, 1), b); }
@@ -127,7 +120,7 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         return it->second;
     };
     // conv over a padded channel-last input [A][Lin+2][Cin_pad]: output raw [A*Lout][Cout] + stats
-    auto conv = [&](const std::string& key, HL in, int Lin, int stride, float* raw, float* stats) {
+    auto conv = [&](const std::string& key, HL in, int Lin, int stride, float* raw, float* stats, int last_only = 0) {
         if (err) return;
         auto it = a.conv.find(key);
         if (it == a.conv.end()) { err = "actor_tc_run: unknown conv"; return; }
@@ -144,14 +137,15 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         TcGemm g;
         g.amap_hi = mh; g.amap_lo = ml; g.wmap = cv.wmap; g.split = 1; g.k_blocks = cv.Kpad / 64;
         g.r_in = r_in; g.r_out = r_out; g.L_inner = Lout; g.n_outer = A;
-        g.N = cv.Cout; g.n_tile = cv.Cout; g.C = raw; g.ldc = cv.Cout; g.stats = stats; g.err = a.d_err;
+        g.N = cv.Cout; g.n_tile = cv.Cout; g.C = raw; g.ldc = cv.Cout; g.c_last_only = last_only; g.stats = stats; g.err = a.d_err;
         err = tcg_launch(g, sm_count, st);
     };
     auto apply = [&](const float* raw, const float* stats, const std::string& gk, int L, int C, int relu, HL out_hl, float* out_f32,
                      const float* res_raw = nullptr, const float* res_stats = nullptr, const std::string& rk = "",
-                     const HL* res_hl = nullptr) {
+                     const HL* res_hl = nullptr, const float* up_prev = nullptr, int last_only = 0) {
         if (err) return;
         TcApply q;
+        q.up_prev = up_prev; q.last_only = last_only;
         q.raw = raw; q.stats = stats; q.gamma = V(gk + ".weight"); q.beta = V(gk + ".bias");
         if (res_raw) { q.res_raw = res_raw; q.res_stats = res_stats; q.res_gamma = V(rk + ".weight"); q.res_beta = V(rk + ".bias"); }
         if (res_hl) { q.res_hi = res_hl->hi; q.res_lo = res_hl->lo; }
@@ -190,24 +184,21 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
     conv("actor_net.lateral.3.conv.weight", b.o[3], 6, 1, b.raw1, b.st1);
     apply(b.raw1, b.st1, "actor_net.lateral.3.norm", 6, 128, 0, none, b.pyr0);
     float* pyr = b.pyr0; float* nxt = b.pyr1;
-    for (int i = 2; i >= 0 && !err; --i) {
+    for (int i = 2; i >= 0 && !err; --i) {      // lateral GroupNorm and the top-down step (:57-58) in one pass over the conv output
         char p[64];
         snprintf(p, sizeof p, "actor_net.lateral.%d", i);
         conv(std::string(p) + ".conv.weight", b.o[i], Ls[i], 1, b.raw1, b.st1);
-        apply(b.raw1, b.st1, std::string(p) + ".norm", Ls[i], 128, 0, none, b.lat);
-        if (!err) tcg_fpn_up_add(pyr, b.lat, nxt, i == 0 ? b.p.hi : nullptr, i == 0 ? b.p.lo : nullptr, A, Ls[i], 128, st);
+        // the finest level is only read as the (hi, lo) input / shortcut of the output block
+        apply(b.raw1, b.st1, std::string(p) + ".norm", Ls[i], 128, 0, i == 0 ? b.p : none, i == 0 ? nullptr : nxt,
+              nullptr, nullptr, "", nullptr, pyr);
         float* t = pyr; pyr = nxt; nxt = t;
     }
-    // output Res1d(128,128), identity shortcut = the pyramid top; keep the last time step only
+    // output Res1d(128,128), identity shortcut = the pyramid top.  Only its last time step leaves ActorNet (:60), but both
+    // GroupNorms take their statistics over all 48: conv2 runs in full, stores row 47 only, and is normalised there
     conv("actor_net.output.conv1.weight", b.p, 48, 1, b.raw1, b.st1);
     apply(b.raw1, b.st1, "actor_net.output.bn1", 48, 128, 1, b.t0, nullptr);
-    conv("actor_net.output.conv2.weight", b.t0, 48, 1, b.raw2, b.st2);
-    apply(b.raw2, b.st2, "actor_net.output.bn2", 48, 128, 1, none, b.outf, nullptr, nullptr, "", &b.p);
-    if (!err) {
-        const int64_t n = (int64_t)A * 128;
-        k_last_step<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.outf, out, A, 48, 128);
-        ++g_launches;
-    }
+    conv("actor_net.output.conv2.weight", b.t0, 48, 1, b.raw2, b.st2, 1);
+    apply(b.raw2, b.st2, "actor_net.output.bn2", 48, 128, 1, none, out, nullptr, nullptr, "", &b.p, nullptr, 1);
     return err;
 }
 

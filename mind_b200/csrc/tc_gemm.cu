@@ -112,7 +112,7 @@ struct Args {
     int r_in, r_out;
     int L_inner, n_outer;
     int N, n_tile;
-    float* C; int ldc;
+    float* C; int ldc; int c_last;
     __half* Chi; __half* Clo; int ldh;      // optional fp16 (hi, lo) copy of the output (operand of a following GEMM)
     const float* bias; int relu;
     const float* gbias; int gsize, ldg;     // per row-group bias [(row / gsize), N]
@@ -309,8 +309,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                     const int trow = lg * 32 + rr;
                     const int outer_r = o * g.r_out + (trow >> g.r_in_shift), inner_r = c * g.r_in + (trow & (g.r_in - 1));
                     if (outer_r >= g.n_outer || inner_r >= g.L_inner) continue;
+                    if (g.c_last && inner_r != g.L_inner - 1) continue;          // only the last inner row is kept (statistics over all)
                     const float4 x = *reinterpret_cast<const float4*>(stg + rr * STG_STRIDE + c4 * 4);
-                    const int64_t orow_r = (int64_t)outer_r * g.L_inner + inner_r;
+                    const int64_t orow_r = g.c_last ? (int64_t)outer_r : (int64_t)outer_r * g.L_inner + inner_r;
                     const int n = nb + c4 * 4;
                     if (g.C) {
                         float* cr = g.C + orow_r * g.ldc;
@@ -386,6 +387,8 @@ struct ApplyArgs {
     const float* res_raw; const float* res_stats; const float* res_gamma; const float* res_beta;
     const __half* res_hi; const __half* res_lo;     // identity shortcut, padded [A][L+2][C]
     __half* out_hi; __half* out_lo; float* out_f32;
+    const float* up_prev;   // + linear x2 upsampling of [A][L/2][C] (FPN top-down step, network.py:57-58)
+    int last_only;          // raw / out_f32 hold time step L-1 only
     int A, L, C, relu;
     int c_shift;            // log2(C) when C is a power of two, else -1
 };
@@ -407,10 +410,12 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
             const float v2 = fmaxf((((r[1] + r[3]) + (r[5] + r[7])) + (r[9] + r[11])) / fn - m2 * m2, 0.f);
             rstd2 = rsqrtf(v2 + 1e-5f);
         }
-        for (int i4 = lane; i4 < n4; i4 += 32) {      // C % 4 == 0: 4 channels per iteration
+        const int first4 = p.last_only ? ((p.L - 1) * p.C) >> 2 : 0;
+        const int64_t rbase = p.last_only ? (int64_t)a * p.C - (int64_t)(p.L - 1) * p.C : (int64_t)a * n;   // raw / out_f32 row base
+        for (int i4 = first4 + lane; i4 < n4; i4 += 32) {      // C % 4 == 0: 4 channels per iteration
             const int i = i4 << 2;
             const int t = p.c_shift >= 0 ? (i >> p.c_shift) : i / p.C, c = i - t * p.C;
-            const float4 x = *reinterpret_cast<const float4*>(p.raw + (int64_t)a * n + i);
+            const float4 x = *reinterpret_cast<const float4*>(p.raw + rbase + i);
             const float4 gm = *reinterpret_cast<const float4*>(p.gamma + c), bt = *reinterpret_cast<const float4*>(p.beta + c);
             float y[4] = {(x.x - mean) * rstd * gm.x + bt.x, (x.y - mean) * rstd * gm.y + bt.y,
                           (x.z - mean) * rstd * gm.z + bt.z, (x.w - mean) * rstd * gm.w + bt.w};
@@ -426,6 +431,16 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
                 const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
                 y[0] += h0.x + l0.x; y[1] += h0.y + l0.y; y[2] += h1.x + l1.x; y[3] += h1.y + l1.y;
             }
+            if (p.up_prev) {      // out = lerp_x2(prev) + lateral, same expression as the reference's interpolate(align_corners=False)
+                const int Lp = p.L >> 1;
+                const float src = fmaxf(((float)t + 0.5f) * 0.5f - 0.5f, 0.f);
+                const int i0 = (int)floorf(src), i1 = min(i0 + 1, Lp - 1);
+                const float lam = src - (float)i0;
+                const float* pp = p.up_prev + (int64_t)a * Lp * p.C;
+                const float4 p0 = *reinterpret_cast<const float4*>(pp + i0 * p.C + c), p1 = *reinterpret_cast<const float4*>(pp + i1 * p.C + c);
+                y[0] = p0.x * (1.f - lam) + p1.x * lam + y[0]; y[1] = p0.y * (1.f - lam) + p1.y * lam + y[1];
+                y[2] = p0.z * (1.f - lam) + p1.z * lam + y[2]; y[3] = p0.w * (1.f - lam) + p1.w * lam + y[3];
+            }
             if (p.relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
             if (p.out_hi) {
                 const __half2 a01 = __floats2half2_rn(y[0], y[1]), a23 = __floats2half2_rn(y[2], y[3]);
@@ -437,7 +452,7 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
                 *reinterpret_cast<uint2*>(p.out_hi + pidx) = uh;
                 *reinterpret_cast<uint2*>(p.out_lo + pidx) = ul;
             }
-            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)a * n + i) = make_float4(y[0], y[1], y[2], y[3]);
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + rbase + i) = make_float4(y[0], y[1], y[2], y[3]);
         }
         if (p.out_hi) {   // zero pad rows t = 0 and t = L+1
             for (int c = lane; c < 2 * p.C; c += 32) {
@@ -455,45 +470,6 @@ __global__ void __launch_bounds__(256) k_gn_apply(ApplyArgs p) {
                 }
             }
         }
-    }
-}
-
-// FPN top-down step (network.py:57-58): out[a,t,c] = lerp_x2(prev)[a,t,c] + lat[a,t,c]; channel-last fp32,
-// optionally also emitted as padded hi/lo (input of the output Res1d) ; last_only extracts t = L-1
-__global__ void __launch_bounds__(256) k_fpn_up_add(const float* __restrict__ prev, const float* __restrict__ lat,
-                                                    float* __restrict__ out, __half* hi, __half* lo, int A, int L, int C) {
-    // 4 channels per thread (C % 4 == 0)
-    const int64_t idx4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int C4 = C >> 2;
-    if (idx4 >= (int64_t)A * L * C4) return;
-    const int c = (int)(idx4 % C4) * 4;
-    const int t = (int)((idx4 / C4) % L);
-    const int a = (int)(idx4 / ((int64_t)C4 * L));
-    const int Lp = L >> 1;
-    float src = fmaxf(((float)t + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int i0 = (int)floorf(src);
-    const int i1 = min(i0 + 1, Lp - 1);
-    const float lam = src - (float)i0;
-    const float* pp = prev + (int64_t)a * Lp * C;
-    const float4 p0 = *reinterpret_cast<const float4*>(pp + i0 * C + c), p1 = *reinterpret_cast<const float4*>(pp + i1 * C + c);
-    const int64_t idx = ((int64_t)a * L + t) * C + c;
-    const float4 lt = *reinterpret_cast<const float4*>(lat + idx);
-    float y[4] = {p0.x * (1.f - lam) + p1.x * lam + lt.x, p0.y * (1.f - lam) + p1.y * lam + lt.y,
-                  p0.z * (1.f - lam) + p1.z * lam + lt.z, p0.w * (1.f - lam) + p1.w * lam + lt.w};
-    *reinterpret_cast<float4*>(out + idx) = make_float4(y[0], y[1], y[2], y[3]);
-    if (hi) {
-        const int64_t pidx = ((int64_t)a * (L + 2) + t + 1) * C + c;
-        const __half2 a01 = __floats2half2_rn(y[0], y[1]), a23 = __floats2half2_rn(y[2], y[3]);
-        const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
-        const __half2 b01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), b23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
-        uint2 uh, ul;
-        uh.x = *reinterpret_cast<const uint32_t*>(&a01); uh.y = *reinterpret_cast<const uint32_t*>(&a23);
-        ul.x = *reinterpret_cast<const uint32_t*>(&b01); ul.y = *reinterpret_cast<const uint32_t*>(&b23);
-        *reinterpret_cast<uint2*>(hi + pidx) = uh;
-        *reinterpret_cast<uint2*>(lo + pidx) = ul;
-        const uint2 z = make_uint2(0u, 0u);
-        if (t == 0) { const int64_t zi = ((int64_t)a * (L + 2)) * C + c; *reinterpret_cast<uint2*>(hi + zi) = z; *reinterpret_cast<uint2*>(lo + zi) = z; }
-        if (t == L - 1) { const int64_t zi = ((int64_t)a * (L + 2) + L + 1) * C + c; *reinterpret_cast<uint2*>(hi + zi) = z; *reinterpret_cast<uint2*>(lo + zi) = z; }
     }
 }
 
@@ -569,7 +545,7 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.tiles_inner = (p.L_inner + p.r_in - 1) / p.r_in;
     g.tiles_outer = (p.n_outer + p.r_out - 1) / p.r_out;
     g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
-    g.C = p.C; g.ldc = p.ldc; g.Chi = p.Chi; g.Clo = p.Clo; g.ldh = p.ldh; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
+    g.C = p.C; g.ldc = p.ldc; g.c_last = p.c_last_only; g.Chi = p.Chi; g.Clo = p.Clo; g.ldh = p.ldh; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
     g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
     const int nkb_w = (p.split ? 2 : 1) * p.k_blocks;
     g.res_w_bytes = (uint32_t)nkb_w * (uint32_t)p.n_tile * 128u;
@@ -601,6 +577,7 @@ void tcg_gn_apply(const TcApply& q, cudaStream_t st) {
     p.raw = q.raw; p.stats = q.stats; p.gamma = q.gamma; p.beta = q.beta;
     p.res_raw = q.res_raw; p.res_stats = q.res_stats; p.res_gamma = q.res_gamma; p.res_beta = q.res_beta;
     p.res_hi = q.res_hi; p.res_lo = q.res_lo; p.out_hi = q.out_hi; p.out_lo = q.out_lo; p.out_f32 = q.out_f32;
+    p.up_prev = q.up_prev; p.last_only = q.last_only;
     p.A = q.A; p.L = q.L; p.C = q.C; p.relu = q.relu;
     p.c_shift = -1;
     for (int sft = 0; sft < 12; ++sft) if ((1 << sft) == q.C) p.c_shift = sft;
@@ -608,11 +585,4 @@ void tcg_gn_apply(const TcApply& q, cudaStream_t st) {
     tcg::k_gn_apply<<<(unsigned)std::min((q.A + 7) / 8, 148 * 8), 256, 0, st>>>(p);
     ++g_launches;
 }
-void tcg_fpn_up_add(const float* prev, const float* lat, float* out, __half* hi, __half* lo, int A, int L, int C, cudaStream_t st) {
-    const int64_t n = (int64_t)A * L * (C / 4);
-    if (n <= 0) return;
-    tcg::k_fpn_up_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prev, lat, out, hi, lo, A, L, C);
-    ++g_launches;
-}
-
 }  // namespace mind

@@ -17,6 +17,7 @@ struct TcGemm {
     int L_inner = 0, n_outer = 1;    // logical extents; output row = outer * L_inner + inner
     int N = 0, n_tile = 128;
     float* C = nullptr; int ldc = 0;
+    int c_last_only = 0;             // store only the row inner = L_inner - 1 of every outer group: C is [n_outer][N]
     __half* Chi = nullptr; __half* Clo = nullptr; int ldh = 0;   // optional fp16 (hi, lo) copy of the output
     const float* bias = nullptr; int relu = 0;
     const float* gbias = nullptr; int gsize = 1, ldg = 0;   // per row-group bias [(row / gsize), N]
@@ -34,11 +35,12 @@ struct TcApply {
     const float* res_raw = nullptr; const float* res_stats = nullptr; const float* res_gamma = nullptr; const float* res_beta = nullptr;
     const __half* res_hi = nullptr; const __half* res_lo = nullptr;
     __half* out_hi = nullptr; __half* out_lo = nullptr; float* out_f32 = nullptr;
+    const float* up_prev = nullptr;  // FPN top-down step: + linear x2 upsampling of the coarser level [A][L/2][C] (fp32)
+    int last_only = 0;               // raw is [A][C] = time step L-1 only (statistics still over L*C); out_f32 is [A][C]
     int A = 0, L = 0, C = 0, relu = 0;
 };
 void tcg_actor_prep(const float* actors, __half* hi, __half* lo, int A, cudaStream_t st);
 void tcg_gn_apply(const TcApply& q, cudaStream_t st);
-void tcg_fpn_up_add(const float* prev, const float* lat, float* out, __half* hi, __half* lo, int A, int L, int C, cudaStream_t st);
 
 // ---- ActorNet (reference network.py:12-61) on the GEMM engine --------------------------------
 struct ActorTcConv {
