@@ -409,6 +409,11 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 // (free until G2 of this tile is issued) so nothing has to live in registers across the barrier
                 const uint32_t scr_t = tmem + lane_base + 128 + col0;
                 const uint32_t d1c = (!a.has_edge && (g & 1)) ? 128u : 0u;      // D1 / A operand region of this tile (see the issuer)
+                // the two statistics buffers swap roles from tile to tile (this tile: epilogue 1 and pass B -> sx, pass A -> sy).
+                // Every re-use of a buffer is then already ordered by one of the three row-group barriers of the tile body:
+                // sy of this tile was last read in pass B of the previous tile (before its third barrier), sx in its pass C
+                // (before this tile's first barrier), so no barrier is needed at the end of a tile.
+                const int sx = (int)(g & 1), sy = sx ^ 1;
                 // A/B build for the next round: x stays in 32 registers across the row-group barrier instead of a round trip
                 // through the TMEM scratch cells (2 tcgen05.st + wait::st + 2 tcgen05.ld per thread-tile).  Not yet run on hardware.
                 uint32_t xr[32];
@@ -444,7 +449,7 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
 #pragma unroll
                         for (int e = 0; e < 16; ++e) xr[hf * 16 + e] = r[e];
                     }
-                    sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
+                    sStat[(sx * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                 };
                 if (mode) e1_pass1(std::true_type{});
                 else e1_pass1(std::false_type{});
@@ -454,8 +459,8 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 TR(3, g);
                 tc_fence_after();
                 {
-                    const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
-                    const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
+                    const float2 p0 = sStat[(sx * 4 + 0) * 128 + row], p1 = sStat[(sx * 4 + 1) * 128 + row];
+                    const float2 p2 = sStat[(sx * 4 + 2) * 128 + row], p3 = sStat[(sx * 4 + 3) * 128 + row];
                     const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                     const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                     const float rstd = rsqrtf(var + kEps);
@@ -526,14 +531,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                 s2a = fma2(x0, x0, s2a); s2b = fma2(x1, x1, s2b);
                             }
                         }
-                        sStat[(1 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
+                        sStat[(sy * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                     }
                     TR(8, g);
                     row_group_sync(lg);
                     TR(9, g);
                     {   // pass B: x = edge + ReLU(LN_p(Dpe + b)) written back to the same cells, statistics of x
-                        const float2 p0 = sStat[(1 * 4 + 0) * 128 + row], p1 = sStat[(1 * 4 + 1) * 128 + row];
-                        const float2 p2 = sStat[(1 * 4 + 2) * 128 + row], p3 = sStat[(1 * 4 + 3) * 128 + row];
+                        const float2 p0 = sStat[(sy * 4 + 0) * 128 + row], p1 = sStat[(sy * 4 + 1) * 128 + row];
+                        const float2 p2 = sStat[(sy * 4 + 2) * 128 + row], p3 = sStat[(sy * 4 + 3) * 128 + row];
                         const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
@@ -566,14 +571,14 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                                 }
                             }
                         }
-                        sStat[(0 * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
+                        sStat[(sx * 4 + q) * 128 + row] = make_float2(hsum2(add2(s1a, s1b)), hsum2(add2(s2a, s2b)));
                     }
                     TR(10, g);
                     row_group_sync(lg);
                     TR(11, g);
                     {   // pass C: edge' = LN_e(x) -> fp16, in place in the smem tile
-                        const float2 p0 = sStat[(0 * 4 + 0) * 128 + row], p1 = sStat[(0 * 4 + 1) * 128 + row];
-                        const float2 p2 = sStat[(0 * 4 + 2) * 128 + row], p3 = sStat[(0 * 4 + 3) * 128 + row];
+                        const float2 p0 = sStat[(sx * 4 + 0) * 128 + row], p1 = sStat[(sx * 4 + 1) * 128 + row];
+                        const float2 p2 = sStat[(sx * 4 + 2) * 128 + row], p3 = sStat[(sx * 4 + 3) * 128 + row];
                         const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 128.f);
                         const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 128.f) - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + kEps);
@@ -607,7 +612,6 @@ k_rela_fusion_tc(const __grid_constant__ CUtensorMap emap, const __grid_constant
                 tc_fence_before();
                 TR(12, g);
                 handoff_arrive(kBarE);                             // tile done: edge' in smem, all TMEM reads retired
-                row_group_sync(lg);                                // statistics buffers can be reused by the next tile
             }
 
             attend((g - 1) & 1, ((ch1 - 1) * kstep + i_l) < N);        // attention epilogue of the work item's last tile

@@ -12,6 +12,7 @@ memory, streams and host<->device copies only.  No CPU fallback: a non-CUDA devi
 """
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -128,7 +129,9 @@ class ScenePredNetB200:
         self._ws = None
         self._out_cache = {}
         self.training = False
-        self.precision = _lib.PREC_FP32
+        # what the string import gives MIND is the benchmarked tensor-core mode (two tiers, parity <= 1e-3: DESIGN.md 2);
+        # net_cfg["precision"] = "fp32" or MIND_B200_PRECISION=fp32 selects the exact SIMT path
+        self.set_precision((cfg or {}).get("precision") or os.environ.get("MIND_B200_PRECISION", "f16tc"))
         self.rpe_on_device = True       # pre_process uploads anchors instead of dense RPE when the dict has them
         self._geom_pin = {}
 
