@@ -60,28 +60,38 @@ void actor_tc_free(ActorTc& a) {
 const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<float>>& host,
                           const std::map<std::string, const float*>& dev) {
     actor_tc_free(a);
-    auto add = [&](const std::string& key, int Cout, int Cin, int Cin_pad, int ks) -> const char* {
+    // Narrow layers (C = 32) fold `fold` consecutive output steps into one GEMM row: the row's window is (fold-1)*stride + ks
+    // taps of the padded input, its N = fold*Cout columns are the outputs of step fold*p + u at [u*Cout, (u+1)*Cout) -- the
+    // same memory as [step][Cout] -- and the weight of (u, o) sits at taps u*stride + k (zero elsewhere).  Same kernel, but
+    // 128-row tiles of N = 64 / 128 instead of 32: half / a quarter of the tiles and of the operand traffic per output.
+    auto add = [&](const std::string& key, int Cout, int Cin, int Cin_pad, int ks, int stride, int fold) -> const char* {
         auto it = host.find(key);
         if (it == host.end() || it->second.size() != (size_t)Cout * Cin * ks) return "actor_tc_pack: missing / mis-sized conv weight";
         ActorTcConv cv;
-        cv.Cout = Cout; cv.Cin_pad = Cin_pad; cv.ksize = ks;
-        cv.Kpad = ((ks * Cin_pad + 63) / 64) * 64;
-        std::vector<__half> W((size_t)Cout * 2 * cv.Kpad, __float2half(0.f));
-        for (int o = 0; o < Cout; ++o)
-            for (int i = 0; i < Cin; ++i)
-                for (int k = 0; k < ks; ++k) {
-                    const float w = it->second[((size_t)o * Cin + i) * ks + k];
-                    const __half h = __float2half_rn(w);
-                    const size_t kk = (size_t)k * Cin_pad + i;
-                    W[(size_t)o * 2 * cv.Kpad + kk] = h;
-                    W[(size_t)o * 2 * cv.Kpad + cv.Kpad + kk] = __float2half_rn(w - __half2float(h));
-                }
+        cv.Cout = Cout; cv.Cin_pad = Cin_pad; cv.ksize = ks; cv.stride = stride; cv.fold = fold;
+        const int taps = (fold - 1) * stride + ks;
+        cv.Kpad = ((taps * Cin_pad + 63) / 64) * 64;
+        const int N = fold * Cout;
+        std::vector<__half> W((size_t)N * 2 * cv.Kpad, __float2half(0.f));
+        for (int u = 0; u < fold; ++u)
+            for (int o = 0; o < Cout; ++o)
+                for (int i = 0; i < Cin; ++i)
+                    for (int k = 0; k < ks; ++k) {
+                        const float w = it->second[((size_t)o * Cin + i) * ks + k];
+                        const __half h = __float2half_rn(w);
+                        const size_t kk = (size_t)(u * stride + k) * Cin_pad + i, n = (size_t)u * Cout + o;
+                        W[n * 2 * cv.Kpad + kk] = h;
+                        W[n * 2 * cv.Kpad + cv.Kpad + kk] = __float2half_rn(w - __half2float(h));
+                    }
         if (cudaMalloc(&cv.W, W.size() * sizeof(__half)) != cudaSuccess) return "actor_tc_pack: cudaMalloc failed";
         cudaMemcpy(cv.W, W.data(), W.size() * sizeof(__half), cudaMemcpyHostToDevice);
-        if (const char* e = tcg_encode_w(cv.wmap, cv.W, 2 * cv.Kpad, Cout, Cout)) return e;
+        if (const char* e = tcg_encode_w(cv.wmap, cv.W, 2 * cv.Kpad, N, N)) return e;
         a.conv[key] = cv;
         return nullptr;
     };
+    int fold0 = 2;
+    if (const char* ev = getenv("MIND_ACTOR_FOLD")) fold0 = atoi(ev);
+    if (fold0 != 1 && fold0 != 2 && fold0 != 4) return "actor_tc_pack: MIND_ACTOR_FOLD must be 1, 2 or 4";
     const int Cg[4] = {32, 64, 128, 256};
     int cin = 14, cinp = 16;
     for (int g = 0; g < 4; ++g) {
@@ -89,17 +99,18 @@ const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<fl
         snprintf(p, sizeof p, "actor_net.groups.%d.", g);
         std::string P(p);
         const char* e;
-        if ((e = add(P + "0.conv1.weight", Cg[g], cin, cinp, 3))) return e;
-        if ((e = add(P + "0.conv2.weight", Cg[g], Cg[g], Cg[g], 3))) return e;
-        if ((e = add(P + "0.downsample.0.weight", Cg[g], cin, cinp, 1))) return e;
-        if ((e = add(P + "1.conv1.weight", Cg[g], Cg[g], Cg[g], 3))) return e;
-        if ((e = add(P + "1.conv2.weight", Cg[g], Cg[g], Cg[g], 3))) return e;
+        const int st = g == 0 ? 1 : 2, f = g == 0 ? fold0 : 1;
+        if ((e = add(P + "0.conv1.weight", Cg[g], cin, cinp, 3, st, f))) return e;
+        if ((e = add(P + "0.conv2.weight", Cg[g], Cg[g], Cg[g], 3, 1, f))) return e;
+        if ((e = add(P + "0.downsample.0.weight", Cg[g], cin, cinp, 1, st, f))) return e;
+        if ((e = add(P + "1.conv1.weight", Cg[g], Cg[g], Cg[g], 3, 1, f))) return e;
+        if ((e = add(P + "1.conv2.weight", Cg[g], Cg[g], Cg[g], 3, 1, f))) return e;
         snprintf(p, sizeof p, "actor_net.lateral.%d.conv.weight", g);
-        if ((e = add(p, 128, Cg[g], Cg[g], 3))) return e;
+        if ((e = add(p, 128, Cg[g], Cg[g], 3, 1, 1))) return e;
         cin = cinp = Cg[g];
     }
-    if (const char* e = add("actor_net.output.conv1.weight", 128, 128, 128, 3)) return e;
-    if (const char* e = add("actor_net.output.conv2.weight", 128, 128, 128, 3)) return e;
+    if (const char* e = add("actor_net.output.conv1.weight", 128, 128, 128, 3, 1, 1)) return e;
+    if (const char* e = add("actor_net.output.conv2.weight", 128, 128, 128, 3, 1, 1)) return e;
     for (auto& kv : dev)
         if (kv.first.rfind("actor_net.", 0) == 0 && kv.first.find('#') == std::string::npos) a.vec[kv.first] = kv.second;
     if (cudaMalloc(&a.d_err, sizeof(int)) != cudaSuccess) return "actor_tc_pack: cudaMalloc(err) failed";
@@ -125,19 +136,23 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         auto it = a.conv.find(key);
         if (it == a.conv.end()) { err = "actor_tc_run: unknown conv"; return; }
         const ActorTcConv& cv = it->second;
+        if (stride != cv.stride) { err = "actor_tc_run: conv stride differs from the packed one"; return; }
         const int Lout = (Lin - 1) / stride + 1;
-        const int r_in = Lout >= 48 ? 16 : Lout / 3;     // 48->16, 24->8, 12->4, 6->2 : always 3 inner tiles
+        if (Lout % cv.fold || (last_only && cv.fold != 1)) { err = "actor_tc_run: fold does not divide the output length"; return; }
+        const int Lf = Lout / cv.fold;                   // GEMM rows per actor
+        const int r_in = Lf >= 48 ? 16 : Lf / 3;         // 48->16, 24->8, 12->4, 6->2 : always 3 inner tiles
         const int r_out = 128 / r_in;
-        const int C = cv.Cin_pad;
+        const int C = cv.Cin_pad, N = cv.fold * cv.Cout;
         // k=3: window starts at padded row t*stride (original t*stride-1); k=1: padded row t*stride+1
         const int64_t base_off = (cv.ksize == 1) ? C : 0;
+        const int64_t row_step = (int64_t)cv.fold * stride * C;
         alignas(64) unsigned char mh[128], ml[128];
-        if ((err = tcg_encode_a(mh, in.hi + base_off, cv.Kpad, Lout, A, (int64_t)stride * C, (int64_t)(Lin + 2) * C, r_in, r_out))) return;
-        if ((err = tcg_encode_a(ml, in.lo + base_off, cv.Kpad, Lout, A, (int64_t)stride * C, (int64_t)(Lin + 2) * C, r_in, r_out))) return;
+        if ((err = tcg_encode_a(mh, in.hi + base_off, cv.Kpad, Lf, A, row_step, (int64_t)(Lin + 2) * C, r_in, r_out))) return;
+        if ((err = tcg_encode_a(ml, in.lo + base_off, cv.Kpad, Lf, A, row_step, (int64_t)(Lin + 2) * C, r_in, r_out))) return;
         TcGemm g;
         g.amap_hi = mh; g.amap_lo = ml; g.wmap = cv.wmap; g.split = 1; g.k_blocks = cv.Kpad / 64;
-        g.r_in = r_in; g.r_out = r_out; g.L_inner = Lout; g.n_outer = A;
-        g.N = cv.Cout; g.n_tile = cv.Cout; g.C = raw; g.ldc = cv.Cout; g.c_last_only = last_only; g.stats = stats; g.err = a.d_err;
+        g.r_in = r_in; g.r_out = r_out; g.L_inner = Lf; g.n_outer = A;
+        g.N = N; g.n_tile = N; g.C = raw; g.ldc = N; g.c_last_only = last_only; g.stats = stats; g.err = a.d_err;
         err = tcg_launch(g, sm_count, st);
     };
     auto apply = [&](const float* raw, const float* stats, const std::string& gk, int L, int C, int relu, HL out_hl, float* out_f32,

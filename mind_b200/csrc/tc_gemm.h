@@ -44,8 +44,10 @@ void tcg_gn_apply(const TcApply& q, cudaStream_t st);
 
 // ---- ActorNet (reference network.py:12-61) on the GEMM engine --------------------------------
 struct ActorTcConv {
-    __half* W = nullptr;     // [Cout][2*Kpad] fp16 = [hi | lo], k index = tap * Cin_pad + ci
+    __half* W = nullptr;     // [fold*Cout][2*Kpad] fp16 = [hi | lo], k index = tap * Cin_pad + ci
     int Cout = 0, Cin_pad = 0, ksize = 3, Kpad = 0;
+    int stride = 1;          // time stride of the convolution
+    int fold = 1;            // `fold` consecutive output steps form one GEMM row: N = fold*Cout, taps = (fold-1)*stride + ksize
     alignas(64) unsigned char wmap[128];
 };
 struct ActorTc {
