@@ -145,6 +145,9 @@ struct MindCtx {
     NodeW node_tc[6][4];          // per fusion layer: [S|T|q] (384x128), out-proj (128x128), linear1 (256x128), linear2 (128x256)
     // exact tier of the tensor-core mode (scenes with fewer than tc_min_tokens tokens): W_e, W_pe, W_k|W_v as 3-term operands
     NodeW pair_tc[6][3];
+    // decoder: reg.0, reg.3, reg.6 (49k rows at B = 256) and actor_proj.0, actor_proj.3 as 3-term operands of the GEMM engine
+    NodeW dec_tc[5];
+    int decoder_simt = 0;         // diagnostics: keep the decoder's large linears on the fp32 SIMT GEMM
     int tc_min_tokens = 128;
     int32_t* d_small = nullptr; int small_cap = 0;
     // descriptor tables
@@ -208,6 +211,7 @@ extern "C" void mind_destroy(MindCtx* c) {
     if (c->lane_err) cudaFree(c->lane_err);
     for (auto& lay : c->node_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
     for (auto& lay : c->pair_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
+    for (auto& nw : c->dec_tc) if (nw.W) cudaFree(nw.W);
     delete c;
 }
 
@@ -225,6 +229,9 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
         c->precision = (int)value;
     } else if (!strcmp(name, "actor_simt")) {
         c->actor_simt = value != 0;
+    } else if (!strcmp(name, "decoder_simt")) {
+        if (c->decoder_simt != (value != 0)) graph_cache_clear(c);
+        c->decoder_simt = value != 0;
     } else if (!strcmp(name, "node_unfused")) {
         if (c->node_unfused != (value != 0)) graph_cache_clear(c);
         c->node_unfused = value != 0;
@@ -498,6 +505,30 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
             std::vector<float> Wkv(Win->begin() + 128 * 128, Win->end());
             if ((e3 = pack(c->pair_tc[l][2], Wkv, 256, 128, 256))) return fail("pair pack: %s", e3);
         }
+        {   // decoder linears with many rows: [N rows, padded to the column tile][hi K | lo K]
+            struct DSpec { const char* key; int N, K, n_tile; };
+            const DSpec ds[5] = {{"pred_scene.reg.0.weight", 128, 128, 128}, {"pred_scene.reg.3.weight", 128, 128, 128},
+                                 {"pred_scene.reg.6.weight", 40, 128, 64}, {"pred_scene.actor_proj.0.weight", 384, 128, 128},
+                                 {"pred_scene.actor_proj.3.weight", 768, 384, 128}};
+            for (int i = 0; i < 5; ++i) {
+                const std::vector<float>* Wv = find(c, ds[i].key);
+                if (!Wv || Wv->size() != (size_t)ds[i].N * ds[i].K) return fail("missing / mis-sized %s", ds[i].key);
+                const int K = ds[i].K, Np = ((ds[i].N + ds[i].n_tile - 1) / ds[i].n_tile) * ds[i].n_tile;
+                std::vector<__half> Wp((size_t)Np * 2 * K, __float2half(0.f));
+                for (int o = 0; o < ds[i].N; ++o)
+                    for (int k = 0; k < K; ++k) {
+                        const float wv = (*Wv)[(size_t)o * K + k];
+                        const __half hh = __float2half_rn(wv);
+                        Wp[(size_t)o * 2 * K + k] = hh;
+                        Wp[(size_t)o * 2 * K + K + k] = __float2half_rn(wv - __half2float(hh));
+                    }
+                MindCtx::NodeW& nw = c->dec_tc[i];
+                if (!nw.W) CUDA_OK(cudaMalloc(&nw.W, Wp.size() * sizeof(__half)));
+                CUDA_OK(cudaMemcpy(nw.W, Wp.data(), Wp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                nw.N = ds[i].N; nw.K = K; nw.n_tile = ds[i].n_tile;
+                if (const char* e5 = tcg_encode_w(nw.wmap, nw.W, 2 * K, Np, ds[i].n_tile)) return fail("decoder wmap: %s", e5);
+            }
+        }
         // token-side chain kernel: layer l's out-proj / FFN / norms + layer l+1's fused [S | T | q/4] projection
         for (int l = 0; l < 6; ++l) {
             char pfx[96];
@@ -551,6 +582,7 @@ struct Ws {
     __half *lh[3], *ll[3];     // lane-net fp16 hi/lo operand buffers [R,128]
     float* lt32;
     __half *xh, *xl, *ah, *al, *fh, *fl;   // token state / attention output / FFN hidden as fp16 hi/lo operands
+    __half *dh, *dl;                       // decoder: operand of the current large linear [A*6,128] or [A,384]
     // exact tier (compact pair grid of the small scenes): fp32 edge + operands of the 3-term GEMMs
     float *xe32, *xtmp, *xkv;
     __half *xeh, *xel, *xmh, *xml;
@@ -592,6 +624,7 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, int n
         for (int i = 0; i < 3; ++i) w.lh[i] = w.ll[i] = nullptr;
         w.lt32 = nullptr;
         w.xh = w.xl = w.ah = w.al = w.fh = w.fl = nullptr;
+        w.dh = w.dl = nullptr;
     } else {
         w.edge = w.tmp = w.memory = w.kv = nullptr;
         w.edge16 = n_big > 0 ? cv.take<__half>((int64_t)B * pairs * 128) : nullptr;
@@ -608,6 +641,7 @@ int64_t carve(const MindCtx* c, void* base, int B, int A, int L, int Nmax, int n
         w.xh = cv.take<__half>(TOK * 128 + 512); w.xl = cv.take<__half>(TOK * 128 + 512);
         w.ah = cv.take<__half>(TOK * 128 + 512); w.al = cv.take<__half>(TOK * 128 + 512);
         w.fh = cv.take<__half>(TOK * 256 + 512); w.fl = cv.take<__half>(TOK * 256 + 512);
+        w.dh = cv.take<__half>((int64_t)A * 768 + 512); w.dl = cv.take<__half>((int64_t)A * 768 + 512);
     }
     w.actors_f = cv.take<float>((int64_t)A * 128);
     w.cls_tok = cv.take<float>((int64_t)B * 128);
@@ -796,7 +830,7 @@ static void run_node_post(MindCtx* c, const FusionLayerW& f, const Ws& w, int64_
     launch_layernorm(x, xo, f.n3_g, f.n3_b, x, rows, 128, 0, st);
 }
 
-static void run_decoder(MindCtx* c, const Ws& w, const MindBatch* bt, const MindOutputs* out, int B, int A,
+static const char* run_decoder(MindCtx* c, const Ws& w, const MindBatch* bt, const MindOutputs* out, int B, int A,
                         const float* tgt_feat, cudaStream_t st) {
     Lin L{c, st};
     const std::string P = "pred_scene.";
@@ -822,9 +856,25 @@ static void run_decoder(MindCtx* c, const Ws& w, const MindBatch* bt, const Mind
         L.gemm(w.f1, 1536, L.W(Q + "linear2.weight"), 1536, L.W(Q + "linear2.bias"), w.f2, 128, (int64_t)B * 6, 128, 1536);
         launch_layernorm(w.ce, w.f2, L.W(Q + "norm2.weight"), L.W(Q + "norm2.bias"), w.ce, (int64_t)B * 6, 128, 0, st);
     }
+    // The linears over actor rows (A) and actor x mode rows (6A) run as 3-term fp16 products on the GEMM engine in the
+    // tensor-core mode (fp32-equivalent, like the token-side projections): operand split -> k_tc_gemm -> LayerNorm
+    const bool dtc = c->precision == MIND_PREC_F16TC && !c->decoder_simt && w.dh;
+    const char* derr = nullptr;
+    auto tc_lin = [&](int wi, const float* x32, int64_t rows, const std::string& bias_key, float* y, int ldy) {
+        const MindCtx::NodeW& nw = c->dec_tc[wi];
+        if (x32) launch_split_hl(x32, w.dh, w.dl, rows * nw.K, st);
+        if (!derr) derr = node_tc_gemm(c, nw, w.dh, w.dl, rows, L.W(bias_key), 0, y, ldy, nullptr, nullptr, 0, st);
+    };
     // actor_embed = actor_proj(actors).view(Na,6,128)   (:504)
-    L.lin_ln_relu(P + "actor_proj.", 0, w.actors_f, 128, w.a1, 384, A);
-    L.lin_ln_relu(P + "actor_proj.", 3, w.a1, 384, w.ae, 768, A);
+    if (dtc) {
+        tc_lin(3, w.actors_f, A, P + "actor_proj.0.bias", w.a1, 384);
+        launch_layernorm(w.a1, nullptr, L.W(P + "actor_proj.1.weight"), L.W(P + "actor_proj.1.bias"), w.a1, A, 384, 1, st);
+        tc_lin(4, w.a1, A, P + "actor_proj.3.bias", w.ae, 768);
+        launch_layernorm(w.ae, nullptr, L.W(P + "actor_proj.4.weight"), L.W(P + "actor_proj.4.bias"), w.ae, A, 768, 1, st);
+    } else {
+        L.lin_ln_relu(P + "actor_proj.", 0, w.actors_f, 128, w.a1, 384, A);
+        L.lin_ln_relu(P + "actor_proj.", 3, w.a1, 384, w.ae, 768, A);
+    }
     launch_embed_combine(w.ce, w.ae, w.tg1, c->d_actor_scene, w.embed, A, st);   // (:506-510)
     // cls head (:512,547-548)
     L.lin_ln_relu(P + "cls.", 0, w.ce, 128, w.k1, 128, (int64_t)B * 6);
@@ -832,11 +882,21 @@ static void run_decoder(MindCtx* c, const Ws& w, const MindBatch* bt, const Mind
     L.gemm(w.k2, 128, L.W(P + "cls.6.weight"), 128, L.W(P + "cls.6.bias"), w.logit, 1, (int64_t)B * 6, 1, 128);
     launch_softmax6(w.logit, out->cls, B, st);
     // reg head + Bezier (:515-523,545)
-    L.lin_ln_relu(P + "reg.", 0, w.embed, 128, w.h1, 128, (int64_t)A * 6);
-    L.lin_ln_relu(P + "reg.", 3, w.h1, 128, w.h2, 128, (int64_t)A * 6);
     float* param = out->param ? out->param : w.param;
-    L.gemm(w.h2, 128, L.W(P + "reg.6.weight"), 128, L.W(P + "reg.6.bias"), param, 40, (int64_t)A * 6, 40, 128);
+    if (dtc) {     // LayerNorm + ReLU write the next product's (hi, lo) operand directly
+        const int64_t R6 = (int64_t)A * 6;
+        tc_lin(0, w.embed, R6, P + "reg.0.bias", w.h1, 128);
+        launch_layernorm_hl(w.h1, nullptr, L.W(P + "reg.1.weight"), L.W(P + "reg.1.bias"), nullptr, w.dh, w.dl, R6, 1, st);
+        tc_lin(1, nullptr, R6, P + "reg.3.bias", w.h2, 128);
+        launch_layernorm_hl(w.h2, nullptr, L.W(P + "reg.4.weight"), L.W(P + "reg.4.bias"), nullptr, w.dh, w.dl, R6, 1, st);
+        tc_lin(2, nullptr, R6, P + "reg.6.bias", param, 40);
+    } else {
+        L.lin_ln_relu(P + "reg.", 0, w.embed, 128, w.h1, 128, (int64_t)A * 6);
+        L.lin_ln_relu(P + "reg.", 3, w.h1, 128, w.h2, 128, (int64_t)A * 6);
+        L.gemm(w.h2, 128, L.W(P + "reg.6.weight"), 128, L.W(P + "reg.6.bias"), param, 40, (int64_t)A * 6, 40, 128);
+    }
     launch_bezier(param, L.W("__bezier_T"), L.W("__bezier_Tp"), out->reg, out->vel, out->cov_vel, A * 6, st);
+    return derr;
 }
 
 extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* out, void* workspace,
@@ -1081,7 +1141,7 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
     launch_gather_tokens(w.x, c->d_sd, w.actors_f, w.cls_tok, B, Nmax, st);                 // :334-336
     PROF_NEXT("fusion_other");
     // ---- decoder --------------------------------------------------------------------------
-    run_decoder(c, w, bt, out, B, A, tgt_feat, st);
+    if (const char* e = run_decoder(c, w, bt, out, B, A, tgt_feat, st)) return fail("run_decoder: %s", e);
     PROF_NEXT("decoder");
     if (c->prof.on && pb_) c->prof.pool.push_back(pb_);
     CUDA_OK(cudaGetLastError());
