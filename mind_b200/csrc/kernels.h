@@ -85,8 +85,12 @@ void launch_gather_tokens(const float* x, const SceneDesc* sd, float* actors, fl
 // OutT = float (exact path) or __half (tensor-core path)
 void launch_edge_init_f32(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
                           const float* g, const float* be, float* edge, int b0, int nb, int Nmax, cudaStream_t st);
-void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
-                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st);
+
+// tensor-core mode (fp16 edge stream): closed-form LayerNorm statistics, channel-parallel (simt_kernels.cu, k_edge_init_ch);
+// the table packs gamma * centred W / b and beta per lane, quad21 the variance coefficients
+void edge_init_pack_ch(const float* W, const float* b, const float* g, const float* be, float* tab896, float* quad21);
+void launch_edge_init_ch(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* dev_tab, const float* quad21,
+                         __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st);
 
 // exact-path pair epilogues on rows r = ((b*Nmax + i)*Nmax + j)
 // memory = ReLU(LN(tmp + S[b,j] + T[b,i]))   with STQ [B*Nmax, 384] = [S | T | q]

@@ -148,6 +148,8 @@ struct MindCtx {
     // decoder: reg.0, reg.3, reg.6 (49k rows at B = 256) and actor_proj.0, actor_proj.3 as 3-term operands of the GEMM engine
     NodeW dec_tc[5];
     int decoder_simt = 0;         // diagnostics: keep the decoder's large linears on the fp32 SIMT GEMM
+    float* ei_tab = nullptr;      // edge init (channel-parallel form): per-lane parameter table [32][2][7] float2
+    float ei_quad[21] = {};       //   and the closed-form variance coefficients
     int tc_min_tokens = 128;
     int32_t* d_small = nullptr; int small_cap = 0;
     // descriptor tables
@@ -212,6 +214,7 @@ extern "C" void mind_destroy(MindCtx* c) {
     for (auto& lay : c->node_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
     for (auto& lay : c->pair_tc) for (auto& nw : lay) if (nw.W) cudaFree(nw.W);
     for (auto& nw : c->dec_tc) if (nw.W) cudaFree(nw.W);
+    if (c->ei_tab) cudaFree(c->ei_tab);
     delete c;
 }
 
@@ -504,6 +507,18 @@ extern "C" int mind_finalize_weights(MindCtx* c) {
             if (l < 5 && (e3 = pack(c->pair_tc[l][1], *find(c, P + "proj_edge.0.weight"), 128, 128, 128))) return fail("pair pack: %s", e3);
             std::vector<float> Wkv(Win->begin() + 128 * 128, Win->end());
             if ((e3 = pack(c->pair_tc[l][2], Wkv, 256, 128, 256))) return fail("pair pack: %s", e3);
+        }
+        {   // edge init: closed-form LayerNorm statistics + per-lane parameter table (simt_kernels.cu, k_edge_init_ch)
+            const std::vector<float>* Wv = find(c, "fusion_net.proj_rpe_scene.0.weight");
+            const std::vector<float>* bv = find(c, "fusion_net.proj_rpe_scene.0.bias");
+            const std::vector<float>* gv = find(c, "fusion_net.proj_rpe_scene.1.weight");
+            const std::vector<float>* ev = find(c, "fusion_net.proj_rpe_scene.1.bias");
+            if (!Wv || !bv || !gv || !ev || Wv->size() != 640 || bv->size() != 128 || gv->size() != 128 || ev->size() != 128)
+                return fail("missing / mis-sized fusion_net.proj_rpe_scene weights");
+            std::vector<float> tab(896);
+            edge_init_pack_ch(Wv->data(), bv->data(), gv->data(), ev->data(), tab.data(), c->ei_quad);
+            if (!c->ei_tab) CUDA_OK(cudaMalloc(&c->ei_tab, tab.size() * sizeof(float)));
+            CUDA_OK(cudaMemcpy(c->ei_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
         {   // decoder linears with many rows: [N rows, padded to the column tile][hi K | lo K]
             struct DSpec { const char* key; int N, K, n_tile; };
@@ -1095,7 +1110,8 @@ extern "C" int mind_forward(MindCtx* c, const MindBatch* bt, const MindOutputs* 
             }
         }
     } else {
-        if (n_big > 0) launch_edge_init_f16(c->d_sd, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.edge16, 0, B, Nmax, c->tc_min_tokens, st);
+        if (n_big > 0)
+            launch_edge_init_ch(c->d_sd, bt->ctrs, bt->vecs, c->ei_tab, c->ei_quad, w.edge16, 0, B, Nmax, c->tc_min_tokens, st);
         const int64_t xrows = (int64_t)n_small * Ns * Ns;
         launch_x3_edge_init(c->d_sd, c->d_small, bt->ctrs, bt->vecs, Wr, br, gr, ber, w.xe32, w.xeh, w.xel, n_small, Ns, st);
         const int64_t TOKR = (int64_t)B * Nmax;

@@ -738,12 +738,7 @@ void launch_edge_init_f32(const SceneDesc* sd, const float* ctrs, const float* v
     k_edge_init<float><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sd, ctrs, vecs, W, b, g, be, edge, b0, nb, Nmax);
     ++g_launches;
 }
-// fp16 edge stream for the tensor-core path.  One THREAD per pair row: the 5 -> 128 projection, the LayerNorm statistics
-// and the normalisation run on packed fp32 pairs in the thread's own registers (no cross-lane reduction), the per-channel
-// parameters are broadcast shared-memory loads, and the 256-byte fp16 rows leave through a padded shared-memory tile so
-// that the global stores are full 256-byte segments.  (The warp-per-row version before it was issue-bound: 124 warp
-// instructions per pair row, 77 % issue-slot utilisation at 1.7 TB/s of a pure write stream, profiles/r02_v1_other_kernels_ncu_full.md;
-// this one needs ~30.)
+// fp16 edge stream for the tensor-core path: packed fp32 pair helpers, then the kernel
 namespace {
 typedef unsigned long long ef2;
 __device__ __forceinline__ ef2 e_pk2(float a, float b) { ef2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -756,117 +751,148 @@ __device__ __forceinline__ uint32_t e_cvt_relu_h2(ef2 v) {      // (lo, hi) fp32
     float a, b; e_upk2(v, a, b); uint32_t d;
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a)); return d;
 }
-constexpr int kEiRows = 128;            // pair rows (= threads) per tile
-constexpr int kEiStride = 272;          // bytes per staged row: 256 + 16 keeps the 16-byte stores of 32 lanes conflict-free
 }  // namespace
 
-__global__ void __launch_bounds__(kEiRows, 3) k_edge_init_rows(const SceneDesc* __restrict__ sd, const float* __restrict__ ctrs,
-                                                               const float* __restrict__ vecs, const float* __restrict__ W,
-                                                               const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, __half* __restrict__ edge, int nb,
-                                                               int Nmax, int min_tokens) {
-    // per channel pair p: [b | w0 | w1 | w2] [w3 | w4 | gamma | beta], each entry a (channel 2p, channel 2p+1) pair
-    __shared__ __align__(16) float sw[64 * 16];
-    __shared__ __align__(16) unsigned char stile[kEiRows * kEiStride];
-    for (int e = threadIdx.x; e < 64 * 16; e += kEiRows) {
-        const int p = e >> 4, f = (e >> 1) & 7, c = 2 * p + (e & 1);
-        sw[e] = f == 0 ? bias[c] : f <= 5 ? W[c * 5 + (f - 1)] : f == 6 ? gamma[c] : beta[c];
-    }
-    __syncthreads();
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+// ---- edge init, channel-parallel form ----------------------------------------------------------------------------
+// LayerNorm of a 5 -> 128 projection has closed-form statistics: with Wc = W - mean_c(W), bc = b - mean_c(b) (centred over
+// the 128 channels) x[c] - mean = Wc[c].r + bc[c], so var(r) = r^T Q r + L.r + c0 with Q = Wc^T Wc / 128, L = 2 Wc^T bc / 128,
+// c0 = bc.bc / 128 (21 coefficients, formed in double on the host; centred, so no cancellation), and
+//     y[c] = G[c].(rstd r) + g5[c] rstd + beta[c],   G = gamma Wc,  g5 = gamma bc.
+// Nothing has to be held per channel across a reduction, so the work is laid out the other way round from a row per
+// thread (the previous kernel: 0.70 ms, bound by 256 broadcast parameter loads per row): lane l owns channels [4l, 4l+4) with its 28 parameters in REGISTERS for the whole kernel (no
+// parameter loads at all inside the loop), a warp takes 32 pair rows:
+// phase 1, lane = row: RPE entry, variance, rstd -> (rstd r, rstd) through 64 B of shared memory per row; phase 2, lane =
+// channels: 12 FFMA2 + 2 conversions per row and ONE coalesced 256-byte row store per warp instruction (no staging tile).
+struct EiQuad { float q[21]; };     // c0, L[5], Q upper triangle by rows (off-diagonals doubled)
+__global__ void __launch_bounds__(128) k_edge_init_ch(const SceneDesc* __restrict__ sd, const float* __restrict__ ctrs,
+                                                      const float* __restrict__ vecs, const float2* __restrict__ tab,
+                                                      const EiQuad quad, __half* __restrict__ edge, int nb, int Nmax, int min_tokens) {
+    __shared__ __align__(16) float srow[4][32][16];          // per warp, per row: (r'_0, r'_0) ... (r'_4, r'_4), (rstd, rstd), valid, -
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ef2 P[2][7];                                             // [channel pair][G0..G4, g5, beta] of channels 4 lane + 2 pair + {0,1}
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+        for (int f = 0; f < 7; ++f) {
+            const float2 v = __ldg(tab + (lane * 2 + pr) * 7 + f);
+            P[pr][f] = e_pk2(v.x, v.y);
+        }
     const int64_t per = (int64_t)Nmax * Nmax;
-    const int tiles_per_scene = (int)((per + kEiRows - 1) / kEiRows);
-    const int64_t n_tiles = (int64_t)nb * tiles_per_scene;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = (int)(tile / tiles_per_scene);
-        const int64_t r0 = (int64_t)(tile - (int64_t)b * tiles_per_scene) * kEiRows;
+    const int groups_per_scene = (int)((per + 31) / 32);
+    const int64_t n_groups = (int64_t)nb * groups_per_scene;
+    const int64_t wstride = (int64_t)gridDim.x * 4;
+    for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < n_groups; grp += wstride) {
+        const int b = (int)(grp / groups_per_scene);
+        const int64_t r0 = (grp - (int64_t)b * groups_per_scene) * 32;
         const SceneDesc d = sd[b];
         const int M = d.n_actor + d.n_lane;
-        if (M + 1 < min_tokens) continue;            // exact-tier scene: its edge lives in the fp32 pair grid (uniform per tile)
-        const int64_t r = r0 + t;
-        const int i = (int)(r / Nmax), j = (int)(r - (int64_t)i * Nmax);
-        uint4* srow = reinterpret_cast<uint4*>(stile + t * kEiStride);
-        if (r < per && i < M && j < M) {
-            float rk[5];
-            if (d.rpe) {
+        if (M + 1 < min_tokens) continue;                    // exact-tier scene (uniform per warp)
+        {   // phase 1: this lane's row
+            const int64_t r = r0 + lane;
+            const int i = (int)(r / Nmax), j = (int)(r - (int64_t)i * Nmax);
+            float rk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            const bool ok = r < per && i < M && j < M;
+            if (ok) {
+                if (d.rpe) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) rk[k] = __ldg(d.rpe + ((int64_t)k * M + i) * M + j);
-            } else {      // entry [i, j]: v1 = vecs[j], v2 = vecs[i], dpos = ctrs[j] - ctrs[i]   (utils.py:195-209)
-                const float2 ci = reinterpret_cast<const float2*>(ctrs)[d.geom_off + i];
-                const float2 cj = reinterpret_cast<const float2*>(ctrs)[d.geom_off + j];
-                const float2 vi = reinterpret_cast<const float2*>(vecs)[d.geom_off + i];
-                const float2 vj = reinterpret_cast<const float2*>(vecs)[d.geom_off + j];
-                const float dx = cj.x - ci.x, dy = cj.y - ci.y;
-                const float dist = sqrtf(dx * dx + dy * dy);
-                const float nj = sqrtf(vj.x * vj.x + vj.y * vj.y), ni = sqrtf(vi.x * vi.x + vi.y * vi.y);
-                const float den1 = nj * ni + 1e-10f, den2 = nj * dist + 1e-10f;
-                rk[0] = (vj.x * vi.x + vj.y * vi.y) / den1;
-                rk[1] = (vj.x * vi.y - vj.y * vi.x) / den1;
-                rk[2] = (vj.x * dx + vj.y * dy) / den2;
-                rk[3] = (vj.x * dy - vj.y * dx) / den2;
-                rk[4] = dist * 2.f / 100.f;
-            }
-            const ef2 q0 = e_pk2(rk[0], rk[0]), q1 = e_pk2(rk[1], rk[1]), q2 = e_pk2(rk[2], rk[2]), q3 = e_pk2(rk[3], rk[3]),
-                      q4 = e_pk2(rk[4], rk[4]);
-            ef2 y[64];
-            ef2 s1 = 0ull;
-#pragma unroll
-            for (int p = 0; p < 64; ++p) {
-                const ulonglong2 A = *reinterpret_cast<const ulonglong2*>(sw + p * 16);        // b, w0
-                const ulonglong2 Bv = *reinterpret_cast<const ulonglong2*>(sw + p * 16 + 4);   // w1, w2
-                const ulonglong2 Cv = *reinterpret_cast<const ulonglong2*>(sw + p * 16 + 8);   // w3, w4
-                const ef2 v = e_fma2(Cv.y, q4, e_fma2(Cv.x, q3, e_fma2(Bv.y, q2, e_fma2(Bv.x, q1, e_fma2(A.y, q0, A.x)))));
-                y[p] = v;
-                s1 = e_add2(s1, v);
-            }
-            float sa, sb;
-            e_upk2(s1, sa, sb);
-            const float mean = (sa + sb) * (1.f / 128.f);
-            const ef2 m2 = e_pk2(mean, mean);
-            ef2 qq = 0ull;
-#pragma unroll
-            for (int p = 0; p < 64; ++p) { y[p] = e_sub2(y[p], m2); qq = e_fma2(y[p], y[p], qq); }
-            e_upk2(qq, sa, sb);
-            const float rstd = rsqrtf((sa + sb) * (1.f / 128.f) + LN_EPS);
-            const ef2 r2 = e_pk2(rstd, rstd);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {          // 8 channels = 4 pairs per 16-byte chunk
-                uint32_t o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int p = c * 4 + e;
-                    const ulonglong2 G = *reinterpret_cast<const ulonglong2*>(sw + p * 16 + 12);   // gamma, beta
-                    o[e] = e_cvt_relu_h2(e_fma2(e_mul2(y[p], r2), G.x, G.y));
+                    for (int k = 0; k < 5; ++k) rk[k] = __ldg(d.rpe + ((int64_t)k * M + i) * M + j);
+                } else {      // entry [i, j]: v1 = vecs[j], v2 = vecs[i], dpos = ctrs[j] - ctrs[i]   (utils.py:195-209)
+                    const float2 ci = reinterpret_cast<const float2*>(ctrs)[d.geom_off + i];
+                    const float2 cj = reinterpret_cast<const float2*>(ctrs)[d.geom_off + j];
+                    const float2 vi = reinterpret_cast<const float2*>(vecs)[d.geom_off + i];
+                    const float2 vj = reinterpret_cast<const float2*>(vecs)[d.geom_off + j];
+                    const float dx = cj.x - ci.x, dy = cj.y - ci.y;
+                    const float dist = sqrtf(dx * dx + dy * dy);
+                    const float nj = sqrtf(vj.x * vj.x + vj.y * vj.y), ni = sqrtf(vi.x * vi.x + vi.y * vi.y);
+                    const float den1 = nj * ni + 1e-10f, den2 = nj * dist + 1e-10f;
+                    rk[0] = (vj.x * vi.x + vj.y * vi.y) / den1;
+                    rk[1] = (vj.x * vi.y - vj.y * vi.x) / den1;
+                    rk[2] = (vj.x * dx + vj.y * dy) / den2;
+                    rk[3] = (vj.x * dy - vj.y * dx) / den2;
+                    rk[4] = dist * 2.f / 100.f;
                 }
-                srow[c] = make_uint4(o[0], o[1], o[2], o[3]);
             }
-        } else if (r < per) {
+            float var = quad.q[0];
+            int qi = 6;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) srow[c] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
-        // copy-out: a warp moves 2 staged rows (2 x 256 B) per instruction as two full segments
-        __half* dst0 = edge + ((int64_t)b * per + r0) * 128;
-#pragma unroll 4
-        for (int it = 0; it < kEiRows / 8; ++it) {
-            const int rr = it * 8 + warp * 2 + (lane >> 4);
-            if (r0 + rr < per) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stile + rr * kEiStride + (lane & 15) * 16);
-                *reinterpret_cast<uint4*>(dst0 + (int64_t)rr * 128 + (lane & 15) * 8) = v;
+            for (int k = 0; k < 5; ++k) {
+                float t = quad.q[1 + k];
+#pragma unroll
+                for (int l = k; l < 5; ++l) t = fmaf(quad.q[qi++], rk[l], t);
+                var = fmaf(rk[k], t, var);
             }
+            const float rstd = rsqrtf(fmaxf(var, 0.f) + LN_EPS);
+            float4* dst = reinterpret_cast<float4*>(&srow[warp][lane][0]);
+            dst[0] = make_float4(rstd * rk[0], rstd * rk[0], rstd * rk[1], rstd * rk[1]);
+            dst[1] = make_float4(rstd * rk[2], rstd * rk[2], rstd * rk[3], rstd * rk[3]);
+            dst[2] = make_float4(rstd * rk[4], rstd * rk[4], rstd, rstd);
+            dst[3] = make_float4(ok ? 1.f : 0.f, 0.f, 0.f, 0.f);
         }
-        __syncthreads();
+        __syncwarp();
+        // phase 2: lane = channels [4 lane, 4 lane + 4); one row per iteration, 8 bytes per lane = one 256-byte row per warp
+        __half* dst0 = edge + ((int64_t)b * per + r0) * 128 + lane * 4;
+        const int n_rows = (int)min((int64_t)32, per - r0);
+#pragma unroll 4
+        for (int rr = 0; rr < n_rows; ++rr) {
+            const ulonglong2 A = *reinterpret_cast<const ulonglong2*>(&srow[warp][rr][0]);     // r'0, r'1
+            const ulonglong2 Bv = *reinterpret_cast<const ulonglong2*>(&srow[warp][rr][4]);    // r'2, r'3
+            const ulonglong2 Cv = *reinterpret_cast<const ulonglong2*>(&srow[warp][rr][8]);    // r'4, rstd
+            const float okf = srow[warp][rr][12];
+            uint32_t o[2];
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                ef2 y = e_fma2(P[pr][5], Cv.y, P[pr][6]);
+                y = e_fma2(P[pr][0], A.x, y);
+                y = e_fma2(P[pr][1], A.y, y);
+                y = e_fma2(P[pr][2], Bv.x, y);
+                y = e_fma2(P[pr][3], Bv.y, y);
+                y = e_fma2(P[pr][4], Cv.x, y);
+                o[pr] = e_cvt_relu_h2(y);
+            }
+            if (okf == 0.f) { o[0] = 0u; o[1] = 0u; }         // padding rows of the [Nmax x Nmax] grid are zero (uniform per row)
+            *reinterpret_cast<uint2*>(dst0 + (int64_t)rr * 128) = make_uint2(o[0], o[1]);
+        }
+        __syncwarp();                                         // the row table is rewritten by the next group
     }
 }
 
-void launch_edge_init_f16(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* W, const float* b,
-                          const float* g, const float* be, __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st) {
-    const int64_t tiles = (int64_t)nb * (((int64_t)Nmax * Nmax + kEiRows - 1) / kEiRows);
-    if (tiles <= 0) return;
-    const int64_t blocks = std::min<int64_t>(tiles, 148 * 3 * 4);
-    k_edge_init_rows<<<(unsigned)blocks, kEiRows, 0, st>>>(sd + b0, ctrs, vecs, W, b, g, be, edge, nb, Nmax, min_tokens);
+// host side of k_edge_init_ch: lane parameter table [32 lanes][2 pairs][7] float2 and the 21 variance coefficients
+void edge_init_pack_ch(const float* W, const float* b, const float* g, const float* be, float* tab896, float* quad21) {
+    double wm[5] = {0, 0, 0, 0, 0}, bm = 0;
+    for (int c = 0; c < 128; ++c) { for (int k = 0; k < 5; ++k) wm[k] += W[c * 5 + k]; bm += b[c]; }
+    for (int k = 0; k < 5; ++k) wm[k] /= 128.0;
+    bm /= 128.0;
+    double Q[5][5] = {}, Lv[5] = {}, c0 = 0;
+    for (int c = 0; c < 128; ++c) {
+        double wc[5];
+        for (int k = 0; k < 5; ++k) wc[k] = W[c * 5 + k] - wm[k];
+        const double bc = b[c] - bm;
+        for (int k = 0; k < 5; ++k) { Lv[k] += 2.0 * wc[k] * bc; for (int l = 0; l < 5; ++l) Q[k][l] += wc[k] * wc[l]; }
+        c0 += bc * bc;
+        const int lane = c >> 2, pr = (c >> 1) & 1, e = c & 1;
+        float* t = tab896 + ((lane * 2 + pr) * 7) * 2 + e;     // float2 entries: [..][f] = (channel 2p, channel 2p + 1)
+        for (int k = 0; k < 5; ++k) t[k * 2] = (float)(g[c] * wc[k]);
+        t[5 * 2] = (float)(g[c] * bc);
+        t[6 * 2] = be[c];
+    }
+    quad21[0] = (float)(c0 / 128.0);
+    for (int k = 0; k < 5; ++k) quad21[1 + k] = (float)(Lv[k] / 128.0);
+    int qi = 6;
+    for (int k = 0; k < 5; ++k)
+        for (int l = k; l < 5; ++l) quad21[qi++] = (float)((l == k ? 1.0 : 2.0) * Q[k][l] / 128.0);
+}
+
+void launch_edge_init_ch(const SceneDesc* sd, const float* ctrs, const float* vecs, const float* dev_tab, const float* quad21,
+                         __half* edge, int b0, int nb, int Nmax, int min_tokens, cudaStream_t st) {
+    const int64_t groups = (int64_t)nb * (((int64_t)Nmax * Nmax + 31) / 32);
+    if (groups <= 0) return;
+    EiQuad q;
+    for (int i = 0; i < 21; ++i) q.q[i] = quad21[i];
+    const int64_t blocks = std::min<int64_t>((groups + 3) / 4, 148 * 16);
+    k_edge_init_ch<<<(unsigned)blocks, 128, 0, st>>>(sd + b0, ctrs, vecs, reinterpret_cast<const float2*>(dev_tab), q, edge, nb, Nmax, min_tokens);
     ++g_launches;
 }
+
 
 // ------------------------------------------------------------------------------------------
 // exact-path pair epilogues (network.py:197-202, 222)

@@ -16,7 +16,7 @@ timeout 300 $NCU -k regex:k_rela_fusion_tc -s 11 -c 1 -o gpurun_out/prof_last_$R
 timeout 300 $NCU -k regex:k_tc_gemm -s 47 -c 1 -o gpurun_out/prof_gemm_actor_$R python bench.py --steps 1 --warmup 1 --kernel-only >> gpurun_out/ncu_full_$R.log 2>&1
 timeout 300 $NCU -k regex:k_lane_net_tc -s 1 -c 1 -o gpurun_out/prof_lane_chain_$R python bench.py --steps 1 --warmup 1 --kernel-only >> gpurun_out/ncu_full_$R.log 2>&1
 timeout 300 $NCU -k regex:k_node_chain_tc -s 7 -c 1 -o gpurun_out/prof_node_chain_$R python bench.py --steps 1 --warmup 1 --kernel-only >> gpurun_out/ncu_full_$R.log 2>&1
-timeout 300 $NCU -k regex:k_edge_init_rows -s 1 -c 1 -o gpurun_out/prof_edge_init_$R python bench.py --steps 1 --warmup 1 --kernel-only >> gpurun_out/ncu_full_$R.log 2>&1
+timeout 300 $NCU -k regex:k_edge_init_ch -s 1 -c 1 -o gpurun_out/prof_edge_init_$R python bench.py --steps 1 --warmup 1 --kernel-only >> gpurun_out/ncu_full_$R.log 2>&1
 timeout 300 $NCU -k regex:k_gn_apply -s 32 -c 1 -o gpurun_out/prof_gn_apply_$R python bench.py --steps 1 --warmup 1 --kernel-only >> gpurun_out/ncu_full_$R.log 2>&1
 timeout 300 $NCU -k regex:k_node_fields -s 1 -c 1 -o gpurun_out/prof_node_fields_$R python -m pytest tests/test_zz_cost_field_gpu.py -q -m gpu -p no:cacheprovider >> gpurun_out/ncu_full_$R.log 2>&1
 ls -la gpurun_out/*_$R*
