@@ -131,7 +131,10 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         return it->second;
     };
     // conv over a padded channel-last input [A][Lin+2][Cin_pad]: output raw [A*Lout][Cout] + stats
-    auto conv = [&](const std::string& key, HL in, int Lin, int stride, float* raw, float* stats, int last_only = 0) {
+    // gn != nullptr: GroupNorm (+ identity shortcut) (+ ReLU) in the GEMM epilogue, output = padded (hi, lo) operand `gn_out`
+    struct Gn { std::string key; int relu; HL out; const HL* res; };
+    auto conv = [&](const std::string& key, HL in, int Lin, int stride, float* raw, float* stats, int last_only = 0,
+                    const Gn* gn = nullptr) {
         if (err) return;
         auto it = a.conv.find(key);
         if (it == a.conv.end()) { err = "actor_tc_run: unknown conv"; return; }
@@ -140,7 +143,8 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         const int Lout = (Lin - 1) / stride + 1;
         if (Lout % cv.fold || (last_only && cv.fold != 1)) { err = "actor_tc_run: fold does not divide the output length"; return; }
         const int Lf = Lout / cv.fold;                   // GEMM rows per actor
-        const int r_in = Lf >= 48 ? 16 : Lf / 3;         // 48->16, 24->8, 12->4, 6->2 : always 3 inner tiles
+        int r_in = Lf >= 48 ? 16 : Lf / 3;               // 48->16, 24->8, 12->4, 6->2 : always 3 inner tiles
+        if (gn) { r_in = 8; while (r_in < Lf) r_in <<= 1; }   // whole actors per tile: 6->8, 12->16, 24->32, 48->64 (3/4 of the rows used)
         const int r_out = 128 / r_in;
         const int C = cv.Cin_pad, N = cv.fold * cv.Cout;
         // k=3: window starts at padded row t*stride (original t*stride-1); k=1: padded row t*stride+1
@@ -153,6 +157,14 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         g.amap_hi = mh; g.amap_lo = ml; g.wmap = cv.wmap; g.split = 1; g.k_blocks = cv.Kpad / 64;
         g.r_in = r_in; g.r_out = r_out; g.L_inner = Lf; g.n_outer = A;
         g.N = N; g.n_tile = N; g.C = raw; g.ldc = N; g.c_last_only = last_only; g.stats = stats; g.err = a.d_err;
+        if (gn) {
+            g.C = nullptr; g.stats = nullptr;
+            g.gn_gamma = V(gn->key + ".weight"); g.gn_beta = V(gn->key + ".bias"); g.gn_C = cv.Cout;
+            g.gn_inv_n = 1.f / (float)(Lout * cv.Cout); g.relu = gn->relu;
+            g.gn_out_hi = gn->out.hi; g.gn_out_lo = gn->out.lo; g.gn_ld_group = (int64_t)(Lout + 2) * cv.Cout;
+            if (gn->res) { g.gn_res_hi = gn->res->hi; g.gn_res_lo = gn->res->lo; }
+            if (err) return;
+        }
         err = tcg_launch(g, sm_count, st);
     };
     auto apply = [&](const float* raw, const float* stats, const std::string& gk, int L, int C, int relu, HL out_hl, float* out_f32,
@@ -180,17 +192,28 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
         snprintf(p, sizeof p, "actor_net.groups.%d.", g);
         const std::string P(p);
         const int stride = g == 0 ? 1 : 2, Lo = (L - 1) / stride + 1, C = Cg[g];
-        // block 0 (with conv shortcut)
-        conv(P + "0.conv1.weight", cur, L, stride, b.raw1, b.st1);
-        apply(b.raw1, b.st1, P + "0.bn1", Lo, C, 1, b.t0, nullptr);
+        // block 0 (with conv shortcut): bn1 in conv1's epilogue; bn2 joins two GroupNorms, so it stays a separate pass
+        if (a.gn_fused) {
+            const Gn g1{P + "0.bn1", 1, b.t0, nullptr};
+            conv(P + "0.conv1.weight", cur, L, stride, nullptr, nullptr, 0, &g1);
+        } else {
+            conv(P + "0.conv1.weight", cur, L, stride, b.raw1, b.st1);
+            apply(b.raw1, b.st1, P + "0.bn1", Lo, C, 1, b.t0, nullptr);
+        }
         conv(P + "0.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
         conv(P + "0.downsample.0.weight", cur, L, stride, b.raw3, b.st3);
         apply(b.raw2, b.st2, P + "0.bn2", Lo, C, 1, b.t1, nullptr, b.raw3, b.st3, P + "0.downsample.1");
-        // block 1 (identity shortcut)
-        conv(P + "1.conv1.weight", b.t1, Lo, 1, b.raw1, b.st1);
-        apply(b.raw1, b.st1, P + "1.bn1", Lo, C, 1, b.t0, nullptr);
-        conv(P + "1.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
-        apply(b.raw2, b.st2, P + "1.bn2", Lo, C, 1, b.o[g], nullptr, nullptr, nullptr, "", &b.t1);
+        // block 1 (identity shortcut): both GroupNorms in the epilogues
+        if (a.gn_fused) {
+            const Gn g1{P + "1.bn1", 1, b.t0, nullptr}, g2{P + "1.bn2", 1, b.o[g], &b.t1};
+            conv(P + "1.conv1.weight", b.t1, Lo, 1, nullptr, nullptr, 0, &g1);
+            conv(P + "1.conv2.weight", b.t0, Lo, 1, nullptr, nullptr, 0, &g2);
+        } else {
+            conv(P + "1.conv1.weight", b.t1, Lo, 1, b.raw1, b.st1);
+            apply(b.raw1, b.st1, P + "1.bn1", Lo, C, 1, b.t0, nullptr);
+            conv(P + "1.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
+            apply(b.raw2, b.st2, P + "1.bn2", Lo, C, 1, b.o[g], nullptr, nullptr, nullptr, "", &b.t1);
+        }
         cur = b.o[g];
         L = Lo;
     }
@@ -210,8 +233,13 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
     }
     // output Res1d(128,128), identity shortcut = the pyramid top.  Only its last time step leaves ActorNet (:60), but both
     // GroupNorms take their statistics over all 48: conv2 runs in full, stores row 47 only, and is normalised there
-    conv("actor_net.output.conv1.weight", b.p, 48, 1, b.raw1, b.st1);
-    apply(b.raw1, b.st1, "actor_net.output.bn1", 48, 128, 1, b.t0, nullptr);
+    if (a.gn_fused) {
+        const Gn g1{"actor_net.output.bn1", 1, b.t0, nullptr};
+        conv("actor_net.output.conv1.weight", b.p, 48, 1, nullptr, nullptr, 0, &g1);
+    } else {
+        conv("actor_net.output.conv1.weight", b.p, 48, 1, b.raw1, b.st1);
+        apply(b.raw1, b.st1, "actor_net.output.bn1", 48, 128, 1, b.t0, nullptr);
+    }
     conv("actor_net.output.conv2.weight", b.t0, 48, 1, b.raw2, b.st2, 1);
     apply(b.raw2, b.st2, "actor_net.output.bn2", 48, 128, 1, none, out, nullptr, nullptr, "", &b.p, nullptr, 1);
     return err;

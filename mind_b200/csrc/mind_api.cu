@@ -188,6 +188,7 @@ extern "C" int mind_create(MindCtx** out, int device) {
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("mind_create: device sm_%d%d is not Blackwell (sm_100a required)", prop.major, prop.minor);
     MindCtx* c = new MindCtx();
+    if (const char* ev = getenv("MIND_ACTOR_GN_UNFUSED")) c->actor_tc.gn_fused = atoi(ev) == 0;     // A/B switch for profiling runs
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->tc.sm_count = c->sm_count;
@@ -232,6 +233,9 @@ extern "C" int mind_set_option(MindCtx* c, const char* name, int64_t value) {
         c->precision = (int)value;
     } else if (!strcmp(name, "actor_simt")) {
         c->actor_simt = value != 0;
+    } else if (!strcmp(name, "actor_gn_unfused")) {
+        if (c->actor_tc.gn_fused == (value != 0)) graph_cache_clear(c);
+        c->actor_tc.gn_fused = value == 0;      // diagnostics: GroupNorm as a separate pass behind every conv GEMM
     } else if (!strcmp(name, "decoder_simt")) {
         if (c->decoder_simt != (value != 0)) graph_cache_clear(c);
         c->decoder_simt = value != 0;

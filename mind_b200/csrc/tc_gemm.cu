@@ -29,7 +29,8 @@ constexpr uint32_t STG_WARP = 32 * STG_STRIDE * 4;
 constexpr uint32_t SM_STG = RING_BYTES;
 constexpr uint32_t SM_BAR = SM_STG + 8 * STG_WARP;
 constexpr uint32_t SM_TMEM = SM_BAR + 192;
-constexpr uint32_t SMEM_BYTES = SM_TMEM + 16 + 1024;
+constexpr uint32_t SM_GN = SM_TMEM + 16;             // GroupNorm epilogue: gamma | beta (2 x 256 floats), partial sums float2 [2 acc][8 warps][4 slots]
+constexpr uint32_t SMEM_BYTES = SM_GN + 2048 + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,7 +123,149 @@ struct Args {
     int n_stages; uint32_t stage_bytes;      // streaming mode ring
     int res_stages; uint32_t res_w_bytes;    // resident mode: A stages behind the W region
     int r_in_shift;                          // r_in is a power of two: tile row -> (outer, inner) by shift / mask
+    // GroupNorm(1 group) epilogue (ActorNet): a tile holds whole outer groups (tiles_inner = 1), so the statistics over a
+    // group's L_inner x N outputs are complete inside the CTA: y = GN(acc) (+ res) (ReLU) leaves as the padded fp16 (hi, lo)
+    // operand of the next conv, no fp32 round trip through HBM and no second kernel
+    int gn;
+    const float* gn_gamma; const float* gn_beta; int gn_C;      // channel of column n: n & (gn_C - 1)
+    float gn_inv_n;                                              // 1 / (outputs per group)
+    const __half* gn_res_hi; const __half* gn_res_lo;            // identity shortcut (same padded layout) or null
+    __half* gn_out_hi; __half* gn_out_lo;
+    int64_t gn_ld_group;                                         // halfs per group in the padded layout: (L + 2) * C
+    int gn_pad_tail;                                             // halfs of the last padded row: C
 };
+
+// Epilogue of the GroupNorm mode (8 epilogue warps; warp w: TMEM lane quadrant lg = w & 3, column half (w - 2) >> 2).
+// Pass 1 sums x and x^2 of the thread's row over its column half, reduces over the rows of the group inside the warp and
+// publishes one partial per (warp, group slot); one 256-thread named barrier later every thread adds the partials of its
+// group in a fixed order.  Pass 2 re-reads the accumulator (TMEM reads are cheap), normalises, adds the shortcut, applies
+// ReLU, splits to fp16 (hi, lo) and leaves through the warp's staging tile as 64-byte row segments.
+__device__ __forceinline__ void gn_epilogue(const Args& g, uint8_t* sgen, uint32_t bars, uint32_t tmem, int total_tiles, int warp, int lane) {
+    float* sG = reinterpret_cast<float*>(sgen + SM_GN);
+    float* sB = sG + 256;
+    float2* sPart = reinterpret_cast<float2*>(sgen + SM_GN + 2048);
+    for (int i = (int)threadIdx.x - 64; i < g.gn_C; i += 256) { sG[i] = g.gn_gamma[i]; sB[i] = g.gn_beta[i]; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int acc = 0; uint32_t acc_phase = 0;
+    const int ew = warp - 2, lg = warp & 3, chalf = ew >> 2;
+    const int col_lo = chalf * (g.n_tile >> 1), col_hi = col_lo + (g.n_tile >> 1);
+    const int row = lg * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+    const int rw = g.r_in < 32 ? g.r_in : 32;               // rows of one group inside a warp
+    const int slot = g.r_in < 32 ? (lane >> g.r_in_shift) : 0;
+    uint8_t* stg = sgen + SM_STG + (uint32_t)ew * STG_WARP; // [hi: 32 rows x 64 B][lo: 32 rows x 64 B], 16-byte chunks XOR-swizzled
+    const int cmask = g.gn_C - 1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int outer = tile * g.r_out + (row >> g.r_in_shift), inner = row & (g.r_in - 1);
+        const bool valid = outer < g.n_outer && inner < g.L_inner;
+        mbar_wait(bars + 128 + 8 * acc, acc_phase, g.err, 14);
+        tc_fence_after();
+        float s1 = 0.f, s2 = 0.f;
+        for (int n0 = col_lo; n0 < col_hi; n0 += 32) {
+            uint32_t r[32];
+            TCG_LD_X32(tmem + lane_base + acc * 256 + n0, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { const float x = __uint_as_float(r[e]); s1 += x; s2 = fmaf(x, x, s2); }
+        }
+        if (!valid) { s1 = 0.f; s2 = 0.f; }
+        for (int off = rw >> 1; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+        if ((lane & (rw - 1)) == 0) sPart[(acc * 8 + chalf * 4 + lg) * 4 + slot] = make_float2(s1, s2);   // (column half, lane quadrant): warp 2 is quadrant 2
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float S1, S2;
+        if (g.r_in <= 32) {
+            const float2 p0 = sPart[(acc * 8 + lg) * 4 + slot], p1 = sPart[(acc * 8 + 4 + lg) * 4 + slot];
+            S1 = p0.x + p1.x; S2 = p0.y + p1.y;
+        } else {        // r_in = 64: a group spans the lane quadrants 2a and 2a + 1
+            const int l0 = lg & ~1;
+            const float2 p0 = sPart[(acc * 8 + l0) * 4], p1 = sPart[(acc * 8 + l0 + 1) * 4];
+            const float2 p2 = sPart[(acc * 8 + 4 + l0) * 4], p3 = sPart[(acc * 8 + 4 + l0 + 1) * 4];
+            S1 = (p0.x + p1.x) + (p2.x + p3.x); S2 = (p0.y + p1.y) + (p2.y + p3.y);
+        }
+        const float mean = S1 * g.gn_inv_n;
+        const float rstd = rsqrtf(fmaxf(S2 * g.gn_inv_n - mean * mean, 0.f) + 1e-5f);
+        // this row in the padded layout: group base + one pad row + inner * N (N = fold * C consecutive halfs)
+        const int64_t rbase = (int64_t)outer * g.gn_ld_group + g.gn_pad_tail + (int64_t)inner * g.N;
+        for (int n0 = col_lo; n0 < col_hi; n0 += 32) {
+            uint32_t r[32];
+            TCG_LD_X32(tmem + lane_base + acc * 256 + n0, r);
+            uint4 rh[4] = {}, rl[4] = {};
+            if (g.gn_res_hi && valid) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    rh[k] = *reinterpret_cast<const uint4*>(g.gn_res_hi + rbase + n0 + k * 8);
+                    rl[k] = *reinterpret_cast<const uint4*>(g.gn_res_lo + rbase + n0 + k * 8);
+                }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {          // 8 columns -> one 16-byte chunk of hi and of lo
+                uint32_t oh[4], ol[4];
+                const uint32_t rhw[4] = {rh[k].x, rh[k].y, rh[k].z, rh[k].w}, rlw[4] = {rl[k].x, rl[k].y, rl[k].z, rl[k].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = (n0 + k * 8 + e * 2) & cmask;
+                    const float2 gm = *reinterpret_cast<const float2*>(sG + c), bt = *reinterpret_cast<const float2*>(sB + c);
+                    float y0 = (__uint_as_float(r[k * 8 + e * 2]) - mean) * rstd * gm.x + bt.x;
+                    float y1 = (__uint_as_float(r[k * 8 + e * 2 + 1]) - mean) * rstd * gm.y + bt.y;
+                    if (g.gn_res_hi && valid) {
+                        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&rhw[e]));
+                        const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&rlw[e]));
+                        y0 += h.x + l.x; y1 += h.y + l.y;
+                    }
+                    if (g.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                    const __half2 hh = __floats2half2_rn(y0, y1);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+                    oh[e] = *reinterpret_cast<const uint32_t*>(&hh); ol[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                const uint32_t so = (uint32_t)lane * 64u + (uint32_t)((k ^ ((lane >> 1) & 3)) * 16);
+                *reinterpret_cast<uint4*>(stg + so) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                *reinterpret_cast<uint4*>(stg + 2048 + so) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            }
+            __syncwarp();
+            // write-out: 4 lanes cover the 64 bytes of one row's chunk, 8 rows per instruction
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + (lane >> 2), k = lane & 3;
+                const int trow = lg * 32 + rr;
+                const int outer_r = tile * g.r_out + (trow >> g.r_in_shift), inner_r = trow & (g.r_in - 1);
+                if (outer_r >= g.n_outer || inner_r >= g.L_inner) continue;
+                const uint32_t so = (uint32_t)rr * 64u + (uint32_t)((k ^ ((rr >> 1) & 3)) * 16);
+                const int64_t o = (int64_t)outer_r * g.gn_ld_group + g.gn_pad_tail + (int64_t)inner_r * g.N + n0 + k * 8;
+                *reinterpret_cast<uint4*>(g.gn_out_hi + o) = *reinterpret_cast<const uint4*>(stg + so);
+                *reinterpret_cast<uint4*>(g.gn_out_lo + o) = *reinterpret_cast<const uint4*>(stg + 2048 + so);
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
+        // zero pad rows (first and last row of every group this warp owns; hi by the first column half's warps, lo by the
+        // second's) and, behind the last group, the rows a K-padded window of the next conv may read
+        {
+            __half* dst = chalf ? g.gn_out_lo : g.gn_out_hi;
+            const int n_slots = g.r_in < 32 ? (32 >> g.r_in_shift) : 1;
+            if (g.r_in <= 32 || !(lg & 1)) {
+                for (int sl = 0; sl < n_slots; ++sl) {
+                    const int og = tile * g.r_out + ((lg * 32) >> g.r_in_shift) + sl;
+                    if (og >= g.n_outer) break;
+                    uint32_t* z0 = reinterpret_cast<uint32_t*>(dst + (int64_t)og * g.gn_ld_group);
+                    uint32_t* z1 = reinterpret_cast<uint32_t*>(dst + (int64_t)(og + 1) * g.gn_ld_group - g.gn_pad_tail);
+                    for (int c2 = lane; c2 < (g.gn_pad_tail >> 1); c2 += 32) { z0[c2] = 0u; z1[c2] = 0u; }
+                    if (og == g.n_outer - 1) {
+                        uint32_t* zt = reinterpret_cast<uint32_t*>(dst + (int64_t)g.n_outer * g.gn_ld_group);
+                        for (int c2 = lane; c2 < 2 * g.gn_pad_tail; c2 += 32) zt[c2] = 0u;
+                    }
+                }
+            }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
@@ -243,6 +386,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUt
                 }
             }
         }
+    } else if (g.gn) {
+        gn_epilogue(g, sgen, bars, tmem, total_tiles, warp, lane);
     } else {
         int acc = 0; uint32_t acc_phase = 0;
         const int lg = warp & 3;                       // TMEM lane quadrant (warp id mod 4)
@@ -547,6 +692,14 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
     g.C = p.C; g.ldc = p.ldc; g.c_last = p.c_last_only; g.Chi = p.Chi; g.Clo = p.Clo; g.ldh = p.ldh; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
     g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
+    g.gn = p.gn_out_hi ? 1 : 0;
+    g.gn_gamma = p.gn_gamma; g.gn_beta = p.gn_beta; g.gn_C = p.gn_C; g.gn_inv_n = p.gn_inv_n;
+    g.gn_res_hi = p.gn_res_hi; g.gn_res_lo = p.gn_res_lo; g.gn_out_hi = p.gn_out_hi; g.gn_out_lo = p.gn_out_lo;
+    g.gn_ld_group = p.gn_ld_group; g.gn_pad_tail = p.gn_C;
+    if (g.gn) {
+        if (g.tiles_inner != 1 || g.tiles_n != 1 || p.n_tile < 64 || p.n_tile != p.N || (p.gn_C & (p.gn_C - 1)) || p.gn_C > 256 || p.r_in > 64)
+            return "tc_gemm: GroupNorm epilogue needs whole groups per tile, one column tile of 64..256 and a power-of-two channel count";
+    }
     const int nkb_w = (p.split ? 2 : 1) * p.k_blocks;
     g.res_w_bytes = (uint32_t)nkb_w * (uint32_t)p.n_tile * 128u;
     g.w_resident = (g.tiles_n == 1 && (int64_t)nkb_w * p.n_tile * 128 <= (int64_t)tcg::RES_W_MAX) ? 1 : 0;

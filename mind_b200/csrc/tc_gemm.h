@@ -23,6 +23,12 @@ struct TcGemm {
     const float* gbias = nullptr; int gsize = 1, ldg = 0;   // per row-group bias [(row / gsize), N]
     float* stats = nullptr;          // [n_outer][ceil(L_inner / r_in)][2 column halves][2] partial (sum, sum^2) or null
     int* err = nullptr;
+    // GroupNorm(1 group over an outer group's L_inner x N outputs) + shortcut + ReLU in the epilogue, output as the padded
+    // fp16 (hi, lo) operand [n_outer][(L + 2) * C] of the next conv (set gn_out_hi; needs r_in >= L_inner: whole groups per tile)
+    const float* gn_gamma = nullptr; const float* gn_beta = nullptr; int gn_C = 0; float gn_inv_n = 0.f;
+    const __half* gn_res_hi = nullptr; const __half* gn_res_lo = nullptr;
+    __half* gn_out_hi = nullptr; __half* gn_out_lo = nullptr;
+    int64_t gn_ld_group = 0;
 };
 
 const char* tcg_encode_a(void* map, const __half* base, int64_t k_extent, int64_t inner, int64_t outer,
@@ -55,6 +61,7 @@ struct ActorTc {
     std::map<std::string, const float*> vec;     // GN affine parameters (device fp32, owned by the ctx arena)
     int* d_err = nullptr;
     bool ready = false;
+    bool gn_fused = true;      // GroupNorm of bn1 / identity-shortcut bn2 in the conv GEMM's epilogue (false: separate apply pass)
 };
 // host fp32 weights by reference key -> packed device copies
 const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<float>>& host,
