@@ -13,15 +13,19 @@ st = bench["stage_ms_per_step"]
 # ---- launch list ----
 rows = [r for r in csv.reader(open(os.path.join(G, "launches_%s.csv" % R))) if len(r) > 10]
 h = rows[0]; ik, iv = h.index("Kernel Name"), h.index("Metric Value")
+# window = the last forward of the run: from its k_actor_prep launch to the end of the list
+body = rows[1:]
+starts = [i for i, r in enumerate(body) if "k_actor_prep" in r[ik]]
+body = body[starts[-1]:] if starts else body
 agg = collections.OrderedDict()
-for r in rows[1:]:
+for r in body:
     k = r[ik].split("(")[0].replace("mind::", "")
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += float(r[iv].replace(",", "")) / 1e3
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(P, "%s_launches_summary.md" % R), "w") as f:
     f.write("# ncu launch list of ONE forward (B=256, 32x128, f16tc), build %s; cold-cache serialized times: compare shares\n\n" % R)
-    f.write("command: ncu --metrics gpu__time_duration.sum --clock-control none -s 125 -c 125 --csv python bench.py --steps 1 --warmup 1 --kernel-only\n")
-    f.write("(window = the 125 launches of the timed forward)\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
+    f.write("command: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 1 --warmup 1 --kernel-only\n")
+    f.write("(window = the %d launches of the timed forward: from its k_actor_prep to k_bezier)\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n" % len(body))
     for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, a[0], a[1], 100 * a[1] / tot))
     fus = st.get("fusion_tc", 0) + st.get("fusion_tc_last", 0)
@@ -83,10 +87,10 @@ with open(os.path.join(P, "%s_fusion_tc_ncu_full.md" % R), "w") as f:
         table(f, ml)
     f.write("\nSASS (cuobjdump -sass mind_b200/libmind_b200.so): UTCHMMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA), SYNCS (mbarrier), FFMA2 / FADD2 (packed fp32), BAR.ARV / BAR.SYNC (named-barrier hand-offs), ELECT.\n")
 # ---- the other kernels of the step ----
-others = [("gemm_actor", "tcg::k_tc_gemm, an ActorNet conv GEMM (3-term fp16 split)"), ("gemm_lane", "tcg::k_tc_gemm, a LaneNet 128x128 linear over 330k rows (3-term)"),
+others = [("gemm_actor", "tcg::k_tc_gemm, an ActorNet conv GEMM (3-term fp16 split) with the GroupNorm epilogue (group 3, N = 256)"), ("gemm_lane", "tcg::k_tc_gemm, a LaneNet 128x128 linear over 330k rows (3-term)"),
           ("lane_chain", "lane::k_lane_net_tc (the whole LaneNet on chip, 33k polylines)"),
           ("node_chain", "node::k_node_chain_tc (out-proj + LN2 + FFN + LN3 + next layer's S|T|q, 41k token rows)"),
-          ("edge_init", "edge init (5 -> 128 + LN + ReLU, writes the fp16 edge stream: 1.70 GB)"), ("gn_apply", "tcg::k_gn_apply (GroupNorm + shortcut + ReLU + hi/lo re-split)"),
+          ("edge_init", "k_edge_init_ch: edge init (5 -> 128 + closed-form LN + ReLU, writes the fp16 edge stream: 1.70 GB)"), ("gn_apply", "tcg::k_gn_apply (lateral GroupNorm + FPN top-down step -> fp16 hi/lo, finest level)"),
           ("node_fields", "k_node_fields (cost fields of the trajectory-tree optimiser, fp64)")]
 with open(os.path.join(P, "%s_other_kernels_ncu_full.md" % R), "w") as f:
     f.write("# ncu --set full of the kernels next to the fused layer (build %s, B=256 benchmark step; cost fields: demo_2 trees)\n\n" % R)
