@@ -67,7 +67,9 @@ int mind_finalize_weights(MindCtx* ctx);
  * captured CUDA graph when batch shape + pointers repeat), "tc_min_tokens" (MIND_PREC_F16TC only, default 128: scenes with
  * fewer tokens than this run the exact tier -- every N^2 contraction as a 3-term fp16 hi/lo tcgen05 product, fp32 edge --
  * instead of the fp16-operand fused kernel, whose operand rounding is not averaged out over a small scene's few keys;
- * 0 = fused kernel for every scene) */
+ * 0 = fused kernel for every scene).  Diagnostic switches that select the un-fused comparator of a stage (each parity-tested
+ * against the default): "lane_unfused", "node_unfused", "actor_gn_unfused" (GroupNorm as a separate pass behind every ActorNet
+ * conv GEMM), "decoder_simt" (decoder linears on the fp32 SIMT GEMM), "actor_simt" (one-CTA-per-actor fp32 ActorNet). */
 int mind_set_option(MindCtx* ctx, const char* name, int64_t value);
 
 /* ---- one batched forward:  network(data_in)   planners/mind/networks/network.py:582-595 ----

@@ -308,3 +308,40 @@ def test_token_side_chain_kernel_matches_the_launch_by_launch_path(ckpt_sd, dev)
     torch.cuda.synchronize()
     for x, y in zip(*outs):
         assert rel_err(x, y) < 2e-5
+
+
+@pytest.mark.parametrize("n_actor", [1, 2, 3, 15, 16, 17, 33])
+def test_actor_net_groupnorm_epilogue_matches_the_separate_pass(ckpt_sd, dev, n_actor):
+    """GroupNorm (+ shortcut, ReLU) in the conv GEMM's epilogue (whole actors per 128-row tile: 2 / 4 / 8 / 16 actors per tile
+    depending on the group) vs the separate k_gn_apply pass behind every GEMM and vs the oracle, for actor counts around
+    the tile boundaries (part-filled tiles, out-of-bounds actors)."""
+    from mind_b200 import synth
+    from oracle import scene_pred_oracle as O
+    data = synth.batch_from_scenes([synth.scene_s1(700 + n_actor, n_actor, 7)])
+    want = O.actor_net(data[0].float(), O.Params({k: v.float() for k, v in ckpt_sd.items()}).sub("actor_net."))
+    taps = []
+    for unfused in (0, 1):
+        net = make_net(ckpt_sd, dev, "f16tc")
+        net.set_option("actor_gn_unfused", unfused)
+        net(to_dev(data, dev))
+        taps.append(net.debug_tap("actor_feat", n_actor * 128).view(n_actor, 128).clone())
+        net.sync_check()
+    torch.cuda.synchronize()
+    assert rel_err(taps[0], want) < 2e-5 and rel_err(taps[1], want) < 2e-5
+    assert rel_err(taps[0], taps[1]) < 1e-5
+
+
+def test_decoder_tensor_core_linears_match_the_simt_path(ckpt_sd, dev):
+    """actor_proj / reg head as 3-term tcgen05 products vs the fp32 SIMT GEMMs: fp32-equivalent, ragged batch."""
+    from mind_b200 import synth
+    data = synth.batch_from_scenes([synth.scene_s1(960 + i, na, nl) for i, (na, nl) in enumerate([(5, 20), (32, 128), (1, 3), (23, 9)])])
+    outs = []
+    for simt in (0, 1):
+        net = make_net(ckpt_sd, dev, "f16tc")
+        net.set_option("decoder_simt", simt)
+        p = net.forward_packed(to_dev(data, dev))
+        net.sync_check()
+        outs.append([t.clone() for t in p[:5]])
+    torch.cuda.synchronize()
+    for x, y in zip(*outs):
+        assert rel_err(x, y) < 2e-5
