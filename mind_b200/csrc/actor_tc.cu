@@ -132,7 +132,11 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
     };
     // conv over a padded channel-last input [A][Lin+2][Cin_pad]: output raw [A*Lout][Cout] + stats
     // gn != nullptr: GroupNorm (+ identity shortcut) (+ ReLU) in the GEMM epilogue, output = padded (hi, lo) operand `gn_out`
-    struct Gn { std::string key; int relu; HL out; const HL* res; };
+    struct Gn {
+        std::string key; int relu; HL out; const HL* res;
+        const float* res_raw = nullptr; const float* res_stats = nullptr; std::string res_key;   // second GroupNorm'd input (conv shortcut)
+        const float* up_prev = nullptr; float* out_f32 = nullptr;                                // FPN step / fp32 output
+    };
     auto conv = [&](const std::string& key, HL in, int Lin, int stride, float* raw, float* stats, int last_only = 0,
                     const Gn* gn = nullptr) {
         if (err) return;
@@ -163,6 +167,11 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
             g.gn_inv_n = 1.f / (float)(Lout * cv.Cout); g.relu = gn->relu;
             g.gn_out_hi = gn->out.hi; g.gn_out_lo = gn->out.lo; g.gn_ld_group = (int64_t)(Lout + 2) * cv.Cout;
             if (gn->res) { g.gn_res_hi = gn->res->hi; g.gn_res_lo = gn->res->lo; }
+            if (gn->res_raw) {
+                g.gn_res_raw = gn->res_raw; g.gn_res_stats = gn->res_stats;
+                g.gn_res_gamma = V(gn->res_key + ".weight"); g.gn_res_beta = V(gn->res_key + ".bias");
+            }
+            g.gn_up_prev = gn->up_prev; g.gn_out_f32 = gn->out_f32;
             if (err) return;
         }
         err = tcg_launch(g, sm_count, st);
@@ -200,9 +209,15 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
             conv(P + "0.conv1.weight", cur, L, stride, b.raw1, b.st1);
             apply(b.raw1, b.st1, P + "0.bn1", Lo, C, 1, b.t0, nullptr);
         }
-        conv(P + "0.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
         conv(P + "0.downsample.0.weight", cur, L, stride, b.raw3, b.st3);
-        apply(b.raw2, b.st2, P + "0.bn2", Lo, C, 1, b.t1, nullptr, b.raw3, b.st3, P + "0.downsample.1");
+        if (a.gn_fused) {      // bn2 + GroupNorm of the down-sampled shortcut (its raw output and statistics) + ReLU in conv2's epilogue
+            Gn g2{P + "0.bn2", 1, b.t1, nullptr};
+            g2.res_raw = b.raw3; g2.res_stats = b.st3; g2.res_key = P + "0.downsample.1";
+            conv(P + "0.conv2.weight", b.t0, Lo, 1, nullptr, nullptr, 0, &g2);
+        } else {
+            conv(P + "0.conv2.weight", b.t0, Lo, 1, b.raw2, b.st2);
+            apply(b.raw2, b.st2, P + "0.bn2", Lo, C, 1, b.t1, nullptr, b.raw3, b.st3, P + "0.downsample.1");
+        }
         // block 1 (identity shortcut): both GroupNorms in the epilogues
         if (a.gn_fused) {
             const Gn g1{P + "1.bn1", 1, b.t0, nullptr}, g2{P + "1.bn2", 1, b.o[g], &b.t1};
@@ -219,17 +234,31 @@ const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float
     }
     // FPN top-down
     const int Ls[4] = {48, 24, 12, 6};
-    conv("actor_net.lateral.3.conv.weight", b.o[3], 6, 1, b.raw1, b.st1);
-    apply(b.raw1, b.st1, "actor_net.lateral.3.norm", 6, 128, 0, none, b.pyr0);
     float* pyr = b.pyr0; float* nxt = b.pyr1;
-    for (int i = 2; i >= 0 && !err; --i) {      // lateral GroupNorm and the top-down step (:57-58) in one pass over the conv output
-        char p[64];
-        snprintf(p, sizeof p, "actor_net.lateral.%d", i);
-        conv(std::string(p) + ".conv.weight", b.o[i], Ls[i], 1, b.raw1, b.st1);
-        // the finest level is only read as the (hi, lo) input / shortcut of the output block
-        apply(b.raw1, b.st1, std::string(p) + ".norm", Ls[i], 128, 0, i == 0 ? b.p : none, i == 0 ? nullptr : nxt,
-              nullptr, nullptr, "", nullptr, pyr);
-        float* t = pyr; pyr = nxt; nxt = t;
+    if (a.gn_fused) {           // lateral GroupNorm and the top-down step (:57-58) in the lateral conv's epilogue
+        Gn g3{"actor_net.lateral.3.norm", 0, none, nullptr};
+        g3.out_f32 = b.pyr0;
+        conv("actor_net.lateral.3.conv.weight", b.o[3], 6, 1, nullptr, nullptr, 0, &g3);
+        for (int i = 2; i >= 0 && !err; --i) {
+            char p[64];
+            snprintf(p, sizeof p, "actor_net.lateral.%d", i);
+            // the finest level is only read as the (hi, lo) input / shortcut of the output block
+            Gn gl{std::string(p) + ".norm", 0, i == 0 ? b.p : none, nullptr};
+            gl.up_prev = pyr; gl.out_f32 = i == 0 ? nullptr : nxt;
+            conv(std::string(p) + ".conv.weight", b.o[i], Ls[i], 1, nullptr, nullptr, 0, &gl);
+            float* t = pyr; pyr = nxt; nxt = t;
+        }
+    } else {
+        conv("actor_net.lateral.3.conv.weight", b.o[3], 6, 1, b.raw1, b.st1);
+        apply(b.raw1, b.st1, "actor_net.lateral.3.norm", 6, 128, 0, none, b.pyr0);
+        for (int i = 2; i >= 0 && !err; --i) {      // lateral GroupNorm and the top-down step (:57-58) in one pass over the conv output
+            char p[64];
+            snprintf(p, sizeof p, "actor_net.lateral.%d", i);
+            conv(std::string(p) + ".conv.weight", b.o[i], Ls[i], 1, b.raw1, b.st1);
+            apply(b.raw1, b.st1, std::string(p) + ".norm", Ls[i], 128, 0, i == 0 ? b.p : none, i == 0 ? nullptr : nxt,
+                  nullptr, nullptr, "", nullptr, pyr);
+            float* t = pyr; pyr = nxt; nxt = t;
+        }
     }
     // output Res1d(128,128), identity shortcut = the pyramid top.  Only its last time step leaves ActorNet (:60), but both
     // GroupNorms take their statistics over all 48: conv2 runs in full, stores row 47 only, and is normalised there

@@ -29,8 +29,8 @@ constexpr uint32_t STG_WARP = 32 * STG_STRIDE * 4;
 constexpr uint32_t SM_STG = RING_BYTES;
 constexpr uint32_t SM_BAR = SM_STG + 8 * STG_WARP;
 constexpr uint32_t SM_TMEM = SM_BAR + 192;
-constexpr uint32_t SM_GN = SM_TMEM + 16;             // GroupNorm epilogue: gamma | beta (2 x 256 floats), partial sums float2 [2 acc][8 warps][4 slots]
-constexpr uint32_t SMEM_BYTES = SM_GN + 2048 + 512 + 1024;
+constexpr uint32_t SM_GN = SM_TMEM + 16;             // GroupNorm epilogue: gamma | beta | gamma2 | beta2 (4 x 256 floats), partial sums float2 [2 acc][8 warps][4 slots]
+constexpr uint32_t SMEM_BYTES = SM_GN + 4096 + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,6 +133,11 @@ struct Args {
     __half* gn_out_hi; __half* gn_out_lo;
     int64_t gn_ld_group;                                         // halfs per group in the padded layout: (L + 2) * C
     int gn_pad_tail;                                             // halfs of the last padded row: C
+    // second GroupNorm'd input (the conv shortcut of a block's first Res1d): raw fp32 [group][L_inner][N] of another GEMM and
+    // its statistics in that GEMM's `stats` layout (3 inner tiles x 2 column halves)
+    const float* gn_res_raw; const float* gn_res_stats; const float* gn_res_gamma; const float* gn_res_beta;
+    const float* gn_up_prev;                                     // FPN top-down step: + linear x2 upsampling of [group][L/2][C] fp32
+    float* gn_out_f32;                                           // fp32 output [group][L_inner][N] instead of the (hi, lo) operand
 };
 
 // Epilogue of the GroupNorm mode (8 epilogue warps; warp w: TMEM lane quadrant lg = w & 3, column half (w - 2) >> 2).
@@ -143,8 +148,13 @@ struct Args {
 __device__ __forceinline__ void gn_epilogue(const Args& g, uint8_t* sgen, uint32_t bars, uint32_t tmem, int total_tiles, int warp, int lane) {
     float* sG = reinterpret_cast<float*>(sgen + SM_GN);
     float* sB = sG + 256;
-    float2* sPart = reinterpret_cast<float2*>(sgen + SM_GN + 2048);
-    for (int i = (int)threadIdx.x - 64; i < g.gn_C; i += 256) { sG[i] = g.gn_gamma[i]; sB[i] = g.gn_beta[i]; }
+    float* sG2 = sG + 512;
+    float* sB2 = sG + 768;
+    float2* sPart = reinterpret_cast<float2*>(sgen + SM_GN + 4096);
+    for (int i = (int)threadIdx.x - 64; i < g.gn_C; i += 256) {
+        sG[i] = g.gn_gamma[i]; sB[i] = g.gn_beta[i];
+        if (g.gn_res_raw) { sG2[i] = g.gn_res_gamma[i]; sB2[i] = g.gn_res_beta[i]; }
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     int acc = 0; uint32_t acc_phase = 0;
     const int ew = warp - 2, lg = warp & 3, chalf = ew >> 2;
@@ -189,6 +199,22 @@ __device__ __forceinline__ void gn_epilogue(const Args& g, uint8_t* sgen, uint32
         const float rstd = rsqrtf(fmaxf(S2 * g.gn_inv_n - mean * mean, 0.f) + 1e-5f);
         // this row in the padded layout: group base + one pad row + inner * N (N = fold * C consecutive halfs)
         const int64_t rbase = (int64_t)outer * g.gn_ld_group + g.gn_pad_tail + (int64_t)inner * g.N;
+        const int64_t frow = ((int64_t)outer * g.L_inner + inner) * g.N;          // the same row in an unpadded fp32 [group][L_inner][N] tensor
+        float m2 = 0.f, rstd2 = 0.f;
+        if (g.gn_res_raw && valid) {          // statistics of the second input: partial sums in the other GEMM's layout, fixed order
+            const float* q = g.gn_res_stats + (int64_t)outer * 12;
+            m2 = (((q[0] + q[2]) + (q[4] + q[6])) + (q[8] + q[10])) * g.gn_inv_n;
+            rstd2 = rsqrtf(fmaxf((((q[1] + q[3]) + (q[5] + q[7])) + (q[9] + q[11])) * g.gn_inv_n - m2 * m2, 0.f) + 1e-5f);
+        }
+        const float* up0 = nullptr; const float* up1 = nullptr; float lam = 0.f;
+        if (g.gn_up_prev && valid) {          // interpolate(scale 2, linear, align_corners = False) source rows of this step
+            const int Lp = g.L_inner >> 1;
+            const float src = fmaxf(((float)inner + 0.5f) * 0.5f - 0.5f, 0.f);
+            const int i0 = (int)floorf(src), i1 = min(i0 + 1, Lp - 1);
+            lam = src - (float)i0;
+            up0 = g.gn_up_prev + ((int64_t)outer * Lp + i0) * g.N;
+            up1 = g.gn_up_prev + ((int64_t)outer * Lp + i1) * g.N;
+        }
         for (int n0 = col_lo; n0 < col_hi; n0 += 32) {
             uint32_t r[32];
             TCG_LD_X32(tmem + lane_base + acc * 256 + n0, r);
@@ -202,42 +228,84 @@ __device__ __forceinline__ void gn_epilogue(const Args& g, uint8_t* sgen, uint32
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {          // 8 columns -> one 16-byte chunk of hi and of lo
-                uint32_t oh[4], ol[4];
+            for (int k = 0; k < 4; ++k) {          // 8 columns -> one 16-byte chunk of hi and of lo (or two of fp32)
+                float y[8];
                 const uint32_t rhw[4] = {rh[k].x, rh[k].y, rh[k].z, rh[k].w}, rlw[4] = {rl[k].x, rl[k].y, rl[k].z, rl[k].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int c = (n0 + k * 8 + e * 2) & cmask;
                     const float2 gm = *reinterpret_cast<const float2*>(sG + c), bt = *reinterpret_cast<const float2*>(sB + c);
-                    float y0 = (__uint_as_float(r[k * 8 + e * 2]) - mean) * rstd * gm.x + bt.x;
-                    float y1 = (__uint_as_float(r[k * 8 + e * 2 + 1]) - mean) * rstd * gm.y + bt.y;
+                    y[e * 2] = (__uint_as_float(r[k * 8 + e * 2]) - mean) * rstd * gm.x + bt.x;
+                    y[e * 2 + 1] = (__uint_as_float(r[k * 8 + e * 2 + 1]) - mean) * rstd * gm.y + bt.y;
                     if (g.gn_res_hi && valid) {
                         const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&rhw[e]));
                         const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&rlw[e]));
-                        y0 += h.x + l.x; y1 += h.y + l.y;
+                        y[e * 2] += h.x + l.x; y[e * 2 + 1] += h.y + l.y;
                     }
-                    if (g.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-                    const __half2 hh = __floats2half2_rn(y0, y1);
-                    const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
-                    oh[e] = *reinterpret_cast<const uint32_t*>(&hh); ol[e] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
-                const uint32_t so = (uint32_t)lane * 64u + (uint32_t)((k ^ ((lane >> 1) & 3)) * 16);
-                *reinterpret_cast<uint4*>(stg + so) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                *reinterpret_cast<uint4*>(stg + 2048 + so) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                if (g.gn_res_raw && valid) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(g.gn_res_raw + frow + n0 + k * 8);
+                    const float4 a1 = *reinterpret_cast<const float4*>(g.gn_res_raw + frow + n0 + k * 8 + 4);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = (n0 + k * 8 + e) & cmask;
+                        y[e] += (av[e] - m2) * rstd2 * sG2[c] + sB2[c];
+                    }
+                }
+                if (up0) {
+                    const float4 p0 = *reinterpret_cast<const float4*>(up0 + n0 + k * 8), p1 = *reinterpret_cast<const float4*>(up1 + n0 + k * 8);
+                    const float4 p2 = *reinterpret_cast<const float4*>(up0 + n0 + k * 8 + 4), p3 = *reinterpret_cast<const float4*>(up1 + n0 + k * 8 + 4);
+                    const float u0[8] = {p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p2.z, p2.w}, u1[8] = {p1.x, p1.y, p1.z, p1.w, p3.x, p3.y, p3.z, p3.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = u0[e] * (1.f - lam) + u1[e] * lam + y[e];
+                }
+                if (g.relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+                }
+                if (g.gn_out_f32) {
+                    *reinterpret_cast<float4*>(stg + (uint32_t)lane * 128u + (uint32_t)(((2 * k) ^ (lane & 7)) * 16)) = make_float4(y[0], y[1], y[2], y[3]);
+                    *reinterpret_cast<float4*>(stg + (uint32_t)lane * 128u + (uint32_t)(((2 * k + 1) ^ (lane & 7)) * 16)) = make_float4(y[4], y[5], y[6], y[7]);
+                } else {
+                    uint32_t oh[4], ol[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 hh = __floats2half2_rn(y[e * 2], y[e * 2 + 1]);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(y[e * 2] - hf.x, y[e * 2 + 1] - hf.y);
+                        oh[e] = *reinterpret_cast<const uint32_t*>(&hh); ol[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    const uint32_t so = (uint32_t)lane * 64u + (uint32_t)((k ^ ((lane >> 1) & 3)) * 16);
+                    *reinterpret_cast<uint4*>(stg + so) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                    *reinterpret_cast<uint4*>(stg + 2048 + so) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                }
             }
             __syncwarp();
-            // write-out: 4 lanes cover the 64 bytes of one row's chunk, 8 rows per instruction
+            if (g.gn_out_f32) {
+                // write-out: 8 lanes cover the 128 bytes of one row's chunk, 4 rows per instruction
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int rr = it * 8 + (lane >> 2), k = lane & 3;
-                const int trow = lg * 32 + rr;
-                const int outer_r = tile * g.r_out + (trow >> g.r_in_shift), inner_r = trow & (g.r_in - 1);
-                if (outer_r >= g.n_outer || inner_r >= g.L_inner) continue;
-                const uint32_t so = (uint32_t)rr * 64u + (uint32_t)((k ^ ((rr >> 1) & 3)) * 16);
-                const int64_t o = (int64_t)outer_r * g.gn_ld_group + g.gn_pad_tail + (int64_t)inner_r * g.N + n0 + k * 8;
-                *reinterpret_cast<uint4*>(g.gn_out_hi + o) = *reinterpret_cast<const uint4*>(stg + so);
-                *reinterpret_cast<uint4*>(g.gn_out_lo + o) = *reinterpret_cast<const uint4*>(stg + 2048 + so);
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+                    const int trow = lg * 32 + rr;
+                    const int outer_r = tile * g.r_out + (trow >> g.r_in_shift), inner_r = trow & (g.r_in - 1);
+                    if (outer_r >= g.n_outer || inner_r >= g.L_inner) continue;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + (uint32_t)rr * 128u + (uint32_t)((ch ^ (rr & 7)) * 16));
+                    *reinterpret_cast<float4*>(g.gn_out_f32 + ((int64_t)outer_r * g.L_inner + inner_r) * g.N + n0 + ch * 4) = v;
+                }
+            } else {
+                // write-out: 4 lanes cover the 64 bytes of one row's chunk, 8 rows per instruction
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = it * 8 + (lane >> 2), k = lane & 3;
+                    const int trow = lg * 32 + rr;
+                    const int outer_r = tile * g.r_out + (trow >> g.r_in_shift), inner_r = trow & (g.r_in - 1);
+                    if (outer_r >= g.n_outer || inner_r >= g.L_inner) continue;
+                    const uint32_t so = (uint32_t)rr * 64u + (uint32_t)((k ^ ((rr >> 1) & 3)) * 16);
+                    const int64_t o = (int64_t)outer_r * g.gn_ld_group + g.gn_pad_tail + (int64_t)inner_r * g.N + n0 + k * 8;
+                    *reinterpret_cast<uint4*>(g.gn_out_hi + o) = *reinterpret_cast<const uint4*>(stg + so);
+                    *reinterpret_cast<uint4*>(g.gn_out_lo + o) = *reinterpret_cast<const uint4*>(stg + 2048 + so);
+                }
             }
             __syncwarp();
         }
@@ -246,7 +314,7 @@ __device__ __forceinline__ void gn_epilogue(const Args& g, uint8_t* sgen, uint32
         if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
         // zero pad rows (first and last row of every group this warp owns; hi by the first column half's warps, lo by the
         // second's) and, behind the last group, the rows a K-padded window of the next conv may read
-        {
+        if (!g.gn_out_f32) {
             __half* dst = chalf ? g.gn_out_lo : g.gn_out_hi;
             const int n_slots = g.r_in < 32 ? (32 >> g.r_in_shift) : 1;
             if (g.r_in <= 32 || !(lg & 1)) {
@@ -692,7 +760,9 @@ const char* tcg_launch(const TcGemm& p, int sm_count, cudaStream_t st) {
     g.N = p.N; g.n_tile = p.n_tile; g.tiles_n = (p.N + p.n_tile - 1) / p.n_tile;
     g.C = p.C; g.ldc = p.ldc; g.c_last = p.c_last_only; g.Chi = p.Chi; g.Clo = p.Clo; g.ldh = p.ldh; g.bias = p.bias; g.relu = p.relu; g.stats = p.stats; g.err = p.err;
     g.gbias = p.gbias; g.gsize = p.gsize > 0 ? p.gsize : 1; g.ldg = p.ldg;
-    g.gn = p.gn_out_hi ? 1 : 0;
+    g.gn = (p.gn_out_hi || p.gn_out_f32) ? 1 : 0;
+    g.gn_res_raw = p.gn_res_raw; g.gn_res_stats = p.gn_res_stats; g.gn_res_gamma = p.gn_res_gamma; g.gn_res_beta = p.gn_res_beta;
+    g.gn_up_prev = p.gn_up_prev; g.gn_out_f32 = p.gn_out_f32;
     g.gn_gamma = p.gn_gamma; g.gn_beta = p.gn_beta; g.gn_C = p.gn_C; g.gn_inv_n = p.gn_inv_n;
     g.gn_res_hi = p.gn_res_hi; g.gn_res_lo = p.gn_res_lo; g.gn_out_hi = p.gn_out_hi; g.gn_out_lo = p.gn_out_lo;
     g.gn_ld_group = p.gn_ld_group; g.gn_pad_tail = p.gn_C;

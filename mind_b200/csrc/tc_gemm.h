@@ -29,6 +29,10 @@ struct TcGemm {
     const __half* gn_res_hi = nullptr; const __half* gn_res_lo = nullptr;
     __half* gn_out_hi = nullptr; __half* gn_out_lo = nullptr;
     int64_t gn_ld_group = 0;
+    const float* gn_res_raw = nullptr; const float* gn_res_stats = nullptr;      // second GroupNorm'd input: raw output + `stats` of another GEMM
+    const float* gn_res_gamma = nullptr; const float* gn_res_beta = nullptr;
+    const float* gn_up_prev = nullptr;     // + linear x2 upsampling of the coarser FPN level [n_outer][L/2][N] (fp32)
+    float* gn_out_f32 = nullptr;           // fp32 output [n_outer][L][N] instead of the (hi, lo) operand
 };
 
 const char* tcg_encode_a(void* map, const __half* base, int64_t k_extent, int64_t inner, int64_t outer,
