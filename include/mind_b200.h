@@ -266,6 +266,15 @@ int mind_tc_selftest(const float* A_host, const float* W_host, float* D_host);
 int mind_debug_fusion_schedule(const int32_t* n_tokens, int32_t n_scenes, int32_t sm_count, int32_t* work,
                                int32_t capacity, int32_t* info);
 
+/* Host-only diagnostic (no device needed): the parameter tables the fp16 edge-init kernel is driven by, from the four
+ * tensors of fusion_net.proj_rpe_scene (Linear(5,128) + LayerNorm(128) + ReLU, planners/mind/networks/network.py:282-286,
+ * 326-330).  quad21 = {c0, L[5], Q upper triangle by rows with doubled off-diagonals}: LayerNorm variance of the
+ * projection as a quadratic form of the 5 RPE values; tab896 = [32 lanes][2 channel pairs][7][2]: gamma * centred W (5),
+ * gamma * centred b, beta of channels 4*lane + 2*pair + {0,1}.  With rstd = rsqrt(var + 1e-5) the layer's pre-ReLU output
+ * is  y[c] = sum_k tab[c][k] * rstd * r[k] + tab[c][5] * rstd + tab[c][6]. */
+int mind_debug_edge_init_pack(const float* W, const float* b, const float* gamma, const float* beta, float* tab896,
+                              float* quad21);
+
 /* cudaDeviceSynchronize + kernel-side protocol error flag (0 = clean) */
 int mind_sync_check(MindCtx* ctx);
 

@@ -1229,6 +1229,13 @@ extern "C" int mind_tc_selftest(const float* A_host, const float* W_host, float*
     return 0;
 }
 
+extern "C" int mind_debug_edge_init_pack(const float* W, const float* b, const float* gamma, const float* beta, float* tab896,
+                                         float* quad21) {
+    if (!W || !b || !gamma || !beta || !tab896 || !quad21) return fail("mind_debug_edge_init_pack: null argument");
+    edge_init_pack_ch(W, b, gamma, beta, tab896, quad21);
+    return 0;
+}
+
 extern "C" int mind_debug_fusion_schedule(const int32_t* n_tokens, int32_t B, int32_t sm_count, int32_t* work_out,
                                           int32_t capacity, int32_t* info) {
     if (!n_tokens || B <= 0 || sm_count <= 0 || !info) return fail("mind_debug_fusion_schedule: bad argument");
