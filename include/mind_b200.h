@@ -275,6 +275,14 @@ int mind_debug_fusion_schedule(const int32_t* n_tokens, int32_t n_scenes, int32_
 int mind_debug_edge_init_pack(const float* W, const float* b, const float* gamma, const float* beta, float* tab896,
                               float* quad21);
 
+/* Host-only diagnostic: the GEMM operand the ActorNet conv engine uses for a Conv1d weight [Cout][Cin][ks] (padding ks/2,
+ * planners/mind/networks/layers.py:36-60) when `fold` consecutive output steps share one GEMM row: out receives
+ * [fold*Cout][Kpad] fp32 (capacity in floats; Kpad is returned, or -1 if capacity is too small / arguments are bad).
+ * GEMM row p, column u*Cout + o = sum over the row's window (padded input rows fold*p*stride ..., Cin_pad channels each) =
+ * output channel o at step fold*p + u. */
+int mind_debug_conv_fold_pack(const float* w, int32_t Cout, int32_t Cin, int32_t Cin_pad, int32_t ksize, int32_t stride,
+                              int32_t fold, float* out, int64_t capacity);
+
 /* cudaDeviceSynchronize + kernel-side protocol error flag (0 = clean) */
 int mind_sync_check(MindCtx* ctx);
 

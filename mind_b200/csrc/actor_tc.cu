@@ -50,6 +50,22 @@ char g_aerr[256];
 
 int64_t actor_tc_ws_bytes(int A) { Bufs b; return carve(nullptr, std::max(A, 1), b); }
 
+// Conv weight [Cout][Cin][ks] -> GEMM operand [fold*Cout][Kpad] (fp32; Kpad = taps*Cin_pad rounded up to 64, taps =
+// (fold-1)*stride + ks): row u*Cout + o produces output step fold*p + u of GEMM row p from the window of `taps` padded input
+// rows that starts at row fold*p*stride, so its weights sit at taps u*stride + k, zero elsewhere.  fold = 1 is the plain
+// im2col layout.  Host only (also behind mind_debug_conv_fold_pack for the CPU test).
+int actor_tc_fold_weights(const float* w, int Cout, int Cin, int Cin_pad, int ks, int stride, int fold, std::vector<float>& out) {
+    const int taps = (fold - 1) * stride + ks;
+    const int Kpad = ((taps * Cin_pad + 63) / 64) * 64;
+    out.assign((size_t)fold * Cout * Kpad, 0.f);
+    for (int u = 0; u < fold; ++u)
+        for (int o = 0; o < Cout; ++o)
+            for (int i = 0; i < Cin; ++i)
+                for (int k = 0; k < ks; ++k)
+                    out[((size_t)u * Cout + o) * Kpad + (size_t)(u * stride + k) * Cin_pad + i] = w[((size_t)o * Cin + i) * ks + k];
+    return Kpad;
+}
+
 void actor_tc_free(ActorTc& a) {
     for (auto& kv : a.conv) if (kv.second.W) cudaFree(kv.second.W);
     a.conv.clear();
@@ -69,20 +85,17 @@ const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<fl
         if (it == host.end() || it->second.size() != (size_t)Cout * Cin * ks) return "actor_tc_pack: missing / mis-sized conv weight";
         ActorTcConv cv;
         cv.Cout = Cout; cv.Cin_pad = Cin_pad; cv.ksize = ks; cv.stride = stride; cv.fold = fold;
-        const int taps = (fold - 1) * stride + ks;
-        cv.Kpad = ((taps * Cin_pad + 63) / 64) * 64;
+        std::vector<float> Wf;
+        cv.Kpad = actor_tc_fold_weights(it->second.data(), Cout, Cin, Cin_pad, ks, stride, fold, Wf);
         const int N = fold * Cout;
-        std::vector<__half> W((size_t)N * 2 * cv.Kpad, __float2half(0.f));
-        for (int u = 0; u < fold; ++u)
-            for (int o = 0; o < Cout; ++o)
-                for (int i = 0; i < Cin; ++i)
-                    for (int k = 0; k < ks; ++k) {
-                        const float w = it->second[((size_t)o * Cin + i) * ks + k];
-                        const __half h = __float2half_rn(w);
-                        const size_t kk = (size_t)(u * stride + k) * Cin_pad + i, n = (size_t)u * Cout + o;
-                        W[n * 2 * cv.Kpad + kk] = h;
-                        W[n * 2 * cv.Kpad + cv.Kpad + kk] = __float2half_rn(w - __half2float(h));
-                    }
+        std::vector<__half> W((size_t)N * 2 * cv.Kpad);
+        for (int n = 0; n < N; ++n)
+            for (int kk = 0; kk < cv.Kpad; ++kk) {
+                const float w = Wf[(size_t)n * cv.Kpad + kk];
+                const __half h = __float2half_rn(w);
+                W[(size_t)n * 2 * cv.Kpad + kk] = h;
+                W[(size_t)n * 2 * cv.Kpad + cv.Kpad + kk] = __float2half_rn(w - __half2float(h));
+            }
         if (cudaMalloc(&cv.W, W.size() * sizeof(__half)) != cudaSuccess) return "actor_tc_pack: cudaMalloc failed";
         cudaMemcpy(cv.W, W.data(), W.size() * sizeof(__half), cudaMemcpyHostToDevice);
         if (const char* e = tcg_encode_w(cv.wmap, cv.W, 2 * cv.Kpad, N, N)) return e;

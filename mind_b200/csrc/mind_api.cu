@@ -1236,6 +1236,19 @@ extern "C" int mind_debug_edge_init_pack(const float* W, const float* b, const f
     return 0;
 }
 
+extern "C" int mind_debug_conv_fold_pack(const float* w, int32_t Cout, int32_t Cin, int32_t Cin_pad, int32_t ksize, int32_t stride,
+                                         int32_t fold, float* out, int64_t capacity) {
+    if (!w || !out || Cout <= 0 || Cin <= 0 || Cin_pad < Cin || (ksize != 1 && ksize != 3) || stride <= 0 || fold <= 0) {
+        fail("mind_debug_conv_fold_pack: bad argument");
+        return -1;
+    }
+    std::vector<float> Wf;
+    const int Kpad = actor_tc_fold_weights(w, Cout, Cin, Cin_pad, ksize, stride, fold, Wf);
+    if ((int64_t)Wf.size() > capacity) { fail("mind_debug_conv_fold_pack: capacity %lld < %zu", (long long)capacity, Wf.size()); return -1; }
+    memcpy(out, Wf.data(), Wf.size() * sizeof(float));
+    return Kpad;
+}
+
 extern "C" int mind_debug_fusion_schedule(const int32_t* n_tokens, int32_t B, int32_t sm_count, int32_t* work_out,
                                           int32_t capacity, int32_t* info) {
     if (!n_tokens || B <= 0 || sm_count <= 0 || !info) return fail("mind_debug_fusion_schedule: bad argument");

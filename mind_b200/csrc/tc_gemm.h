@@ -71,6 +71,7 @@ struct ActorTc {
 const char* actor_tc_pack(ActorTc& a, const std::map<std::string, std::vector<float>>& host,
                           const std::map<std::string, const float*>& dev);
 void actor_tc_free(ActorTc& a);
+int actor_tc_fold_weights(const float* w, int Cout, int Cin, int Cin_pad, int ks, int stride, int fold, std::vector<float>& out);   // -> Kpad
 int64_t actor_tc_ws_bytes(int A);
 // actors [A,14,48] fp32 -> out [A,128]
 const char* actor_tc_run(ActorTc& a, const float* actors, int A, void* ws, float* out, int sm_count, cudaStream_t st);

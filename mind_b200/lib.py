@@ -66,7 +66,7 @@ class MindTreeUpdate(C.Structure):
 # every symbol include/mind_b200.h declares (tests check that all of them are exported)
 SYMBOLS = ["mind_create", "mind_destroy", "mind_last_error", "mind_build_info", "mind_set_weight",
            "mind_finalize_weights", "mind_set_option", "mind_workspace_bytes", "mind_workspace_bytes_batch", "mind_forward",
-           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_debug_edge_init_pack", "mind_sync_check", "mind_profile_read",
+           "mind_upload_packed_bytes", "mind_upload_packed", "mind_debug_tap", "mind_launch_count", "mind_graph_replays", "mind_tc_selftest", "mind_debug_fusion_schedule", "mind_debug_edge_init_pack", "mind_debug_conv_fold_pack", "mind_sync_check", "mind_profile_read",
            "mind_tree_level", "mind_tree_update", "mind_tree_last_error", "mind_cost_fields", "mind_cost_fields_last_error", "mind_ilqr_tree_solve", "mind_ilqr_last_error", "mind_debug_field_eval"]
 
 _lib = None
@@ -119,6 +119,8 @@ def load(build_if_missing: bool = True):
     lib.mind_debug_fusion_schedule.restype = C.c_int
     lib.mind_debug_edge_init_pack.argtypes = [C.POINTER(C.c_float)] * 6
     lib.mind_debug_edge_init_pack.restype = C.c_int
+    lib.mind_debug_conv_fold_pack.argtypes = [C.POINTER(C.c_float)] + [C.c_int32] * 6 + [C.POINTER(C.c_float), C.c_int64]
+    lib.mind_debug_conv_fold_pack.restype = C.c_int
     lib.mind_sync_check.argtypes = [C.c_void_p]
     lib.mind_sync_check.restype = C.c_int
     lib.mind_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
